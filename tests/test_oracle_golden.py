@@ -1,0 +1,74 @@
+"""CPU: pin the oracle against the reference's golden vector and against the
+vectors the unmodified reference produced over shims (tests/golden)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import distmat_restated as O
+from oracle import rmsd_restated as R
+from oracle.xyz_min import read_xyz
+
+
+def _run(golden_dir, ds, args, **kw):
+    atoms, coords = read_xyz(os.path.join(golden_dir, ds["trajfile"]))
+    noh, do_reorder, rs, ns, ws, excl, fk = args
+    return O.build_distance_matrix(
+        atoms, coords, noh=noh, reorder=R.reorder_hungarian if do_reorder else None,
+        reorder_solvent_only=rs, nsatoms=ns, weight_solute=ws,
+        reorderexcl=np.asarray(excl, np.int32), final_kabsch=fk, **kw)
+
+
+def test_reference_golden_vector_bit_exact(golden_dir, reference_vectors, ref_golden_distmat):
+    """test/test_distmat.py:7-16 pins this config at abs 1e-8; the oracle is bit-exact."""
+    ds = reference_vectors["testtraj"]
+    got = _run(golden_dir, ds, ds["modes"]["noh_ns17"]["args"])
+    assert got.shape == (3,)
+    assert np.array_equal(got, ref_golden_distmat)
+
+
+@pytest.mark.parametrize("dataset", ["testtraj", "synth_solv", "synth_plain"])
+def test_oracle_matches_unmodified_reference(golden_dir, reference_vectors, dataset):
+    ds = reference_vectors[dataset]
+    for name, mode in ds["modes"].items():
+        got = _run(golden_dir, ds, mode["args"])
+        assert got.shape == mode["values"].shape, name
+        assert np.abs(got - mode["values"]).max() <= 1e-12, name
+
+
+def test_oracle_pool_path(golden_dir, reference_vectors, ref_golden_distmat):
+    """distmat.py:73-76 process-pool path (test/test_distmat.py:70-75)."""
+    ds = reference_vectors["testtraj"]
+    got = _run(golden_dir, ds, ds["modes"]["noh_ns17"]["args"], n_workers=2)
+    assert np.array_equal(got, ref_golden_distmat)
+    pool = np.array([float.fromhex(h) for h in ds["pool_noh_ns17_hex"]])
+    assert np.array_equal(pool, ref_golden_distmat)
+
+
+def test_closed_form_is_the_no_reorder_value(golden_dir, reference_vectors):
+    """SURVEY §8a closed forms: the GPU epilogue's specification."""
+    atoms, coords = read_xyz(os.path.join(golden_dir, "ref_testtraj.xyz"))
+    z = atoms[0]
+    for name, keep, ncen in (("plain", z > 0, None), ("noh", z != 1, None),
+                             ("ns17", z > 0, 17), ("noh_ns17", z != 1, 7)):
+        want = reference_vectors["testtraj"]["modes"][name]["values"]
+        got = []
+        for i in range(3):
+            for j in range(i + 1, 3):
+                Q = coords[i][keep].copy()
+                P = coords[j][keep].copy()
+                Q -= Q[:ncen].mean(axis=0)
+                P -= P[:ncen].mean(axis=0)
+                got.append(O.closed_form_kabsch_rmsd(P, Q))
+        assert np.abs(np.array(got) - want).max() < 1e-12, name
+
+
+def test_linkage_labels_config1(reference_vectors):
+    """BASELINE config 1: plain, -rmsd 1.0, average linkage -> labels [1 2 3]."""
+    import scipy.cluster.hierarchy as hcl
+
+    vec = reference_vectors["testtraj"]["modes"]["plain"]["values"]
+    Z = hcl.linkage(vec, "average")
+    assert list(hcl.fcluster(Z, 1.0, criterion="distance")) == [1, 2, 3]
+    assert Z[0, 2] == pytest.approx(3.4161225575825, abs=1e-12)
+    assert Z[1, 2] == pytest.approx(4.419679587281052, abs=1e-12)
