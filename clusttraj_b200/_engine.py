@@ -1,0 +1,201 @@
+"""ctypes binding of the C ABI in include/clusttraj_b200.h — the only way the Python side reaches the
+GPU.  There is no CPU implementation behind it: a missing library or a missing device raises."""
+import ctypes as C
+import os
+import threading
+import weakref
+
+import numpy as np
+
+from . import _build
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class ct_opts(C.Structure):
+    _fields_ = [
+        ("no_hydrogen", C.c_int32),
+        ("solute_natoms", C.c_int32),
+        ("reorder_mode", C.c_int32),
+        ("reorder_solvent_only", C.c_int32),
+        ("final_kabsch", C.c_int32),
+        ("n_excl", C.c_int32),
+        ("weight_solute", C.c_double),
+        ("reorder_excl", C.POINTER(C.c_int32)),
+    ]
+
+
+class ct_stats(C.Structure):
+    _fields_ = [
+        ("pack_ms", C.c_double), ("h2d_ms", C.c_double), ("kernel_ms", C.c_double), ("gram_ms", C.c_double),
+        ("pair_ms", C.c_double), ("d2h_ms", C.c_double), ("total_ms", C.c_double),
+        ("pairs", C.c_int64), ("flagged", C.c_int64), ("launches", C.c_int64), ("kept_atoms", C.c_int64),
+        ("lsap_steps", C.c_int64),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+EXPORTS = [
+    "ct_version", "ct_device_count", "ct_last_error", "ct_engine_create", "ct_engine_destroy", "ct_host_alloc",
+    "ct_host_free", "ct_load_frames", "ct_rows_pairs", "ct_rmsd_rows", "ct_rmsd_rows_device", "ct_copy_slab",
+    "ct_rmsd_condensed", "ct_pair_values", "ct_get_stats",
+]
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+def load_library(build_if_missing=True):
+    """dlopen the in-tree engine (building it with nvcc first when it is missing or stale)."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        path = _build.LIB
+        if build_if_missing and _build.is_stale():
+            try:
+                _build.build()
+            except Exception as exc:  # a prebuilt .so that merely looks stale is still usable
+                if not os.path.exists(path):
+                    raise EngineError(f"clusttraj_b200: CUDA engine is not built and cannot be built: {exc}") from exc
+        if not os.path.exists(path):
+            raise EngineError("clusttraj_b200: CUDA engine library missing (run `python -m clusttraj_b200._build`)")
+        lib = C.CDLL(path)
+        P = C.POINTER
+        lib.ct_version.restype = C.c_char_p
+        lib.ct_device_count.restype = C.c_int
+        lib.ct_last_error.restype = C.c_char_p
+        lib.ct_last_error.argtypes = [C.c_void_p]
+        lib.ct_engine_create.argtypes = [C.c_int, P(C.c_void_p)]
+        lib.ct_engine_destroy.argtypes = [C.c_void_p]
+        lib.ct_engine_destroy.restype = None
+        lib.ct_host_alloc.argtypes = [P(C.c_void_p), C.c_uint64]
+        lib.ct_host_free.argtypes = [C.c_void_p]
+        lib.ct_load_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, P(ct_opts)]
+        lib.ct_rows_pairs.argtypes = [C.c_int64, C.c_int64, C.c_int64]
+        lib.ct_rows_pairs.restype = C.c_int64
+        lib.ct_rmsd_rows.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, P(ct_stats)]
+        lib.ct_rmsd_rows_device.argtypes = [C.c_void_p, C.c_int64, C.c_int64, P(C.c_void_p), P(ct_stats)]
+        lib.ct_copy_slab.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
+        lib.ct_rmsd_condensed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, P(ct_opts),
+                                          C.c_void_p, P(ct_stats)]
+        lib.ct_pair_values.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, P(ct_stats)]
+        lib.ct_get_stats.argtypes = [C.c_void_p, P(ct_stats)]
+        _lib = lib
+        return lib
+
+
+def device_count():
+    return int(load_library().ct_device_count())
+
+
+def pinned_empty(n, dtype=np.float64):
+    """A writable C-contiguous ndarray over page-locked host memory (freed when the array dies)."""
+    lib = load_library()
+    dtype = np.dtype(dtype)
+    nbytes = max(int(n) * dtype.itemsize, 1)
+    ptr = C.c_void_p()
+    rc = lib.ct_host_alloc(C.byref(ptr), nbytes)
+    if rc != 0:
+        raise EngineError("ct_host_alloc failed: " + (lib.ct_last_error(None) or b"").decode())
+    buf = (C.c_char * nbytes).from_address(ptr.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(n))
+    weakref.finalize(buf, lib.ct_host_free, ptr.value)
+    return arr
+
+
+def make_opts(no_hydrogen=False, solute_natoms=None, reorder=False, reorder_solvent_only=False, final_kabsch=False,
+              weight_solute=None, reorder_excl=()):
+    excl = np.ascontiguousarray(np.asarray(reorder_excl, dtype=np.int32).ravel())
+    o = ct_opts()
+    o.no_hydrogen = 1 if no_hydrogen else 0
+    o.solute_natoms = int(solute_natoms) if solute_natoms else 0
+    o.reorder_mode = 1 if reorder else 0
+    o.reorder_solvent_only = 1 if reorder_solvent_only else 0
+    o.final_kabsch = 1 if final_kabsch else 0
+    o.weight_solute = float(weight_solute) if weight_solute else 0.0
+    o.n_excl = int(excl.size)
+    o.reorder_excl = excl.ctypes.data_as(C.POINTER(C.c_int32)) if excl.size else None
+    o._keepalive = excl
+    return o
+
+
+class Engine:
+    """One engine = one GPU.  Not re-entrant: use one host thread per engine."""
+
+    def __init__(self, device=0):
+        self._lib = load_library()
+        h = C.c_void_p()
+        rc = self._lib.ct_engine_create(int(device), C.byref(h))
+        if rc != 0:
+            raise EngineError("ct_engine_create failed: " + (self._lib.ct_last_error(None) or b"").decode())
+        self._h = h
+        self.device = int(device)
+        self.M = 0
+        self.N = 0
+        self.K = 0
+        self._finalizer = weakref.finalize(self, self._lib.ct_engine_destroy, h)
+
+    def close(self):
+        self._finalizer()
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise EngineError(f"{what} failed ({rc}): " + (self._lib.ct_last_error(self._h) or b"").decode())
+
+    def load_frames(self, coords, atomic_nums, opts):
+        coords = np.ascontiguousarray(coords, dtype=np.float64)
+        if coords.ndim != 3 or coords.shape[2] != 3:
+            raise ValueError("coords must be [M, N, 3]")
+        z = np.ascontiguousarray(atomic_nums, dtype=np.int32)
+        if z.shape != (coords.shape[1],):
+            raise ValueError("atomic_nums must be [N] (frame-invariant)")
+        self._check(self._lib.ct_load_frames(self._h, coords.ctypes.data, z.ctypes.data, coords.shape[0],
+                                             coords.shape[1], C.byref(opts)), "ct_load_frames")
+        self.M, self.N = coords.shape[0], coords.shape[1]
+        self.K = int(self.stats()["kept_atoms"])
+
+    def rows_pairs(self, row_begin, row_end):
+        return int(self._lib.ct_rows_pairs(self.M, row_begin, row_end))
+
+    def rmsd_rows(self, row_begin, row_end, out=None):
+        n = self.rows_pairs(row_begin, row_end)
+        if out is None:
+            out = np.empty(n, dtype=np.float64)
+        if out.dtype != np.float64 or not out.flags.c_contiguous or out.size < n:
+            raise ValueError("out must be a C-contiguous float64 array with room for the slab")
+        st = ct_stats()
+        self._check(self._lib.ct_rmsd_rows(self._h, row_begin, row_end, out.ctypes.data, C.byref(st)), "ct_rmsd_rows")
+        return out[:n], st.as_dict()
+
+    def rmsd_rows_device(self, row_begin, row_end):
+        """Leaves the slab on the GPU; returns (device pointer, entries, stats)."""
+        st = ct_stats()
+        ptr = C.c_void_p()
+        self._check(self._lib.ct_rmsd_rows_device(self._h, row_begin, row_end, C.byref(ptr), C.byref(st)),
+                    "ct_rmsd_rows_device")
+        return ptr.value, self.rows_pairs(row_begin, row_end), st.as_dict()
+
+    def copy_slab(self, offset, count, out=None):
+        if out is None:
+            out = np.empty(count, dtype=np.float64)
+        self._check(self._lib.ct_copy_slab(self._h, offset, count, out.ctypes.data), "ct_copy_slab")
+        return out
+
+    def pair_values(self, pairs, want_perms=False):
+        pairs = np.ascontiguousarray(pairs, dtype=np.int64).reshape(-1, 2)
+        vals = np.empty(len(pairs), dtype=np.float64)
+        perms = np.empty((len(pairs), self.K), dtype=np.int32) if want_perms else None
+        st = ct_stats()
+        self._check(self._lib.ct_pair_values(self._h, pairs.ctypes.data, len(pairs), vals.ctypes.data,
+                                             perms.ctypes.data if want_perms else None, C.byref(st)), "ct_pair_values")
+        return (vals, perms, st.as_dict()) if want_perms else (vals, st.as_dict())
+
+    def stats(self):
+        st = ct_stats()
+        self._lib.ct_get_stats(self._h, C.byref(st))
+        return st.as_dict()

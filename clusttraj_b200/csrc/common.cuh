@@ -1,0 +1,90 @@
+// Shared declarations of the clusttraj_b200 CUDA engine (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ct {
+
+// ---- packed ("tile-major") layout read by the Gram kernel --------------------------------------
+// packed[tile][kq][c][f][a]  (float64)   tile = frame / 32, f = frame % 32, kq = atom / 4, a = atom % 4,
+// c = x,y,z.  One (tile, kq, c) block is 32 frames x 4 atoms = 1 KiB and is exactly the pair of
+// operand fragments four m8n8k4 DMMAs read (lane l <-> frame l/4, atom l%4), so fragment loads are one
+// conflict-free 256 B LDS.64 per warp, and one pipeline stage of a tile (KC atoms) is ONE contiguous
+// 6 KiB run in HBM that a single cp.async.bulk (TMA) moves.
+constexpr int FT = 32;                                   // frames per packed tile
+constexpr int KC = 8;                                    // atoms per pipeline stage
+constexpr int KQ_STAGE = KC / 4;                         // k4 groups per stage
+constexpr int TILE_STAGE_DOUBLES = KQ_STAGE * 3 * FT * 4;  // 768
+constexpr int TILE_STAGE_BYTES = TILE_STAGE_DOUBLES * 8;   // 6144
+
+struct FixList {
+    int2* pairs;            // flagged (i, j)
+    unsigned int* count;    // tickets handed out in the current chunk (may exceed capacity)
+    unsigned int capacity;
+};
+
+struct GramParams {
+    const double* packed;   // tile-major centred coordinates
+    const double* G;        // per-frame sum of squares, padded to whole tiles
+    double* out;            // condensed slab; element idx(i,j) lives at out[idx(i,j) - idx_base]
+    long long idx_base;
+    int M;                  // frames
+    int kq_total;           // padded atoms / 4
+    int n_stage;            // pipeline stages per tile = padded atoms / KC
+    int row_begin, row_end; // rows of the matrix to produce
+    double inv_k;           // 1 / kept atoms
+    double flag_rel;        // pairs with E < flag_rel * (G_i + G_j) are re-done by the explicit path
+    FixList fix;
+};
+
+__host__ __device__ __forceinline__ long long condensed_row_base(long long M, long long i) {
+    // index of (i, i+1) in SciPy's condensed order (clusttraj/distmat.py:78 flattens rows in order)
+    return M * i - (i * (i + 1)) / 2;
+}
+
+// ---- mbarrier / bulk-copy (TMA) PTX ----------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace ct

@@ -1,0 +1,446 @@
+// C ABI of the engine (include/clusttraj_b200.h): device buffers, mode dispatch, and the chunked
+// compute / device->host streaming pipeline.  No CPU fallback anywhere: every entry point either runs
+// the CUDA kernels or returns an error.
+#include "../../include/clusttraj_b200.h"
+#include "common.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace ct {
+cudaError_t launch_pack(const double* raw, const int* keep, int M, int N, int K, int ncen, int m_pad, int kq_total,
+                        double* centred, double* G, double* packed, int sm_count, cudaStream_t stream);
+cudaError_t launch_gram(const GramParams& p, int variant, int sm_count, cudaStream_t stream);
+int gram_row_align(int variant);
+cudaError_t launch_fixup(const double* centred, int M, int K, const FixList& fix, double* out, long long idx_base,
+                         long long n_entries, unsigned long long* flagged_total, int sm_count, cudaStream_t stream);
+struct PairPlan;
+struct PairPlanHost;
+int pair_plan_build(PairPlanHost** out, const int32_t* kept_z, int K, int natoms, const ct_opts* o, std::string& err);
+void pair_plan_free(PairPlanHost* p);
+cudaError_t launch_pairs_rows(const PairPlanHost* plan, const double* centred, int M, int K, int row_begin, int row_end,
+                              double* out, long long idx_base, unsigned long long* counters, int sm_count,
+                              cudaStream_t stream);
+cudaError_t launch_pairs_list(const PairPlanHost* plan, const double* centred, int M, int K, const long long* pairs_dev,
+                              long long n_pairs, double* values_dev, int* perms_dev, unsigned long long* counters,
+                              int sm_count, cudaStream_t stream);
+}  // namespace ct
+
+struct ct_engine {
+    int device = 0;
+    int sm_count = 0;
+    std::string err;
+    cudaStream_t s_compute = nullptr, s_copy = nullptr;
+    // frames
+    int64_t M = 0;
+    int N = 0, K = 0, natoms = 0, m_pad = 0, kq_total = 0;
+    bool loaded = false;
+    bool use_gram = false;  // pure Kabsch modes go through the DMMA Gram kernel
+    ct_opts opts{};
+    std::vector<int32_t> excl;
+    double* d_raw = nullptr; size_t raw_cap = 0;
+    int* d_keep = nullptr; size_t keep_cap = 0;
+    double* d_centred = nullptr; size_t centred_cap = 0;
+    double* d_G = nullptr; size_t g_cap = 0;
+    double* d_packed = nullptr; size_t packed_cap = 0;
+    ct::PairPlanHost* plan = nullptr;
+    // outputs
+    double* d_slab = nullptr; size_t slab_cap = 0;       // whole-slab device buffer (rows_device)
+    double* d_chunk[2] = {nullptr, nullptr}; size_t chunk_cap = 0;  // streaming double buffer
+    int2* d_fix_pairs = nullptr; unsigned int* d_fix_count = nullptr; unsigned int fix_cap = 1u << 20;
+    unsigned long long* d_counters = nullptr;  // [0] flagged pairs, [1] lsap steps
+    cudaEvent_t ev_chunk_done[2] = {nullptr, nullptr}, ev_copy_done[2] = {nullptr, nullptr};
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
+    ct_stats stats{};
+    int gram_variant = 0;
+    size_t chunk_entries = (size_t)32 << 20;  // 256 MiB of float64 per streaming chunk
+    double flag_rel = 1e-9;
+};
+
+static thread_local std::string g_err;
+
+#define CT_CUDA(e, call)                                                                                   \
+    do {                                                                                                    \
+        cudaError_t _c = (call);                                                                            \
+        if (_c != cudaSuccess) {                                                                            \
+            char _b[512];                                                                                   \
+            snprintf(_b, sizeof _b, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_c), __FILE__, __LINE__); \
+            if (e) (e)->err = _b; else g_err = _b;                                                          \
+            return CT_ERR_CUDA;                                                                             \
+        }                                                                                                   \
+    } while (0)
+
+static int fail(ct_engine* e, int code, const std::string& msg) {
+    if (e) e->err = msg; else g_err = msg;
+    return code;
+}
+
+template <class T>
+static int ensure(ct_engine* e, T*& ptr, size_t& cap, size_t need) {
+    if (need <= cap && ptr) return CT_OK;
+    if (ptr) { CT_CUDA(e, cudaFree(ptr)); ptr = nullptr; cap = 0; }
+    CT_CUDA(e, cudaMalloc(&ptr, need * sizeof(T)));
+    cap = need;
+    return CT_OK;
+}
+
+extern "C" {
+
+const char* ct_version(void) { return "clusttraj_b200 0.1 (sm_100a)"; }
+
+int ct_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+const char* ct_last_error(const ct_engine* e) { return e ? e->err.c_str() : g_err.c_str(); }
+
+int ct_engine_create(int device, ct_engine** out) {
+    if (!out) return fail(nullptr, CT_ERR_ARG, "ct_engine_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t c = cudaGetDeviceCount(&n);
+    if (c != cudaSuccess || n == 0)
+        return fail(nullptr, CT_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(c) +
+                                              " (clusttraj_b200 has no CPU fallback)");
+    if (device < 0 || device >= n) return fail(nullptr, CT_ERR_ARG, "ct_engine_create: bad device ordinal");
+    ct_engine* e = new ct_engine();
+    e->device = device;
+    CT_CUDA((ct_engine*)nullptr, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CT_CUDA((ct_engine*)nullptr, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        delete e;
+        return fail(nullptr, CT_ERR_UNSUPPORTED, "clusttraj_b200 kernels are built for sm_100a (B200) only");
+    }
+    e->sm_count = prop.multiProcessorCount;
+    CT_CUDA((ct_engine*)nullptr, cudaStreamCreateWithFlags(&e->s_compute, cudaStreamNonBlocking));
+    CT_CUDA((ct_engine*)nullptr, cudaStreamCreateWithFlags(&e->s_copy, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+        CT_CUDA((ct_engine*)nullptr, cudaEventCreateWithFlags(&e->ev_chunk_done[k], cudaEventDisableTiming));
+        CT_CUDA((ct_engine*)nullptr, cudaEventCreateWithFlags(&e->ev_copy_done[k], cudaEventDisableTiming));
+    }
+    CT_CUDA((ct_engine*)nullptr, cudaEventCreate(&e->ev_a));
+    CT_CUDA((ct_engine*)nullptr, cudaEventCreate(&e->ev_b));
+    CT_CUDA((ct_engine*)nullptr, cudaEventCreate(&e->ev_c));
+    CT_CUDA((ct_engine*)nullptr, cudaEventCreate(&e->ev_d));
+    CT_CUDA((ct_engine*)nullptr, cudaMalloc(&e->d_fix_pairs, sizeof(int2) * e->fix_cap));
+    CT_CUDA((ct_engine*)nullptr, cudaMalloc(&e->d_fix_count, sizeof(unsigned int)));
+    CT_CUDA((ct_engine*)nullptr, cudaMalloc(&e->d_counters, sizeof(unsigned long long) * 4));
+    const char* v = getenv("CLUSTTRAJ_B200_GRAM_VARIANT");
+    if (v) e->gram_variant = atoi(v);
+    const char* ce = getenv("CLUSTTRAJ_B200_CHUNK_ENTRIES");
+    if (ce && atoll(ce) > 0) e->chunk_entries = (size_t)atoll(ce);
+    const char* fc = getenv("CLUSTTRAJ_B200_FIX_CAPACITY");  // test hook: force the list-overflow path
+    if (fc && atoll(fc) > 0 && (unsigned long long)atoll(fc) < e->fix_cap) e->fix_cap = (unsigned int)atoll(fc);
+    *out = e;
+    return CT_OK;
+}
+
+void ct_engine_destroy(ct_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    cudaFree(e->d_raw); cudaFree(e->d_keep); cudaFree(e->d_centred); cudaFree(e->d_G); cudaFree(e->d_packed);
+    cudaFree(e->d_slab); cudaFree(e->d_chunk[0]); cudaFree(e->d_chunk[1]);
+    cudaFree(e->d_fix_pairs); cudaFree(e->d_fix_count); cudaFree(e->d_counters);
+    for (int k = 0; k < 2; ++k) { cudaEventDestroy(e->ev_chunk_done[k]); cudaEventDestroy(e->ev_copy_done[k]); }
+    cudaEventDestroy(e->ev_a); cudaEventDestroy(e->ev_b); cudaEventDestroy(e->ev_c); cudaEventDestroy(e->ev_d);
+    cudaStreamDestroy(e->s_compute); cudaStreamDestroy(e->s_copy);
+    if (e->plan) ct::pair_plan_free(e->plan);
+    delete e;
+}
+
+int ct_host_alloc(void** ptr, uint64_t bytes) {
+    if (!ptr) return fail(nullptr, CT_ERR_ARG, "ct_host_alloc: ptr is NULL");
+    CT_CUDA((ct_engine*)nullptr, cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable));
+    return CT_OK;
+}
+
+int ct_host_free(void* ptr) {
+    if (ptr) CT_CUDA((ct_engine*)nullptr, cudaFreeHost(ptr));
+    return CT_OK;
+}
+
+int64_t ct_rows_pairs(int64_t M, int64_t row_begin, int64_t row_end) {
+    if (M < 2) return 0;
+    if (row_begin < 0) row_begin = 0;
+    if (row_end > M) row_end = M;
+    if (row_end <= row_begin) return 0;
+    const int64_t last = std::min<int64_t>(row_end, M - 1);
+    if (last <= row_begin) return 0;
+    return ct::condensed_row_base(M, last) - ct::condensed_row_base(M, row_begin);
+}
+
+int ct_load_frames(ct_engine* e, const double* coords, const int32_t* atomic_nums, int64_t M, int32_t N,
+                   const ct_opts* opts) {
+    if (!e) return fail(nullptr, CT_ERR_ARG, "ct_load_frames: engine is NULL");
+    if (!coords || !atomic_nums || !opts) return fail(e, CT_ERR_ARG, "ct_load_frames: NULL argument");
+    if (M < 1 || N < 1) return fail(e, CT_ERR_ARG, "ct_load_frames: need M >= 1 frames and N >= 1 atoms");
+    if (M > (int64_t)1 << 30) return fail(e, CT_ERR_ARG, "ct_load_frames: too many frames");
+    if (opts->n_excl < 0 || (opts->n_excl > 0 && !opts->reorder_excl))
+        return fail(e, CT_ERR_ARG, "ct_load_frames: bad reorder_excl");
+    if (opts->reorder_mode != 0 && opts->reorder_mode != 1)
+        return fail(e, CT_ERR_UNSUPPORTED, "only reorder_mode 0 (none) and 1 (hungarian) are implemented");
+    if (opts->solute_natoms < 0 || opts->solute_natoms > N)
+        return fail(e, CT_ERR_ARG, "ct_load_frames: solute_natoms out of range");
+    CT_CUDA(e, cudaSetDevice(e->device));
+    e->loaded = false;
+    e->opts = *opts;
+    e->excl.assign(opts->reorder_excl, opts->reorder_excl + opts->n_excl);
+    e->opts.reorder_excl = e->excl.data();
+
+    // kept atoms and the centring window (distmat.py:116-118, 134-165)
+    std::vector<int> keep;
+    std::vector<int32_t> kept_z;
+    for (int k = 0; k < N; ++k)
+        if (!opts->no_hydrogen || atomic_nums[k] != 1) { keep.push_back(k); kept_z.push_back(atomic_nums[k]); }
+    const int K = (int)keep.size();
+    if (K == 0) return fail(e, CT_ERR_ARG, "ct_load_frames: the hydrogen mask leaves no atoms");
+    int natoms = opts->solute_natoms;
+    if (opts->no_hydrogen) {
+        natoms = 0;
+        for (int k = 0; k < opts->solute_natoms; ++k) natoms += atomic_nums[k] != 1;
+    }
+    if (opts->solute_natoms && natoms == 0) return fail(e, CT_ERR_ARG, "ct_load_frames: the solute has no kept atoms");
+    for (int32_t x : e->excl)
+        if (x < 0 || x >= K) return fail(e, CT_ERR_ARG, "ct_load_frames: reorder_excl entry outside the kept atoms");
+    const int ncen = opts->solute_natoms ? natoms : K;
+    // Pure Kabsch value (dispatch rows 1-2 of SURVEY §8a): no reorder and no solute weighting.
+    e->use_gram = (opts->reorder_mode == 0) && !(opts->solute_natoms && opts->weight_solute != 0.0);
+    if (!opts->solute_natoms && opts->weight_solute != 0.0)
+        return fail(e, CT_ERR_UNSUPPORTED, "weight_solute without solute_natoms divides by zero in the reference");
+
+    e->M = M; e->N = N; e->K = K; e->natoms = natoms;
+    e->m_pad = (int)((M + 63) / 64 * 64);
+    const int k_pad = (K + ct::KC - 1) / ct::KC * ct::KC;
+    e->kq_total = k_pad / 4;
+
+    int rc;
+    if ((rc = ensure(e, e->d_raw, e->raw_cap, (size_t)M * N * 3))) return rc;
+    if ((rc = ensure(e, e->d_keep, e->keep_cap, (size_t)K))) return rc;
+    if ((rc = ensure(e, e->d_centred, e->centred_cap, (size_t)M * K * 3))) return rc;
+    if ((rc = ensure(e, e->d_G, e->g_cap, (size_t)e->m_pad))) return rc;
+    if (e->use_gram)
+        if ((rc = ensure(e, e->d_packed, e->packed_cap, (size_t)e->m_pad * k_pad * 3))) return rc;
+
+    CT_CUDA(e, cudaEventRecord(e->ev_a, e->s_compute));
+    CT_CUDA(e, cudaMemcpyAsync(e->d_raw, coords, sizeof(double) * (size_t)M * N * 3, cudaMemcpyHostToDevice, e->s_compute));
+    CT_CUDA(e, cudaMemcpyAsync(e->d_keep, keep.data(), sizeof(int) * (size_t)K, cudaMemcpyHostToDevice, e->s_compute));
+    CT_CUDA(e, cudaEventRecord(e->ev_b, e->s_compute));
+    CT_CUDA(e, ct::launch_pack(e->d_raw, e->d_keep, (int)M, N, K, ncen, e->m_pad, e->kq_total, e->d_centred, e->d_G,
+                               e->use_gram ? e->d_packed : nullptr, e->sm_count, e->s_compute));
+    CT_CUDA(e, cudaEventRecord(e->ev_c, e->s_compute));
+    CT_CUDA(e, cudaStreamSynchronize(e->s_compute));  // `keep` (host vector) must outlive the copy
+    float ms = 0.f;
+    CT_CUDA(e, cudaEventElapsedTime(&ms, e->ev_a, e->ev_b)); e->stats.h2d_ms = ms;
+    CT_CUDA(e, cudaEventElapsedTime(&ms, e->ev_b, e->ev_c)); e->stats.pack_ms = ms;
+    e->stats.kept_atoms = K;
+
+    if (e->plan) { ct::pair_plan_free(e->plan); e->plan = nullptr; }
+    {
+        std::string perr;
+        rc = ct::pair_plan_build(&e->plan, kept_z.data(), K, natoms, &e->opts, perr);
+        if (rc) return fail(e, rc, perr);
+    }
+    e->loaded = true;
+    return CT_OK;
+}
+
+// One chunk of rows into `dst` (device), asynchronously on s_compute.
+static int compute_rows_async(ct_engine* e, int row_begin, int row_end, double* dst, long long idx_base,
+                              long long n_entries, int64_t* launches) {
+    if (e->use_gram) {
+        CT_CUDA(e, cudaMemsetAsync(e->d_fix_count, 0, sizeof(unsigned int), e->s_compute));
+        ct::GramParams p;
+        p.packed = e->d_packed; p.G = e->d_G; p.out = dst; p.idx_base = idx_base; p.M = (int)e->M;
+        p.kq_total = e->kq_total; p.n_stage = e->kq_total / ct::KQ_STAGE;
+        p.row_begin = row_begin; p.row_end = row_end;
+        p.inv_k = 1.0 / (double)e->K; p.flag_rel = e->flag_rel;
+        p.fix.pairs = e->d_fix_pairs; p.fix.count = e->d_fix_count; p.fix.capacity = e->fix_cap;
+        CT_CUDA(e, ct::launch_gram(p, e->gram_variant, e->sm_count, e->s_compute));
+        CT_CUDA(e, ct::launch_fixup(e->d_centred, (int)e->M, e->K, p.fix, dst, idx_base, n_entries, e->d_counters,
+                                    e->sm_count, e->s_compute));
+        *launches += 2;
+    } else {
+        CT_CUDA(e, ct::launch_pairs_rows(e->plan, e->d_centred, (int)e->M, e->K, row_begin, row_end, dst, idx_base,
+                                         e->d_counters, e->sm_count, e->s_compute));
+        *launches += 1;
+    }
+    return CT_OK;
+}
+
+static int check_rows(ct_engine* e, int64_t& row_begin, int64_t& row_end) {
+    if (!e) return fail(nullptr, CT_ERR_ARG, "engine is NULL");
+    if (!e->loaded) return fail(e, CT_ERR_STATE, "no frames loaded (call ct_load_frames first)");
+    if (row_begin < 0 || row_end > e->M || row_begin > row_end) return fail(e, CT_ERR_ARG, "bad row range");
+    return CT_OK;
+}
+
+static int finish_stats(ct_engine* e, int64_t pairs, int64_t launches) {
+    unsigned long long c[4];
+    CT_CUDA(e, cudaMemcpy(c, e->d_counters, sizeof c, cudaMemcpyDeviceToHost));
+    e->stats.pairs = pairs;
+    e->stats.launches = launches;
+    e->stats.flagged = (int64_t)c[0];
+    e->stats.lsap_steps = (int64_t)c[1];
+    return CT_OK;
+}
+
+int ct_rmsd_rows_device(ct_engine* e, int64_t row_begin, int64_t row_end, const double** out_dev, ct_stats* stats) {
+    int rc = check_rows(e, row_begin, row_end);
+    if (rc) return rc;
+    CT_CUDA(e, cudaSetDevice(e->device));
+    const int64_t n = ct_rows_pairs(e->M, row_begin, row_end);
+    if ((rc = ensure(e, e->d_slab, e->slab_cap, (size_t)std::max<int64_t>(n, 1)))) return rc;
+    CT_CUDA(e, cudaMemsetAsync(e->d_counters, 0, sizeof(unsigned long long) * 4, e->s_compute));
+    int64_t launches = 0;
+    CT_CUDA(e, cudaEventRecord(e->ev_a, e->s_compute));
+    if (n > 0) {
+        rc = compute_rows_async(e, (int)row_begin, (int)row_end, e->d_slab,
+                                ct::condensed_row_base(e->M, row_begin), n, &launches);
+        if (rc) return rc;
+    }
+    CT_CUDA(e, cudaEventRecord(e->ev_b, e->s_compute));
+    CT_CUDA(e, cudaStreamSynchronize(e->s_compute));
+    float ms = 0.f;
+    CT_CUDA(e, cudaEventElapsedTime(&ms, e->ev_a, e->ev_b));
+    e->stats.kernel_ms = ms; e->stats.total_ms = ms; e->stats.d2h_ms = 0.0;
+    e->stats.gram_ms = e->use_gram ? ms : 0.0; e->stats.pair_ms = e->use_gram ? 0.0 : ms;
+    if ((rc = finish_stats(e, n, launches))) return rc;
+    if (out_dev) *out_dev = e->d_slab;
+    if (stats) *stats = e->stats;
+    return CT_OK;
+}
+
+int ct_copy_slab(ct_engine* e, int64_t offset, int64_t count, double* out) {
+    if (!e || !out) return fail(e, CT_ERR_ARG, "ct_copy_slab: NULL argument");
+    if (offset < 0 || count < 0 || (size_t)(offset + count) > e->slab_cap) return fail(e, CT_ERR_ARG, "ct_copy_slab: range");
+    CT_CUDA(e, cudaSetDevice(e->device));
+    CT_CUDA(e, cudaMemcpy(out, e->d_slab + offset, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost));
+    return CT_OK;
+}
+
+int ct_rmsd_rows(ct_engine* e, int64_t row_begin, int64_t row_end, double* out, ct_stats* stats) {
+    int rc = check_rows(e, row_begin, row_end);
+    if (rc) return rc;
+    const int64_t n = ct_rows_pairs(e->M, row_begin, row_end);
+    if (n > 0 && !out) return fail(e, CT_ERR_ARG, "ct_rmsd_rows: out is NULL");
+    CT_CUDA(e, cudaSetDevice(e->device));
+    // Row chunks of about chunk_entries matrix entries, aligned to the Gram block height so that no
+    // block of frame pairs is computed twice; chunk c+1 is computed while chunk c streams to the host.
+    const int align = e->use_gram ? ct::gram_row_align(e->gram_variant) : 1;
+    std::vector<int64_t> cuts;
+    cuts.push_back(row_begin);
+    {
+        int64_t r = row_begin;
+        const int64_t last = std::min<int64_t>(row_end, e->M - 1);
+        while (r < last) {
+            int64_t acc = 0, r2 = r;
+            while (r2 < last && acc < (int64_t)e->chunk_entries) {
+                int64_t nxt = std::min<int64_t>(last, (r2 / align + 1) * align);
+                acc += ct_rows_pairs(e->M, r2, nxt);
+                r2 = nxt;
+            }
+            cuts.push_back(r2);
+            r = r2;
+        }
+    }
+    size_t biggest = 1;
+    for (size_t c = 0; c + 1 < cuts.size(); ++c)
+        biggest = std::max<size_t>(biggest, (size_t)ct_rows_pairs(e->M, cuts[c], cuts[c + 1]));
+    if (biggest > e->chunk_cap || !e->d_chunk[0]) {
+        for (int k = 0; k < 2; ++k) {
+            if (e->d_chunk[k]) { CT_CUDA(e, cudaFree(e->d_chunk[k])); e->d_chunk[k] = nullptr; }
+            CT_CUDA(e, cudaMalloc(&e->d_chunk[k], biggest * sizeof(double)));
+        }
+        e->chunk_cap = biggest;
+    }
+    CT_CUDA(e, cudaMemsetAsync(e->d_counters, 0, sizeof(unsigned long long) * 4, e->s_compute));
+    int64_t launches = 0;
+    CT_CUDA(e, cudaEventRecord(e->ev_a, e->s_compute));
+    int64_t written = 0;
+    for (size_t c = 0; c + 1 < cuts.size(); ++c) {
+        const int b = (int)(c & 1);
+        const int64_t cn = ct_rows_pairs(e->M, cuts[c], cuts[c + 1]);
+        if (cn == 0) continue;
+        if (c >= 2) CT_CUDA(e, cudaStreamWaitEvent(e->s_compute, e->ev_copy_done[b], 0));
+        rc = compute_rows_async(e, (int)cuts[c], (int)cuts[c + 1], e->d_chunk[b],
+                                ct::condensed_row_base(e->M, cuts[c]), cn, &launches);
+        if (rc) return rc;
+        CT_CUDA(e, cudaEventRecord(e->ev_chunk_done[b], e->s_compute));
+        CT_CUDA(e, cudaStreamWaitEvent(e->s_copy, e->ev_chunk_done[b], 0));
+        CT_CUDA(e, cudaMemcpyAsync(out + written, e->d_chunk[b], sizeof(double) * (size_t)cn, cudaMemcpyDeviceToHost,
+                                   e->s_copy));
+        CT_CUDA(e, cudaEventRecord(e->ev_copy_done[b], e->s_copy));
+        written += cn;
+    }
+    CT_CUDA(e, cudaEventRecord(e->ev_b, e->s_compute));
+    CT_CUDA(e, cudaStreamWaitEvent(e->s_compute, e->ev_copy_done[0], 0));
+    CT_CUDA(e, cudaStreamWaitEvent(e->s_compute, e->ev_copy_done[1], 0));
+    CT_CUDA(e, cudaEventRecord(e->ev_c, e->s_compute));
+    CT_CUDA(e, cudaStreamSynchronize(e->s_compute));
+    CT_CUDA(e, cudaStreamSynchronize(e->s_copy));
+    float ms = 0.f;
+    CT_CUDA(e, cudaEventElapsedTime(&ms, e->ev_a, e->ev_b));
+    e->stats.kernel_ms = ms;  // compute stream busy time (includes waits for buffer reuse)
+    e->stats.gram_ms = e->use_gram ? ms : 0.0; e->stats.pair_ms = e->use_gram ? 0.0 : ms;
+    CT_CUDA(e, cudaEventElapsedTime(&ms, e->ev_a, e->ev_c));
+    e->stats.total_ms = ms;
+    e->stats.d2h_ms = ms;
+    if ((rc = finish_stats(e, n, launches))) return rc;
+    if (stats) *stats = e->stats;
+    return CT_OK;
+}
+
+int ct_rmsd_condensed(ct_engine* e, const double* coords, const int32_t* atomic_nums, int64_t M, int32_t N,
+                      const ct_opts* opts, double* out, ct_stats* stats) {
+    int rc = ct_load_frames(e, coords, atomic_nums, M, N, opts);
+    if (rc) return rc;
+    return ct_rmsd_rows(e, 0, M, out, stats);
+}
+
+int ct_pair_values(ct_engine* e, const int64_t* pairs, int64_t n_pairs, double* values, int32_t* perms, ct_stats* stats) {
+    if (!e) return fail(nullptr, CT_ERR_ARG, "engine is NULL");
+    if (!e->loaded) return fail(e, CT_ERR_STATE, "no frames loaded (call ct_load_frames first)");
+    if (n_pairs < 0 || (n_pairs > 0 && (!pairs || !values))) return fail(e, CT_ERR_ARG, "ct_pair_values: NULL argument");
+    for (int64_t t = 0; t < n_pairs; ++t)
+        if (pairs[2 * t] < 0 || pairs[2 * t + 1] >= e->M || pairs[2 * t] >= pairs[2 * t + 1])
+            return fail(e, CT_ERR_ARG, "ct_pair_values: need 0 <= i < j < M");
+    if (n_pairs == 0) return CT_OK;
+    CT_CUDA(e, cudaSetDevice(e->device));
+    long long* d_pairs = nullptr; double* d_vals = nullptr; int* d_perms = nullptr;
+    CT_CUDA(e, cudaMalloc(&d_pairs, sizeof(long long) * 2 * (size_t)n_pairs));
+    CT_CUDA(e, cudaMalloc(&d_vals, sizeof(double) * (size_t)n_pairs));
+    if (perms) CT_CUDA(e, cudaMalloc(&d_perms, sizeof(int) * (size_t)n_pairs * e->K));
+    CT_CUDA(e, cudaMemcpy(d_pairs, pairs, sizeof(long long) * 2 * (size_t)n_pairs, cudaMemcpyHostToDevice));
+    CT_CUDA(e, cudaMemsetAsync(e->d_counters, 0, sizeof(unsigned long long) * 4, e->s_compute));
+    CT_CUDA(e, cudaEventRecord(e->ev_a, e->s_compute));
+    CT_CUDA(e, ct::launch_pairs_list(e->plan, e->d_centred, (int)e->M, e->K, d_pairs, n_pairs, d_vals, d_perms,
+                                     e->d_counters, e->sm_count, e->s_compute));
+    CT_CUDA(e, cudaEventRecord(e->ev_b, e->s_compute));
+    CT_CUDA(e, cudaStreamSynchronize(e->s_compute));
+    float ms = 0.f;
+    CT_CUDA(e, cudaEventElapsedTime(&ms, e->ev_a, e->ev_b));
+    e->stats.kernel_ms = ms; e->stats.pair_ms = ms; e->stats.gram_ms = 0.0; e->stats.total_ms = ms; e->stats.d2h_ms = 0.0;
+    CT_CUDA(e, cudaMemcpy(values, d_vals, sizeof(double) * (size_t)n_pairs, cudaMemcpyDeviceToHost));
+    if (perms) CT_CUDA(e, cudaMemcpy(perms, d_perms, sizeof(int) * (size_t)n_pairs * e->K, cudaMemcpyDeviceToHost));
+    cudaFree(d_pairs); cudaFree(d_vals); cudaFree(d_perms);
+    int rc = finish_stats(e, n_pairs, 1);
+    if (rc) return rc;
+    if (stats) *stats = e->stats;
+    return CT_OK;
+}
+
+int ct_get_stats(const ct_engine* e, ct_stats* stats) {
+    if (!e || !stats) return CT_ERR_ARG;
+    *stats = e->stats;
+    return CT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,174 @@
+// 3x3 superposition solvers used by the Gram epilogue and the per-pair kernels.
+//
+// What they replace in the reference: rmsd.kabsch (numpy.linalg.svd of the 3x3 covariance + the
+// det(V)det(W) reflection fix) as reached from clusttraj/distmat.py:178,220,227 and, through
+// rmsd.kabsch_rmsd, from distmat.py:275.  Neither function is a translation of that code: the
+// RMSD only needs  lambda = s1 + s2 + sign(det S) s3  (S = covariance, s = singular values), which is
+// the largest eigenvalue of Horn's symmetric 4x4 quaternion matrix; its characteristic polynomial in
+// terms of three invariants of S is
+//     f(x) = (x^2 - a)^2 - 8 d x - 4 b,   a = |S|_F^2,  b = |cof S|_F^2,  d = det S,
+// and lambda is its largest root.  The rotation itself (needed before a Hungarian reorder) is the
+// eigenvector of that root.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace ct {
+
+// Invariants of the 3x3 covariance S (row-major s[9]).  39 FP64 operations.
+__device__ __forceinline__ void quartic_invariants(const double* s, double& a, double& b, double& d) {
+    const double c00 = s[4] * s[8] - s[5] * s[7];
+    const double c01 = s[5] * s[6] - s[3] * s[8];
+    const double c02 = s[3] * s[7] - s[4] * s[6];
+    const double c10 = s[2] * s[7] - s[1] * s[8];
+    const double c11 = s[0] * s[8] - s[2] * s[6];
+    const double c12 = s[1] * s[6] - s[0] * s[7];
+    const double c20 = s[1] * s[5] - s[2] * s[4];
+    const double c21 = s[2] * s[3] - s[0] * s[5];
+    const double c22 = s[0] * s[4] - s[1] * s[3];
+    a = s[0] * s[0];
+#pragma unroll
+    for (int k = 1; k < 9; ++k) a = fma(s[k], s[k], a);
+    b = c00 * c00;
+    b = fma(c01, c01, b); b = fma(c02, c02, b);
+    b = fma(c10, c10, b); b = fma(c11, c11, b); b = fma(c12, c12, b);
+    b = fma(c20, c20, b); b = fma(c21, c21, b); b = fma(c22, c22, b);
+    d = fma(s[0], c00, fma(s[1], c01, s[2] * c02));
+}
+
+// Largest root of f.  `half_g` = (G_i + G_j)/2 is an upper bound of the root (E >= 0), sqrt(3a) is
+// another; Newton from above on a polynomial with only real roots is monotone, so the coarse phase
+// runs in FP32 on the normalised polynomial (separate pipe from the FP64 MMA) and FP64 only polishes.
+// Returns false when the iteration did not settle (near-double root: mirror images, collinear atoms,
+// or non-finite intermediates); the caller then re-does the pair with the explicit-rotation path.
+__device__ __forceinline__ bool largest_root(double a, double b, double d, double half_g, double& lam_out) {
+    const float af0 = (float)a;
+    float l0 = fminf((float)half_g, sqrtf(3.0f * af0)) * 1.000001f;
+    if (!(l0 > 0.0f)) {  // S == 0 (e.g. zero padding): all roots are 0
+        lam_out = 0.0;
+        return a == 0.0;
+    }
+    const float sc = 1.0f / l0;
+    const float sc2 = sc * sc;
+    const float af = af0 * sc2;
+    const float df2 = 2.0f * ((float)d * sc2 * sc);
+    const float bf4 = 4.0f * ((float)b * sc2 * sc2);
+    float x = 1.0f;
+#pragma unroll 1
+    for (int it = 0; it < 14; ++it) {
+        const float t = fmaf(x, x, -af);
+        const float f = fmaf(t, t, fmaf(-4.0f * df2, x, -bf4));
+        const float fq = fmaf(x, t, -df2);
+        if (!(fq > 0.0f)) break;
+        const float step = 0.25f * __fdividef(f, fq);
+        x -= step;
+        if (fabsf(step) <= 3e-7f * x) break;
+    }
+    double lam = (double)x * (double)l0;
+    const double m2d = -2.0 * d, m4b = -4.0 * b;
+    double step = 0.0;
+    bool ok = false;
+#pragma unroll 1
+    for (int it = 0; it < 24; ++it) {
+        const double t = fma(lam, lam, -a);
+        const double f = fma(t, t, fma(4.0 * m2d, lam, m4b));
+        const double fq = fma(lam, t, m2d);
+        const float r = 0.25f * __frcp_rn((float)fq);
+        step = f * (double)r;
+        lam -= step;
+        if (it >= 1 && fabs(step) <= 1e-13 * lam) { ok = true; break; }
+    }
+    lam_out = lam;
+    return ok && (lam == lam);
+}
+
+// Cyclic Jacobi on a symmetric 4x4 matrix (in registers, fully unrolled indices).  On return A holds the
+// eigenvalues on its diagonal and the columns of V the eigenvectors.
+__device__ __forceinline__ void jacobi4(double (&A)[4][4], double (&V)[4][4]) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) V[r][c] = (r == c) ? 1.0 : 0.0;
+#pragma unroll 1
+    for (int sweep = 0; sweep < 16; ++sweep) {
+        const double off = A[0][1] * A[0][1] + A[0][2] * A[0][2] + A[0][3] * A[0][3] + A[1][2] * A[1][2] +
+                           A[1][3] * A[1][3] + A[2][3] * A[2][3];
+        const double dia = A[0][0] * A[0][0] + A[1][1] * A[1][1] + A[2][2] * A[2][2] + A[3][3] * A[3][3];
+        if (!(off > 1e-34 * dia)) break;
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+#pragma unroll
+            for (int q = p + 1; q < 4; ++q) {
+                const double apq = A[p][q];
+                if (apq != 0.0) {
+                    const double theta = 0.5 * (A[q][q] - A[p][p]) / apq;
+                    const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
+                    const double c = rsqrt(fma(t, t, 1.0));
+                    const double s = t * c;
+                    A[p][p] -= t * apq;
+                    A[q][q] += t * apq;
+                    A[p][q] = 0.0;
+                    A[q][p] = 0.0;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        if (r != p && r != q) {
+                            const double arp = A[r][p], arq = A[r][q];
+                            const double np_ = c * arp - s * arq, nq_ = s * arp + c * arq;
+                            A[r][p] = np_; A[p][r] = np_;
+                            A[r][q] = nq_; A[q][r] = nq_;
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const double vrp = V[r][p], vrq = V[r][q];
+                        V[r][p] = c * vrp - s * vrq;
+                        V[r][q] = s * vrp + c * vrq;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Best proper rotation for covariance S[a][b] = sum_k p_k[a] q_k[b] (p = moving frame, q = reference
+// frame).  Writes U (row-major, used as p_row * U like the reference's np.dot(P, U), distmat.py:181,223,
+// 228) and returns lambda = s1 + s2 + sign(det S) s3.
+__device__ __forceinline__ double kabsch_rotation(const double* s, double* U) {
+    double A[4][4], V[4][4];
+    const double Sxx = s[0], Sxy = s[1], Sxz = s[2], Syx = s[3], Syy = s[4], Syz = s[5], Szx = s[6], Szy = s[7],
+                 Szz = s[8];
+    A[0][0] = Sxx + Syy + Szz;
+    A[1][1] = Sxx - Syy - Szz;
+    A[2][2] = -Sxx + Syy - Szz;
+    A[3][3] = -Sxx - Syy + Szz;
+    A[0][1] = A[1][0] = Syz - Szy;
+    A[0][2] = A[2][0] = Szx - Sxz;
+    A[0][3] = A[3][0] = Sxy - Syx;
+    A[1][2] = A[2][1] = Sxy + Syx;
+    A[1][3] = A[3][1] = Szx + Sxz;
+    A[2][3] = A[3][2] = Syz + Szy;
+    jacobi4(A, V);
+    double lam = A[0][0];
+    double q0 = V[0][0], q1 = V[1][0], q2 = V[2][0], q3 = V[3][0];
+#pragma unroll
+    for (int c = 1; c < 4; ++c) {
+        if (A[c][c] > lam) {
+            lam = A[c][c];
+            q0 = V[0][c]; q1 = V[1][c]; q2 = V[2][c]; q3 = V[3][c];
+        }
+    }
+    const double nrm = rsqrt(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
+    q0 *= nrm; q1 *= nrm; q2 *= nrm; q3 *= nrm;
+    // R rotates column vectors p -> q; U = R^T acts on row vectors.
+    const double r00 = q0 * q0 + q1 * q1 - q2 * q2 - q3 * q3, r01 = 2.0 * (q1 * q2 - q0 * q3),
+                 r02 = 2.0 * (q1 * q3 + q0 * q2);
+    const double r10 = 2.0 * (q2 * q1 + q0 * q3), r11 = q0 * q0 - q1 * q1 + q2 * q2 - q3 * q3,
+                 r12 = 2.0 * (q2 * q3 - q0 * q1);
+    const double r20 = 2.0 * (q3 * q1 - q0 * q2), r21 = 2.0 * (q3 * q2 + q0 * q1),
+                 r22 = q0 * q0 - q1 * q1 - q2 * q2 + q3 * q3;
+    U[0] = r00; U[1] = r10; U[2] = r20;
+    U[3] = r01; U[4] = r11; U[5] = r21;
+    U[6] = r02; U[7] = r12; U[8] = r22;
+    return lam;
+}
+
+}  // namespace ct

@@ -1,0 +1,456 @@
+// K3 / K4 — the general per-pair path of clusttraj/distmat.py:133-275, one warp per frame pair:
+// stepwise solute superposition (-ns), per-element Hungarian reordering (-e, rmsd.reorder_hungarian =
+// scipy cdist("euclidean") + linear_sum_assignment per element, bound at io.py:559-561 and called at
+// distmat.py:192,243), --final-kabsch, -ws weights and -eex exclusions.  The control flow per pair
+// follows the reference's dispatch (SURVEY.md §8a mode table); the arithmetic is new:
+//   * rotations come from the quaternion eigenproblem (solve3x3.cuh), not an SVD;
+//   * the assignment is a warp-parallel shortest-augmenting-path solver (the algorithm family of
+//     SciPy's linear_sum_assignment, Crouse 2016): lanes own columns, the frontier minimum is a
+//     warp-shuffle argmin, duals and path state live in shared memory, and EUCLIDEAN (not squared)
+//     costs are evaluated on the fly in FP64 from coordinates staged in shared memory — no cost matrix
+//     is ever materialised.
+// With continuous coordinates the optimal assignment is unique, so the permutation equals SciPy's.
+#include "common.cuh"
+#include "solve3x3.cuh"
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/clusttraj_b200.h"
+
+namespace ct {
+
+struct PairPlan {
+    int K;            // kept atoms
+    int natoms;       // kept solute atoms (0 without -ns)
+    int has_ns, do_reorder, solute_phase, final_direct, weighted;
+    double w_solute, w_solvent;  // per-atom weights (distmat.py:259-262)
+    // element blocks: phase 0 = solute reorder (distmat.py:184-223), phase 1 = main reorder (:231-256)
+    int nblocks[2];
+    const int* block_off[2];  // [nblocks+1] offsets into idx
+    const int* idx[2];        // kept-atom positions, ascending inside a block
+    int nmax;                 // largest block
+};
+
+struct PairPlanHost {
+    PairPlan plan{};
+    int* d_ints = nullptr;        // all index arrays in one allocation
+    double* d_work = nullptr;     // per-resident-warp working copy of the moving frame [K][3]
+    int* d_perm = nullptr;        // per-resident-warp composite permutation [K]
+    size_t work_warps = 0;
+    int smem_per_warp = 0;
+};
+
+static constexpr int PAIR_WARPS = 4;
+
+__host__ __device__ inline int pair_smem_per_warp(int nmax) {
+    // Qe, Pe (3 doubles per row/column), u, v, shortest (doubles), pred, row4col, col4row, old perm (ints),
+    // scanned (bytes)
+    int b = nmax * (24 + 24 + 24 + 16) + ((nmax + 7) / 8) * 8;
+    return (b + 15) / 16 * 16;
+}
+
+// ---- warp-parallel shortest augmenting path ------------------------------------------------------------
+// rows = atoms of the reference frame (Qe), columns = atoms of the moving frame (Pe); on return
+// c4r[r] is the column matched to row r.  Returns the number of frontier scans.
+__device__ int lsap_warp(int n, const double* Qe, const double* Pe, double* u, double* v, double* sh, int* pred,
+                         int* r4c, int* c4r, unsigned char* scanned, int lane) {
+    for (int j = lane; j < n; j += 32) { u[j] = 0.0; v[j] = 0.0; r4c[j] = -1; c4r[j] = -1; }
+    __syncwarp();
+    int steps = 0;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    for (int cur = 0; cur < n; ++cur) {
+        for (int j = lane; j < n; j += 32) { sh[j] = INF; scanned[j] = 0; }
+        __syncwarp();
+        int i = cur, sink = -1;
+        double minVal = 0.0;
+        while (sink < 0) {
+            const double qx = Qe[3 * i], qy = Qe[3 * i + 1], qz = Qe[3 * i + 2], ui = u[i];
+            double best = INF;
+            int bestj = 0x7fffffff, bestfree = 0;
+            for (int j = lane; j < n; j += 32) {
+                if (scanned[j]) continue;
+                const double dx = qx - Pe[3 * j], dy = qy - Pe[3 * j + 1], dz = qz - Pe[3 * j + 2];
+                const double cost = sqrt(dx * dx + dy * dy + dz * dz);
+                const double r = minVal + cost - ui - v[j];
+                double s = sh[j];
+                if (r < s) { s = r; sh[j] = r; pred[j] = i; }
+                const int fr = r4c[j] < 0;
+                if (s < best || (s == best && fr > bestfree)) { best = s; bestj = j; bestfree = fr; }
+            }
+            // warp argmin: lower value, then unassigned column, then lower index
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oj = __shfl_xor_sync(0xffffffffu, bestj, o);
+                const int of = __shfl_xor_sync(0xffffffffu, bestfree, o);
+                const bool take = ob < best || (ob == best && (of > bestfree || (of == bestfree && oj < bestj)));
+                if (take) { best = ob; bestj = oj; bestfree = of; }
+            }
+            ++steps;
+            if (bestj == 0x7fffffff) return -steps;  // no finite cost left (NaN coordinates)
+            minVal = best;
+            if (lane == 0) scanned[bestj] = 1;
+            __syncwarp();
+            const int owner = r4c[bestj];
+            if (owner < 0) sink = bestj; else i = owner;
+        }
+        // dual update through the scanned columns (their rows are exactly the scanned rows)
+        for (int j = lane; j < n; j += 32) {
+            if (scanned[j]) {
+                const double delta = minVal - sh[j];
+                v[j] -= delta;
+                const int r = r4c[j];
+                if (r >= 0) u[r] += delta;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            u[cur] += minVal;
+            int j = sink;
+            while (true) {
+                const int r = pred[j];
+                r4c[j] = r;
+                const int pj = c4r[r];
+                c4r[r] = j;
+                j = pj;
+                if (r == cur) break;
+            }
+        }
+        __syncwarp();
+    }
+    return steps;
+}
+
+// rotate the working frame in place: W[k] = W[k] * U (row vector times matrix)
+__device__ __forceinline__ void warp_rotate(double* W, int K, const double* U, int lane) {
+    for (int k = lane; k < K; k += 32) {
+        const double x = W[3 * k], y = W[3 * k + 1], z = W[3 * k + 2];
+        W[3 * k] = fma(x, U[0], fma(y, U[3], z * U[6]));
+        W[3 * k + 1] = fma(x, U[1], fma(y, U[4], z * U[7]));
+        W[3 * k + 2] = fma(x, U[2], fma(y, U[5], z * U[8]));
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void warp_cov(const double* P, const double* Q, int k1, int lane, double* s) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t) s[t] = 0.0;
+    for (int k = lane; k < k1; k += 32) {
+        const double px = P[3 * k], py = P[3 * k + 1], pz = P[3 * k + 2];
+        const double qx = Q[3 * k], qy = Q[3 * k + 1], qz = Q[3 * k + 2];
+        s[0] = fma(px, qx, s[0]); s[1] = fma(px, qy, s[1]); s[2] = fma(px, qz, s[2]);
+        s[3] = fma(py, qx, s[3]); s[4] = fma(py, qy, s[4]); s[5] = fma(py, qz, s[5]);
+        s[6] = fma(pz, qx, s[6]); s[7] = fma(pz, qy, s[7]); s[8] = fma(pz, qz, s[8]);
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) s[t] = warp_sum(s[t]);
+}
+
+__device__ int reorder_phase(const PairPlan& pl, int phase, double* W, int* perm, const double* Q, unsigned char* sm,
+                             int lane) {
+    const int nmax = pl.nmax;
+    double* Qe = reinterpret_cast<double*>(sm);
+    double* Pe = Qe + 3 * nmax;
+    double* u = Pe + 3 * nmax;
+    double* v = u + nmax;
+    double* sh = v + nmax;
+    int* pred = reinterpret_cast<int*>(sh + nmax);
+    int* r4c = pred + nmax;
+    int* c4r = r4c + nmax;
+    int* oldp = c4r + nmax;
+    unsigned char* scanned = reinterpret_cast<unsigned char*>(oldp + nmax);
+    int steps = 0;
+    for (int b = 0; b < pl.nblocks[phase]; ++b) {
+        const int o0 = pl.block_off[phase][b], n = pl.block_off[phase][b + 1] - o0;
+        if (n < 2) continue;
+        const int* idx = pl.idx[phase] + o0;
+        for (int t = lane; t < n; t += 32) {
+            const int k = idx[t];
+            Qe[3 * t] = Q[3 * k]; Qe[3 * t + 1] = Q[3 * k + 1]; Qe[3 * t + 2] = Q[3 * k + 2];
+            Pe[3 * t] = W[3 * k]; Pe[3 * t + 1] = W[3 * k + 1]; Pe[3 * t + 2] = W[3 * k + 2];
+            oldp[t] = perm[k];
+        }
+        __syncwarp();
+        const int st = lsap_warp(n, Qe, Pe, u, v, sh, pred, r4c, c4r, scanned, lane);
+        steps += st < 0 ? -st : st;
+        if (st >= 0) {
+            // rmsd.reorder_hungarian: the atom matched to reference row t moves to position idx[t]
+            for (int t = lane; t < n; t += 32) {
+                const int c = c4r[t], k = idx[t];
+                W[3 * k] = Pe[3 * c]; W[3 * k + 1] = Pe[3 * c + 1]; W[3 * k + 2] = Pe[3 * c + 2];
+                perm[k] = oldp[c];
+            }
+        }
+        __syncwarp();
+    }
+    return steps;
+}
+
+__device__ double pair_value_warp(const PairPlan& pl, const double* __restrict__ Pg, const double* __restrict__ Qg,
+                                  double* W, int* perm, unsigned char* sm, int lane, int& steps) {
+    const int K = pl.K, ns = pl.natoms;
+    double s[9], U[9];
+    steps = 0;
+    // working copy of the moving frame; with -ns the reference subtracts centroid(Q[:natoms]) from P
+    // once more (distmat.py:174) although Q is already centred on it
+    double qc0 = 0.0, qc1 = 0.0, qc2 = 0.0;
+    if (pl.has_ns) {
+        for (int k = lane; k < ns; k += 32) { qc0 += Qg[3 * k]; qc1 += Qg[3 * k + 1]; qc2 += Qg[3 * k + 2]; }
+        qc0 = warp_sum(qc0) / ns; qc1 = warp_sum(qc1) / ns; qc2 = warp_sum(qc2) / ns;
+    }
+    for (int k = lane; k < K; k += 32) {
+        W[3 * k] = Pg[3 * k] - qc0; W[3 * k + 1] = Pg[3 * k + 1] - qc1; W[3 * k + 2] = Pg[3 * k + 2] - qc2;
+        perm[k] = k;
+    }
+    __syncwarp();
+    // rotation(s) before the main reorder (distmat.py:172-228)
+    warp_cov(W, Qg, pl.has_ns ? ns : K, lane, s);
+    kabsch_rotation(s, U);
+    warp_rotate(W, K, U, lane);
+    if (pl.solute_phase) {
+        steps += reorder_phase(pl, 0, W, perm, Qg, sm, lane);
+        warp_cov(W, Qg, ns, lane, s);
+        kabsch_rotation(s, U);
+        warp_rotate(W, K, U, lane);
+    }
+    if (pl.do_reorder) steps += reorder_phase(pl, 1, W, perm, Qg, sm, lane);
+
+    // final value (distmat.py:259-275)
+    if (pl.final_direct) {
+        double res = 0.0;
+        for (int k = lane; k < K; k += 32) {
+            const double dx = W[3 * k] - Qg[3 * k], dy = W[3 * k + 1] - Qg[3 * k + 1], dz = W[3 * k + 2] - Qg[3 * k + 2];
+            const double d2 = dx * dx + dy * dy + dz * dz;
+            res += pl.weighted ? d2 * (k < ns ? pl.w_solute : pl.w_solvent) : d2;
+        }
+        res = warp_sum(res);
+        return pl.weighted ? sqrt(res) : sqrt(res / (double)K);
+    }
+    if (!pl.weighted) {
+        // rmsd.kabsch_rmsd: rotate again (no re-centring) and measure directly
+        warp_cov(W, Qg, K, lane, s);
+        kabsch_rotation(s, U);
+        double res = 0.0;
+        for (int k = lane; k < K; k += 32) {
+            const double x = W[3 * k], y = W[3 * k + 1], z = W[3 * k + 2];
+            const double dx = fma(x, U[0], fma(y, U[3], z * U[6])) - Qg[3 * k];
+            const double dy = fma(x, U[1], fma(y, U[4], z * U[7])) - Qg[3 * k + 1];
+            const double dz = fma(x, U[2], fma(y, U[5], z * U[8])) - Qg[3 * k + 2];
+            res = fma(dx, dx, fma(dy, dy, fma(dz, dz, res)));
+        }
+        res = warp_sum(res);
+        return sqrt(res / (double)K);
+    }
+    // rmsd.kabsch_weighted_rmsd (distmat.py:273): weighted, weighted-centred covariance; the value is
+    // sqrt(max(psq + qsq - 2 lambda, 0)) with sum(w) = 1
+    double cp[3] = {0, 0, 0}, cq[3] = {0, 0, 0}, pq = 0.0;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) s[t] = 0.0;
+    double wsum = 0.0;
+    for (int k = lane; k < K; k += 32) {
+        const double w = k < ns ? pl.w_solute : pl.w_solvent;
+        const double px = W[3 * k], py = W[3 * k + 1], pz = W[3 * k + 2];
+        const double qx = Qg[3 * k], qy = Qg[3 * k + 1], qz = Qg[3 * k + 2];
+        wsum += w;
+        cp[0] += w * px; cp[1] += w * py; cp[2] += w * pz;
+        cq[0] += w * qx; cq[1] += w * qy; cq[2] += w * qz;
+        pq += w * (px * px + py * py + pz * pz + qx * qx + qy * qy + qz * qz);
+        s[0] += w * px * qx; s[1] += w * px * qy; s[2] += w * px * qz;
+        s[3] += w * py * qx; s[4] += w * py * qy; s[5] += w * py * qz;
+        s[6] += w * pz * qx; s[7] += w * pz * qy; s[8] += w * pz * qz;
+    }
+    wsum = warp_sum(wsum); pq = warp_sum(pq);
+#pragma unroll
+    for (int t = 0; t < 3; ++t) { cp[t] = warp_sum(cp[t]); cq[t] = warp_sum(cq[t]); }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) s[t] = warp_sum(s[t]);
+    const double iw = 1.0 / wsum;
+    double c2 = 0.0;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) c2 += cp[t] * cp[t] + cq[t] * cq[t];
+    const double pqs = pq - c2 * iw;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) s[a * 3 + b] = (s[a * 3 + b] - cp[a] * cq[b] * iw) * iw;
+    const double lam = kabsch_rotation(s, U);
+    const double msd = pqs * iw - 2.0 * lam;
+    return sqrt(fmax(msd, 0.0));
+}
+
+// pairs given by the condensed slab of rows [row_begin,row_end) (pairs_list == nullptr) or explicitly
+__global__ void __launch_bounds__(PAIR_WARPS * 32) pair_kernel(const PairPlan pl, const double* __restrict__ centred, int M,
+                                                               long long idx_base, long long n_entries,
+                                                               const long long* __restrict__ pairs_list,
+                                                               double* __restrict__ out, int* __restrict__ perms_out,
+                                                               double* __restrict__ work, int* __restrict__ perm_work,
+                                                               int smem_per_warp, unsigned long long* counters) {
+    extern __shared__ __align__(16) unsigned char pair_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long gw = (long long)blockIdx.x * PAIR_WARPS + warp;
+    const long long nw = (long long)gridDim.x * PAIR_WARPS;
+    unsigned char* sm = pair_smem + (size_t)warp * smem_per_warp;
+    double* W = work + (size_t)gw * pl.K * 3;
+    int* perm = perm_work + (size_t)gw * pl.K;
+    unsigned long long my_steps = 0;
+    for (long long e = gw; e < n_entries; e += nw) {
+        int i, j;
+        if (pairs_list) { i = (int)pairs_list[2 * e]; j = (int)pairs_list[2 * e + 1]; }
+        else {
+            const long long idx = idx_base + e;
+            const double b = 2.0 * (double)M - 1.0;
+            long long r = (long long)floor((b - sqrt(b * b - 8.0 * (double)idx)) * 0.5);
+            if (r < 0) r = 0;
+            while (r > 0 && condensed_row_base(M, r) > idx) --r;
+            while (condensed_row_base(M, r + 1) <= idx) ++r;
+            i = (int)r;
+            j = (int)(idx - condensed_row_base(M, r) + r + 1);
+        }
+        int steps;
+        const double val = pair_value_warp(pl, centred + (size_t)j * pl.K * 3, centred + (size_t)i * pl.K * 3, W, perm, sm,
+                                           lane, steps);
+        my_steps += (unsigned long long)steps;
+        if (lane == 0) out[e] = val;
+        if (perms_out) {
+            __syncwarp();
+            for (int k = lane; k < pl.K; k += 32) perms_out[(size_t)e * pl.K + k] = perm[k];
+        }
+        __syncwarp();
+    }
+    if (lane == 0 && my_steps) atomicAdd(counters + 1, my_steps);
+}
+
+// ---- host side: build the frame-invariant plan ---------------------------------------------------------
+static void element_blocks(const std::vector<int>& view, const int32_t* kept_z, std::vector<int>& off, std::vector<int>& idx) {
+    // np.unique(ref atoms) order = ascending atomic number; positions ascending inside an element
+    std::map<int, std::vector<int>> by_z;
+    for (int k : view) by_z[kept_z[k]].push_back(k);
+    off.assign(1, 0);
+    idx.clear();
+    for (auto& kv : by_z) {
+        idx.insert(idx.end(), kv.second.begin(), kv.second.end());
+        off.push_back((int)idx.size());
+    }
+}
+
+int pair_plan_build(PairPlanHost** out, const int32_t* kept_z, int K, int natoms, const ct_opts* o, std::string& err) {
+    for (int t = 1; t < o->n_excl; ++t)
+        if (o->reorder_excl[t] <= o->reorder_excl[t - 1]) {
+            err = "reorder_excl must be strictly ascending (the reference re-inserts excluded atoms in list order, "
+                  "distmat.py:200-214,247-253; other orders are not implemented)";
+            return CT_ERR_UNSUPPORTED;
+        }
+    PairPlanHost* h = new PairPlanHost();
+    PairPlan& p = h->plan;
+    p.K = K;
+    p.has_ns = o->solute_natoms != 0;
+    p.natoms = p.has_ns ? natoms : 0;
+    p.do_reorder = o->reorder_mode != 0;
+    p.solute_phase = p.has_ns && p.do_reorder && !o->reorder_solvent_only;
+    p.final_direct = p.has_ns && p.do_reorder && !o->final_kabsch;
+    p.weighted = o->weight_solute != 0.0;
+    if (p.weighted) {
+        if (!p.has_ns || K == natoms) { delete h; err = "weight_solute needs solute_natoms and at least one solvent atom"; return CT_ERR_UNSUPPORTED; }
+        p.w_solute = o->weight_solute / natoms;
+        p.w_solvent = (1.0 - o->weight_solute) / (K - natoms);
+    }
+    std::vector<bool> excl(K, false);
+    for (int t = 0; t < o->n_excl; ++t) excl[o->reorder_excl[t]] = true;
+    std::vector<int> off[2], idx[2];
+    off[0].assign(1, 0); off[1].assign(1, 0);
+    if (p.solute_phase) {
+        std::vector<int> view;
+        for (int k = 0; k < natoms; ++k) if (!excl[k]) view.push_back(k);
+        element_blocks(view, kept_z, off[0], idx[0]);
+    }
+    if (p.do_reorder) {
+        std::vector<int> view;
+        for (int k = p.has_ns ? natoms : 0; k < K; ++k) if (!excl[k]) view.push_back(k);
+        element_blocks(view, kept_z, off[1], idx[1]);
+    }
+    p.nmax = 1;
+    for (int ph = 0; ph < 2; ++ph) {
+        p.nblocks[ph] = (int)off[ph].size() - 1;
+        for (int b = 0; b + 1 < (int)off[ph].size(); ++b) p.nmax = std::max(p.nmax, off[ph][b + 1] - off[ph][b]);
+    }
+    h->smem_per_warp = pair_smem_per_warp(p.nmax);
+    if ((size_t)h->smem_per_warp * PAIR_WARPS > 227 * 1024) {
+        // fall back to fewer warps is not implemented; blocks beyond ~680 atoms per element do not fit
+        delete h;
+        err = "an element block is too large for the shared-memory assignment solver";
+        return CT_ERR_UNSUPPORTED;
+    }
+    std::vector<int> all;
+    size_t pos[4];
+    pos[0] = all.size(); all.insert(all.end(), off[0].begin(), off[0].end());
+    pos[1] = all.size(); all.insert(all.end(), idx[0].begin(), idx[0].end());
+    pos[2] = all.size(); all.insert(all.end(), off[1].begin(), off[1].end());
+    pos[3] = all.size(); all.insert(all.end(), idx[1].begin(), idx[1].end());
+    if (cudaMalloc(&h->d_ints, sizeof(int) * std::max<size_t>(all.size(), 1)) != cudaSuccess ||
+        cudaMemcpy(h->d_ints, all.data(), sizeof(int) * all.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+        err = std::string("pair plan upload failed: ") + cudaGetErrorString(cudaGetLastError());
+        delete h;
+        return CT_ERR_CUDA;
+    }
+    p.block_off[0] = h->d_ints + pos[0]; p.idx[0] = h->d_ints + pos[1];
+    p.block_off[1] = h->d_ints + pos[2]; p.idx[1] = h->d_ints + pos[3];
+    *out = h;
+    return CT_OK;
+}
+
+void pair_plan_free(PairPlanHost* p) {
+    if (!p) return;
+    cudaFree(p->d_ints); cudaFree(p->d_work); cudaFree(p->d_perm);
+    delete p;
+}
+
+static cudaError_t launch_pairs(PairPlanHost* h, const double* centred, int M, long long idx_base, long long n_entries,
+                                const long long* pairs_list, double* out, int* perms_out, unsigned long long* counters,
+                                int sm_count, cudaStream_t stream) {
+    if (n_entries <= 0) return cudaSuccess;
+    const int smem = h->smem_per_warp * PAIR_WARPS;
+    cudaError_t e = cudaFuncSetAttribute(pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pair_kernel, PAIR_WARPS * 32, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long)sm_count * per_sm;
+    const long long need = (n_entries + PAIR_WARPS - 1) / PAIR_WARPS;
+    if (grid > need) grid = need;
+    const size_t warps = (size_t)grid * PAIR_WARPS;
+    if (warps > h->work_warps) {
+        cudaFree(h->d_work); cudaFree(h->d_perm);
+        h->d_work = nullptr; h->d_perm = nullptr; h->work_warps = 0;
+        if ((e = cudaMalloc(&h->d_work, sizeof(double) * warps * h->plan.K * 3)) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&h->d_perm, sizeof(int) * warps * h->plan.K)) != cudaSuccess) return e;
+        h->work_warps = warps;
+    }
+    pair_kernel<<<(unsigned)grid, PAIR_WARPS * 32, smem, stream>>>(h->plan, centred, M, idx_base, n_entries, pairs_list, out,
+                                                                   perms_out, h->d_work, h->d_perm, h->smem_per_warp,
+                                                                   counters);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pairs_rows(const PairPlanHost* plan, const double* centred, int M, int K, int row_begin, int row_end,
+                              double* out, long long idx_base, unsigned long long* counters, int sm_count,
+                              cudaStream_t stream) {
+    (void)K;
+    const long long last = row_end < M - 1 ? row_end : M - 1;
+    const long long n = last > row_begin ? condensed_row_base(M, last) - condensed_row_base(M, row_begin) : 0;
+    return launch_pairs(const_cast<PairPlanHost*>(plan), centred, M, idx_base, n, nullptr, out, nullptr, counters, sm_count,
+                        stream);
+}
+
+cudaError_t launch_pairs_list(const PairPlanHost* plan, const double* centred, int M, int K, const long long* pairs_dev,
+                              long long n_pairs, double* values_dev, int* perms_dev, unsigned long long* counters,
+                              int sm_count, cudaStream_t stream) {
+    (void)K;
+    return launch_pairs(const_cast<PairPlanHost*>(plan), centred, M, 0, n_pairs, pairs_dev, values_dev, perms_dev, counters,
+                        sm_count, stream);
+}
+
+}  // namespace ct

@@ -1,0 +1,168 @@
+"""Drop-in for clusttraj/distmat.py: the same three entry points, the same condensed float64 vector,
+computed by the B200 engine.
+
+  get_distmat(clust_opt)            distmat.py:15-41   (-i load, or build + np.save)
+  build_distance_matrix(clust_opt)  distmat.py:44-78   (whole matrix; the Pool over rows becomes
+                                                        equal-area row slabs over the visible GPUs)
+  compute_distmat_line(...)         distmat.py:81-277  (one row)
+
+Differences a caller can observe: the trajectory is parsed ONCE (the reference re-parses it for every
+pair), ``n_workers`` does not fork processes (CUDA and fork do not mix) and nothing runs on the CPU:
+without a GPU these functions raise EngineError.
+"""
+import os
+import threading
+
+import numpy as np
+
+from . import _engine
+from .io import ClustOptions, Logger  # noqa: F401  (re-exported like the reference module)
+from .reorder import reorder_mode_of
+from .xyz import read_trajectory
+
+_engines = {}
+_engines_lock = threading.Lock()
+_traj_cache = {}
+
+
+def _engine_for(device):
+    with _engines_lock:
+        eng = _engines.get(device)
+        if eng is None:
+            eng = _engines[device] = _engine.Engine(device)
+        return eng
+
+
+def visible_devices():
+    """GPUs this process drives: CLUSTTRAJ_B200_DEVICES="0,1,..." or all visible; under torchrun
+    (LOCAL_RANK set) only the rank's own GPU."""
+    env = os.environ.get("CLUSTTRAJ_B200_DEVICES")
+    if env:
+        return [int(x) for x in env.split(",") if x.strip() != ""]
+    n = _engine.device_count()
+    if n == 0:
+        raise _engine.EngineError("clusttraj_b200: no CUDA device visible (there is no CPU fallback)")
+    if "LOCAL_RANK" in os.environ:
+        return [int(os.environ["LOCAL_RANK"]) % n]
+    return list(range(n))
+
+
+def _load_trajectory(trajfile):
+    """(atomic numbers int32[N], coords float64[M,N,3]); the engine needs frame-invariant atoms."""
+    key = (os.path.abspath(trajfile), os.path.getmtime(trajfile), os.path.getsize(trajfile))
+    hit = _traj_cache.get("last")
+    if hit and hit[0] == key:
+        return hit[1], hit[2]
+    atoms, coords = read_trajectory(trajfile)
+    if (atoms != atoms[0]).any():
+        raise NotImplementedError(
+            "clusttraj_b200 needs the same atom order in every frame (the reference tolerates per-frame "
+            "element lists; the B200 engine packs a frame-invariant mask)")
+    _traj_cache["last"] = (key, atoms[0].copy(), coords)
+    return atoms[0], coords
+
+
+def _opts_from(noh, reorder, reorder_solvent_only, nsatoms, weight_solute, reorderexcl, final_kabsch):
+    mode = reorder_mode_of(reorder)
+    excl = np.asarray(reorderexcl if reorderexcl is not None else [], dtype=np.int32).ravel()
+    if mode == 0:
+        excl = excl[:0]  # the reference only reads the exclusions inside `if reorder` blocks
+    return _engine.make_opts(no_hydrogen=bool(noh), solute_natoms=nsatoms, reorder=bool(mode),
+                             reorder_solvent_only=bool(reorder_solvent_only), final_kabsch=bool(final_kabsch),
+                             weight_solute=weight_solute, reorder_excl=excl)
+
+
+def slab_bounds(M, parts):
+    """Row boundaries of `parts` contiguous slabs with (nearly) equal numbers of matrix entries
+    (SURVEY.md §8e): the reference's consecutive-row chunks are badly unbalanced on a triangle."""
+    total = M * (M - 1) // 2
+    cuts = [0]
+    for p in range(1, parts):
+        target = total * p / parts
+        # smallest r with r*M - r(r+1)/2 >= target
+        b = 2 * M - 1
+        r = int((b - np.sqrt(max(b * b - 8.0 * target, 0.0))) / 2.0)
+        r = min(max(r, cuts[-1]), M)
+        while r < M and r * M - r * (r + 1) // 2 < target:
+            r += 1
+        cuts.append(r)
+    cuts.append(M)
+    return cuts
+
+
+def condensed_matrix(atomic_nums, coords, opts, devices=None, out=None, return_stats=False):
+    """All-pairs matrix of in-memory frames on one or several GPUs (one engine + one host thread per
+    GPU, no collective: every GPU owns a contiguous slab of the condensed vector)."""
+    coords = np.ascontiguousarray(coords, dtype=np.float64)
+    M = coords.shape[0]
+    total = M * (M - 1) // 2
+    devices = list(devices) if devices is not None else visible_devices()
+    if total == 0:
+        res = np.empty(0, dtype=np.float64)
+        return (res, []) if return_stats else res
+    devices = devices[: max(1, min(len(devices), M - 1))]
+    if out is None:
+        out = _engine.pinned_empty(total)
+    cuts = slab_bounds(M, len(devices))
+    stats = [None] * len(devices)
+    errors = []
+
+    def work(k):
+        try:
+            eng = _engine_for(devices[k])
+            eng.load_frames(coords, atomic_nums, opts)
+            lo = cuts[k] * M - cuts[k] * (cuts[k] + 1) // 2
+            n = eng.rows_pairs(cuts[k], cuts[k + 1])
+            _, st = eng.rmsd_rows(cuts[k], cuts[k + 1], out[lo: lo + n])
+            stats[k] = dict(st, device=devices[k], rows=(cuts[k], cuts[k + 1]))
+        except Exception as exc:  # surfaced below, on the caller's thread
+            errors.append(exc)
+
+    if len(devices) == 1:
+        work(0)
+    else:
+        threads = [threading.Thread(target=work, args=(k,)) for k in range(len(devices))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+    if errors:
+        raise errors[0]
+    return (out, stats) if return_stats else out
+
+
+def get_distmat(clust_opt):
+    """Read (-i) or compute and save the condensed RMSD matrix (distmat.py:15-41)."""
+    if clust_opt.input_distmat:
+        Logger.logger.info(f"Reading condensed RMSD matrix from {clust_opt.distmat_name}\n")
+        return np.load(clust_opt.distmat_name)
+    Logger.logger.info(f"Calculating RMSD matrix on {len(visible_devices())} GPU(s)\n")
+    distmat = build_distance_matrix(clust_opt)
+    Logger.logger.info(f"Saving condensed RMSD matrix to {clust_opt.distmat_name}\n")
+    np.save(clust_opt.distmat_name, distmat)
+    return distmat
+
+
+def build_distance_matrix(clust_opt):
+    """Whole condensed matrix for the options in ``clust_opt`` (distmat.py:44-78)."""
+    atoms, coords = _load_trajectory(clust_opt.trajfile)
+    opts = _opts_from(clust_opt.no_hydrogen, clust_opt.reorder_alg, clust_opt.reorder_solvent_only,
+                      clust_opt.solute_natoms, clust_opt.weight_solute, clust_opt.reorder_excl,
+                      clust_opt.final_kabsch)
+    return condensed_matrix(atoms, coords, opts)
+
+
+def compute_distmat_line(idx1, q_info, trajfile, noh, reorder, reorder_solvent_only, nsatoms, weight_solute,
+                         reorderexcl, final_kabsch):
+    """RMSD between frame ``idx1`` and every later frame (distmat.py:81-277).  ``q_info`` (the row
+    frame's atoms and coordinates) is accepted for signature compatibility and checked against the file."""
+    atoms, coords = _load_trajectory(trajfile)
+    if q_info is not None:
+        q_atoms = np.asarray(q_info[0])
+        if q_atoms.shape != atoms.shape or (q_atoms != atoms).any():
+            raise ValueError("q_info atoms do not match the trajectory file")
+    opts = _opts_from(noh, reorder, reorder_solvent_only, nsatoms, weight_solute, reorderexcl, final_kabsch)
+    eng = _engine_for(visible_devices()[0])
+    eng.load_frames(coords, atoms, opts)
+    line, _ = eng.rmsd_rows(int(idx1), int(idx1) + 1)
+    return [np.float64(x) for x in line]

@@ -1,0 +1,43 @@
+"""CLI entry (reference: clusttraj/main.py:24-174): options -> RMSD matrix on the GPU -> the unchanged
+SciPy linkage / fcluster -> clusters file and summary."""
+import sys
+import time
+
+import numpy as np
+
+from .distmat import get_distmat
+from .io import Logger, configure_runtime
+
+
+def classify(clust_opt, distmat):
+    """SciPy hierarchical clustering exactly as the reference calls it (classify.py:84-143)."""
+    import scipy.cluster.hierarchy as hcl
+
+    Z = hcl.linkage(distmat, clust_opt.method, optimal_ordering=bool(clust_opt.opt_order))
+    if clust_opt.n_clusters is not None:
+        clusters = hcl.fcluster(Z, clust_opt.n_clusters, criterion="maxclust")
+    else:
+        clusters = hcl.fcluster(Z, clust_opt.min_rmsd, criterion="distance")
+    np.savetxt(clust_opt.out_clust_name, clusters, fmt="%d")
+    return Z, clusters
+
+
+def main(args=None):
+    t0 = time.monotonic()
+    clust_opt = configure_runtime(sys.argv[1:] if args is None else args)
+    if clust_opt.silhouette_score:
+        raise SystemExit("-ss (silhouette scan) is downstream of the B200 engine's scope; use -rmsd or -nc")
+    t1 = time.monotonic()
+    distmat = get_distmat(clust_opt)
+    t2 = time.monotonic()
+    n = distmat.size
+    Logger.logger.info(f"Time spent computing (or loading) RMSD matrix: {t2 - t1:.6f} s "
+                       f"({n / max(t2 - t1, 1e-12):.3e} pairs/s)\n")
+    _, clusters = classify(clust_opt, distmat)
+    Logger.logger.info(f"A total {len(clusters)} snapshots were read and {clusters.max()} cluster(s) was(were) found.\n")
+    with open(clust_opt.summary_name, "w") as fh:
+        fh.write(str(clust_opt))
+        fh.write(f"\nTotal sum of the RMSD matrix: {float(np.sum(distmat))}\n")
+        fh.write(f"A total {len(clusters)} snapshots were read and {clusters.max()} cluster(s) was(were) found.\n")
+    Logger.logger.info(f"Total wall time: {time.monotonic() - t0:.6f} s\n")
+    return 0

@@ -1,0 +1,111 @@
+/* clusttraj_b200 — C ABI of the B200 all-pairs minimum-RMSD engine.
+ *
+ * The reference (hmcezar/clusttraj v1.2.0) has NO plugin / FFI interface: its seam for this path is
+ * three Python callables in clusttraj/distmat.py plus the ClustOptions dataclass (io.py:42-83).
+ * This header is the boundary a maintainer would bind from those callables (ctypes stub in
+ * INTEGRATION.md).  Each entry point names the reference code it replaces.
+ *
+ * Conventions: plain pointers and sizes, no exceptions across the ABI.  Every function returns 0 on
+ * success or a negative ct_status; ct_last_error(engine) gives the message.  The caller owns all host
+ * buffers.  One host thread per engine handle at a time; one engine drives one GPU.
+ */
+#ifndef CLUSTTRAJ_B200_H
+#define CLUSTTRAJ_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ct_engine ct_engine;
+
+enum ct_status {
+    CT_OK = 0,
+    CT_ERR_CUDA = -1,       /* a CUDA runtime call failed (message in ct_last_error) */
+    CT_ERR_ARG = -2,        /* bad argument */
+    CT_ERR_STATE = -3,      /* call order (e.g. rows requested before frames were loaded) */
+    CT_ERR_UNSUPPORTED = -4 /* option combination the engine does not implement */
+};
+
+/* Per-pair options: the hot-path fields of ClustOptions (io.py:42-83) as read by
+ * build_distance_matrix (distmat.py:54-70) and compute_distmat_line (distmat.py:81-94).
+ * Truthiness follows the reference (distmat.py:134,172,231,259): 0 / 0.0 mean "off". */
+typedef struct ct_opts {
+    int32_t no_hydrogen;          /* -n   : drop atoms with atomic number 1 (distmat.py:135-141,150-156) */
+    int32_t solute_natoms;        /* -ns  : solute size before the H mask; 0 = off (distmat.py:116-118,134) */
+    int32_t reorder_mode;         /* -e   : 0 = none, 1 = hungarian (io.py:559-561 -> rmsd.reorder_hungarian) */
+    int32_t reorder_solvent_only; /* -rs  : skip the solute reorder block (distmat.py:184) */
+    int32_t final_kabsch;         /* --final-kabsch (distmat.py:265,271-275) */
+    int32_t n_excl;               /* length of reorder_excl */
+    double weight_solute;         /* -ws ; 0.0 = off (distmat.py:259-262) */
+    const int32_t* reorder_excl;  /* -eex, 0-based kept-atom positions as in ClustOptions.reorder_excl (io.py:513-517) */
+} ct_opts;
+
+/* Timing / counters of the last ct_rmsd_rows* call (device times from CUDA events). */
+typedef struct ct_stats {
+    double pack_ms;      /* K1 centre/pack kernels of the last ct_load_frames */
+    double h2d_ms;       /* host->device copy of the coordinates in the last ct_load_frames */
+    double kernel_ms;    /* sum of the hot-path kernel launches (Gram+epilogue, fix-up, per-pair) */
+    double gram_ms;      /* the DMMA Gram + fused epilogue kernel only */
+    double pair_ms;      /* per-pair kernel (stepwise / Hungarian modes, fix-up of flagged pairs) */
+    double d2h_ms;       /* device->host streaming of the condensed slab (overlapped with compute) */
+    double total_ms;     /* first launch to last byte on the host, device clock */
+    int64_t pairs;       /* matrix entries produced */
+    int64_t flagged;     /* pairs re-done by the explicit-rotation path (near-duplicates, degenerate 3x3) */
+    int64_t launches;    /* kernel launches issued by the engine in this call */
+    int64_t kept_atoms;  /* K: atoms entering the contraction after the mask */
+    int64_t lsap_steps;  /* total shortest-augmenting-path scan steps (Hungarian modes) */
+} ct_stats;
+
+/* Lifetime.  device = CUDA ordinal.  Fails (never falls back to the CPU) when no device exists. */
+int ct_engine_create(int device, ct_engine** out);
+void ct_engine_destroy(ct_engine* e);
+const char* ct_last_error(const ct_engine* e); /* valid until the next call on e; e may be NULL */
+int ct_device_count(void);
+
+/* Pinned host memory for inputs/outputs (so streaming runs at PCIe rate).  Optional: pageable
+ * pointers are accepted everywhere, only slower. */
+int ct_host_alloc(void** ptr, uint64_t bytes);
+int ct_host_free(void* ptr);
+
+/* Replaces the per-pair get_mol_info + mask + centring of distmat.py:131-169 (done ONCE per frame
+ * here): copies coords [M][N][3] float64 (row-major) and the frame-invariant atomic numbers [N] to the
+ * GPU, applies the -n mask, centres every frame on the centroid the mode prescribes (all kept atoms, or
+ * the first `natoms` kept atoms with -ns) and writes the packed layouts the kernels read. */
+int ct_load_frames(ct_engine* e, const double* coords, const int32_t* atomic_nums, int64_t M, int32_t N,
+                   const ct_opts* opts);
+
+/* Number of matrix entries in rows [row_begin,row_end): sum over i of (M-1-i). */
+int64_t ct_rows_pairs(int64_t M, int64_t row_begin, int64_t row_end);
+
+/* Replaces compute_distmat_line (distmat.py:81-277) for rows row_begin..row_end-1 and the row
+ * flattening of build_distance_matrix (distmat.py:78): writes the contiguous slab of the SciPy-condensed
+ * vector that those rows own, out[k] for k = idx(row_begin,row_begin+1) .. , to HOST memory `out`
+ * (ct_rows_pairs entries).  Compute and the device->host stream are overlapped chunk by chunk. */
+int ct_rmsd_rows(ct_engine* e, int64_t row_begin, int64_t row_end, double* out, ct_stats* stats);
+
+/* Same, but leaves the slab in an engine-owned DEVICE buffer (kernel-only timing, or a consumer that
+ * stays on the GPU).  *out_dev is valid until the next call on e. */
+int ct_rmsd_rows_device(ct_engine* e, int64_t row_begin, int64_t row_end, const double** out_dev,
+                        ct_stats* stats);
+/* Copy entries [offset, offset+count) of the last device slab to host memory. */
+int ct_copy_slab(ct_engine* e, int64_t offset, int64_t count, double* out);
+
+/* Whole matrix in one call = build_distance_matrix (distmat.py:44-78): load + all rows. */
+int ct_rmsd_condensed(ct_engine* e, const double* coords, const int32_t* atomic_nums, int64_t M, int32_t N,
+                      const ct_opts* opts, double* out, ct_stats* stats);
+
+/* Debug / parity aid (not in the reference, which never returns the permutation): value and composite
+ * atom permutation (perm[k] = kept-atom index of frame j that ends at position k) for explicit pairs,
+ * through the per-pair kernel whatever the mode.  pairs = [n_pairs][2] (i, j), i < j. */
+int ct_pair_values(ct_engine* e, const int64_t* pairs, int64_t n_pairs, double* values, int32_t* perms /* [n_pairs][K] or NULL */,
+                   ct_stats* stats);
+
+int ct_get_stats(const ct_engine* e, ct_stats* stats);
+const char* ct_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,289 @@
+"""GPU parity tests (run on the B200 box): the CUDA engine, called through the C ABI, against
+  * the reference's own golden vector (test/ref/test_distmat.npy, abs 1e-8 like test/test_distmat.py),
+  * the vectors the UNMODIFIED reference produced over import shims (tests/golden/reference_vectors.json),
+  * the CPU oracle on seeded synthetic frames,
+and through size-independent properties at BASELINE.json's full sizes.
+Tolerance: |dRMSD| <= 1e-6 A (north star); the observed error is asserted much tighter where the
+arithmetic allows it."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.helpers import condensed_index, engine_opts, oracle_pairs, oracle_rows
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-6
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from clusttraj_b200 import _engine
+
+    return _engine.Engine(0)
+
+
+def _xyz(golden_dir, name):
+    from clusttraj_b200.xyz import read_xyz
+
+    atoms, coords = read_xyz(os.path.join(golden_dir, name))
+    return atoms[0], coords
+
+
+def _full(eng, atoms, coords, **kw):
+    eng.load_frames(coords, atoms, engine_opts(**kw))
+    out, st = eng.rmsd_rows(0, len(coords))
+    return out.copy(), st
+
+
+def test_reference_golden_vector(eng, golden_dir, ref_golden_distmat):
+    atoms, coords = _xyz(golden_dir, "ref_testtraj.xyz")
+    got, st = _full(eng, atoms, coords, noh=True, ns=17)
+    assert got.shape == (3,)
+    assert np.abs(got - ref_golden_distmat).max() < 1e-8
+    assert st["launches"] >= 1 and st["kept_atoms"] == 15
+
+
+@pytest.mark.parametrize("dataset", ["testtraj", "synth_solv", "synth_plain"])
+def test_all_modes_against_unmodified_reference(eng, golden_dir, reference_vectors, dataset):
+    ds = reference_vectors[dataset]
+    atoms, coords = _xyz(golden_dir, ds["trajfile"])
+    worst = 0.0
+    for name, mode in ds["modes"].items():
+        noh, do_reorder, rs, ns, ws, excl, fk = mode["args"]
+        got, _ = _full(eng, atoms, coords, noh=noh, reorder=do_reorder, rs=rs, ns=ns, ws=ws, excl=excl, fk=fk)
+        assert got.shape == mode["values"].shape, name
+        err = np.abs(got - mode["values"]).max()
+        worst = max(worst, err)
+        assert err <= TOL, (name, err)
+        if not do_reorder:
+            assert err <= 1e-9, (name, err)
+    print(f"{dataset}: worst |dRMSD| = {worst:.3e}")
+
+
+def test_drop_in_entry_points(golden_dir, ref_golden_distmat, tmp_path):
+    """The reference's own test_distmat.py, against this package's entry points."""
+    from clusttraj_b200.distmat import build_distance_matrix, compute_distmat_line, get_distmat
+    from clusttraj_b200.io import ClustOptions
+    from clusttraj_b200.xyz import read_xyz
+
+    traj = os.path.join(golden_dir, "ref_testtraj.xyz")
+    opt = ClustOptions(trajfile=traj, no_hydrogen=True, solute_natoms=17, reorder_alg=None, reorder=False,
+                       reorder_solvent_only=False, weight_solute=None, reorder_excl=np.asarray([], np.int32),
+                       final_kabsch=False, n_workers=1, input_distmat=False,
+                       distmat_name=str(tmp_path / "distmat.npy"), method="ward", min_rmsd=1.0)
+    d = get_distmat(opt)
+    assert d.dtype == np.float64 and d.flags.c_contiguous and d.flags.writeable
+    assert np.abs(d - ref_golden_distmat).max() < 1e-8
+    opt.update({"input_distmat": True})
+    assert np.abs(get_distmat(opt) - ref_golden_distmat).max() < 1e-8
+    assert np.abs(build_distance_matrix(opt) - ref_golden_distmat).max() < 1e-8
+    atoms, coords = read_xyz(traj)
+    line = compute_distmat_line(0, (atoms[0], coords[0]), traj, True, None, False, 17, None,
+                                np.asarray([], np.int32), False)
+    assert len(line) == 2
+    assert np.abs(np.array(line) - ref_golden_distmat[:2]).max() < 1e-8
+    line = compute_distmat_line(0, (atoms[0], coords[0]), traj, True, None, False, 17, 0.8,
+                                np.asarray([], np.int32), True)
+    assert len(line) == 2  # test_distmat.py:41-67 checks only the shape of the -ws --final-kabsch row
+
+
+@pytest.mark.parametrize("M,N,kw", [
+    (700, 100, dict()),
+    (333, 57, dict(noh=True)),
+    (260, 64, dict(ns=20)),
+    (200, 301, dict(noh=True, ns=31)),
+])
+def test_kabsch_modes_vs_oracle(eng, M, N, kw):
+    from clusttraj_b200.synth import make_trajectory
+
+    atoms, coords = make_trajectory(M, N, seed=1234 + M)
+    got, st = _full(eng, atoms, coords, **kw)
+    rows = sorted({0, 1, 2, 31, 32, 33, 63, 64, M // 2, M - 3, M - 2})
+    want = oracle_rows(atoms, coords, rows, **kw)
+    pos = 0
+    worst = 0.0
+    for r in rows:
+        n = M - 1 - r
+        lo = condensed_index(M, r, r + 1)
+        err = np.abs(got[lo: lo + n] - want[pos: pos + n]).max()
+        worst = max(worst, err)
+        pos += n
+    print(f"M={M} N={N} {kw}: worst |dRMSD| = {worst:.3e}, flagged = {st['flagged']}")
+    assert worst <= 1e-9
+    assert st["flagged"] >= 1  # frames 1, 2 duplicate frame 0: the near-duplicate path was exercised
+    assert np.isfinite(got).all() and (got >= 0).all()
+
+
+def test_exact_duplicates_and_mirror(eng):
+    """RMSD = 0 edge (cancellation in G_i + G_j - 2 lambda) and the det < 0 (mirror image) edge."""
+    rng = np.random.default_rng(5)
+    base = rng.normal(0, 12.0, size=(300, 3))
+    th = 0.7
+    Rz = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1.0]])
+    frames = np.stack([base, base @ Rz.T + 3.0, base * np.array([1, 1, -1.0]), base + 1e-7 * rng.normal(size=base.shape),
+                       rng.normal(0, 12.0, size=(300, 3))])
+    atoms = np.full(300, 6, np.int32)
+    got, st = _full(eng, atoms, frames)
+    want = oracle_rows(atoms, frames, range(5))
+    assert np.abs(got - want).max() <= 1e-9, np.abs(got - want)
+    assert got[0] < 1e-7  # rotated+translated duplicate
+    assert st["flagged"] >= 2
+
+
+def test_fixup_list_overflow_path(golden_dir):
+    """Force the flagged-pair list to overflow: the marker/scan path must give the same values."""
+    from clusttraj_b200 import _engine
+
+    rng = np.random.default_rng(9)
+    base = rng.normal(0, 5.0, size=(40, 3))
+    frames = np.stack([base + 1e-9 * rng.normal(size=base.shape) for _ in range(70)] +
+                      [rng.normal(0, 5.0, size=(40, 3)) for _ in range(30)])
+    atoms = np.full(40, 6, np.int32)
+    os.environ["CLUSTTRAJ_B200_FIX_CAPACITY"] = "7"
+    try:
+        small = _engine.Engine(0)
+    finally:
+        del os.environ["CLUSTTRAJ_B200_FIX_CAPACITY"]
+    small.load_frames(frames, atoms, engine_opts())
+    got, st = small.rmsd_rows(0, 100)
+    assert st["flagged"] >= 70 * 69 // 2
+    want = oracle_rows(atoms, frames, [0, 1, 50, 69, 70, 98])
+    pos = 0
+    for r in [0, 1, 50, 69, 70, 98]:
+        n = 99 - r
+        lo = condensed_index(100, r, r + 1)
+        assert np.abs(got[lo: lo + n] - want[pos: pos + n]).max() <= 1e-9
+        pos += n
+    assert (got >= 0).all()
+    small.close()
+
+
+@pytest.mark.parametrize("kw", [
+    dict(reorder=True),
+    dict(reorder=True, ns=12),
+    dict(reorder=True, ns=12, rs=True),
+    dict(reorder=True, ns=12, fk=True),
+    dict(reorder=True, ns=12, ws=0.6),
+    dict(reorder=True, ns=12, noh=True),
+])
+def test_hungarian_permutations_identical(eng, kw):
+    """Identical permutation on non-degenerate Hungarian reorders + value parity."""
+    from clusttraj_b200.synth import make_solute_solvent
+
+    atoms, coords = make_solute_solvent(24, n_solute=12, n_solvent_mol=40, seed=77, box=9.0)
+    pairs = [(i, j) for i in range(0, 24, 5) for j in range(i + 1, 24, 3)]
+    eng.load_frames(coords, atoms, engine_opts(**kw))
+    vals, perms, st = eng.pair_values(pairs, want_perms=True)
+    want_v, want_p = oracle_pairs(atoms, coords, pairs, **kw)
+    assert np.abs(vals - want_v).max() <= TOL
+    assert np.abs(vals - want_v).max() <= 1e-9
+    assert (perms == want_p).all()
+    assert st["lsap_steps"] > 0
+    full, _ = eng.rmsd_rows(0, 24)
+    for (i, j), v in zip(pairs, vals):
+        assert full[condensed_index(24, i, j)] == v
+
+
+def test_hungarian_config4_shape_sample(eng):
+    """BASELINE config 4 shape (60 solute + 300 solvent atoms, -ns 60 -e) on a few frames."""
+    from clusttraj_b200.synth import make_solute_solvent
+
+    atoms, coords = make_solute_solvent(12, n_solute=60, n_solvent_mol=100, seed=20250604)
+    kw = dict(reorder=True, ns=60)
+    pairs = [(0, 1), (0, 7), (3, 4), (5, 11), (10, 11)]
+    eng.load_frames(coords, atoms, engine_opts(**kw))
+    vals, perms, _ = eng.pair_values(pairs, want_perms=True)
+    want_v, want_p = oracle_pairs(atoms, coords, pairs, **kw)
+    assert np.abs(vals - want_v).max() <= 1e-9
+    assert (perms == want_p).all()
+
+
+def test_row_slabs_concatenate(eng):
+    from clusttraj_b200.synth import make_trajectory
+
+    atoms, coords = make_trajectory(500, 40, seed=3)
+    full, _ = _full(eng, atoms, coords)
+    parts = [eng.rmsd_rows(a, b)[0].copy() for a, b in [(0, 17), (17, 64), (64, 65), (65, 333), (333, 500)]]
+    assert np.array_equal(np.concatenate(parts), full)
+    dev_ptr, n, _ = eng.rmsd_rows_device(100, 200)
+    assert dev_ptr and n == eng.rows_pairs(100, 200)
+    lo = condensed_index(500, 100, 101)
+    assert np.array_equal(eng.copy_slab(0, n), full[lo: lo + n])
+
+
+def test_streaming_chunks_match_single_chunk():
+    from clusttraj_b200 import _engine
+    from clusttraj_b200.synth import make_trajectory
+
+    atoms, coords = make_trajectory(900, 30, seed=8)
+    os.environ["CLUSTTRAJ_B200_CHUNK_ENTRIES"] = "20000"
+    try:
+        chunky = _engine.Engine(0)
+    finally:
+        del os.environ["CLUSTTRAJ_B200_CHUNK_ENTRIES"]
+    one = _engine.Engine(0)
+    for e in (chunky, one):
+        e.load_frames(coords, atoms, engine_opts())
+    a, sa = chunky.rmsd_rows(0, 900, _engine.pinned_empty(900 * 899 // 2))
+    b, sb = one.rmsd_rows(0, 900)
+    assert sa["launches"] > sb["launches"]
+    assert np.array_equal(a, b)
+    chunky.close(); one.close()
+
+
+def test_identical_cluster_labels(eng):
+    """SciPy linkage on the engine's matrix gives the labels the oracle's matrix gives."""
+    import scipy.cluster.hierarchy as hcl
+    from clusttraj_b200.synth import make_trajectory
+
+    atoms, coords = make_trajectory(160, 30, seed=21, n_modes=5)
+    got, _ = _full(eng, atoms, coords)
+    want = oracle_rows(atoms, coords, range(160), n_workers=4)
+    assert np.abs(got - want).max() <= 1e-9
+    for method in ("average", "ward", "complete"):
+        Zg, Zw = hcl.linkage(got, method), hcl.linkage(want, method)
+        for t in (0.5, 1.0, 2.0):
+            assert (hcl.fcluster(Zg, t, criterion="distance") == hcl.fcluster(Zw, t, criterion="distance")).all()
+
+
+def test_config2_full_size_properties(eng):
+    """BASELINE config 2 (20k frames x 100 atoms, plain) through size-independent properties."""
+    from clusttraj_b200.synth import make_trajectory
+
+    M, N = 20000, 100
+    atoms, coords = make_trajectory(M, N, seed=20250602)
+    eng.load_frames(coords, atoms, engine_opts())
+    out, st = eng.rmsd_rows(0, M, __import__("clusttraj_b200")._engine.pinned_empty(M * (M - 1) // 2))
+    assert st["pairs"] == M * (M - 1) // 2
+    assert np.isfinite(out).all() and out.min() >= 0.0
+    # duplicates of frame 0 (frames 1, 2) up to the 5-decimal rounding; mirrored last frame is NOT a duplicate
+    assert out[condensed_index(M, 0, 1)] < 5e-5 and out[condensed_index(M, 1, 2)] < 5e-5
+    assert out[condensed_index(M, 0, M - 1)] > 0.1
+    # rows against a duplicated reference frame are identical up to the rounding of the input
+    r0 = out[condensed_index(M, 0, 3): condensed_index(M, 0, 3) + 2000]
+    r1 = out[condensed_index(M, 1, 3): condensed_index(M, 1, 3) + 2000]
+    assert np.abs(r0 - r1).max() < 1e-4
+    # sampled entries against the oracle
+    rng = np.random.default_rng(0)
+    pairs = [(int(min(a, b)), int(max(a, b))) for a, b in rng.integers(0, M, size=(300, 2)) if a != b]
+    want, _ = oracle_pairs(atoms, coords, pairs)
+    got = np.array([out[condensed_index(M, i, j)] for i, j in pairs])
+    assert np.abs(got - want).max() <= 1e-9
+    # triangle inequality of the minimum RMSD on sampled triples
+    tri = rng.integers(0, M, size=(2000, 3))
+    for a, b, c in tri:
+        a, b, c = sorted((int(a), int(b), int(c)))
+        if a == b or b == c:
+            continue
+        ab, bc, ac = (out[condensed_index(M, a, b)], out[condensed_index(M, b, c)], out[condensed_index(M, a, c)])
+        assert ac <= ab + bc + 1e-9 and ab <= ac + bc + 1e-9 and bc <= ab + ac + 1e-9
+    # invariance: the same frames rigidly moved give the same matrix rows
+    th = 1.1
+    Rx = np.array([[1, 0, 0], [0, np.cos(th), -np.sin(th)], [0, np.sin(th), np.cos(th)]])
+    sub = coords[:2048] @ Rx.T + np.array([5.0, -3.0, 2.0])
+    eng.load_frames(sub, atoms, engine_opts())
+    moved, _ = eng.rmsd_rows(0, 64)
+    eng.load_frames(coords[:2048], atoms, engine_opts())
+    still, _ = eng.rmsd_rows(0, 64)
+    assert np.abs(moved - still).max() < 1e-9
