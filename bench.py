@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""Benchmark of the all-pairs minimum-RMSD hot path (BASELINE.json metric: RMSD pairs/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg2|cfg3|cfg4|cfg5]
+
+One "step" = one pass of the hot path over one synthetic trajectory: centre/pack (K1), the DMMA Gram
+kernel with its fused RMSD epilogue (K2) and the fix-up of flagged pairs, producing the rank's slab of the
+condensed matrix.  N = 1 runs BASELINE config 2 (20k frames x 100 atoms, plain Kabsch).  N > 1 (torchrun,
+one rank per GPU) shards ONE matrix over the ranks by equal-area row slabs with no collective on the data
+path; the frame count grows with sqrt(N) so that every GPU keeps config 2's pair count ("weak" scaling).
+
+  value : whole-job pairs/s with the coordinates already resident in HBM, output left in HBM.
+  e2e   : the same through the C ABI with HOST buffers: pinned host coordinates -> GPU -> condensed slab
+          streamed to pinned host memory, all inside the timed region.
+  --impl reference : the CPU oracle (restatement of the reference's rmsd-package path) on all host cores,
+          on a bounded sample of rows of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (frames, atoms, engine/oracle options, description)
+    "cfg2": (20000, 100, dict(), "synthetic 20k frames x 100 atoms, plain Kabsch"),
+    "cfg3": (50000, 300, dict(noh=True), "synthetic 50k frames x 300 atoms, -n hydrogen mask"),
+    "cfg5": (100000, 300, dict(), "synthetic 100k frames x 300 atoms, plain Kabsch"),
+    "cfg4": (10000, 360, dict(ns=60, reorder=True), "synthetic 10k frames, 60 solute + 300 solvent atoms, -ns 60 -e hungarian"),
+}
+FP64_PEAK_FILE = os.path.join(ROOT, "profiles", "r01_fp64_peak_microbench.json")
+
+
+def make_workload(name, n_frames):
+    from clusttraj_b200.synth import make_solute_solvent, make_trajectory
+
+    _, n_atoms, kw, _ = WORKLOADS[name]
+    if name == "cfg4":
+        return make_solute_solvent(n_frames, n_solute=60, n_solvent_mol=100, seed=20250604)
+    return make_trajectory(n_frames, n_atoms, seed=20250600 + int(name[-1]))
+
+
+def kept_atoms(atoms, kw):
+    return int((atoms != 1).sum()) if kw.get("noh") else len(atoms)
+
+
+def engine_opts(kw):
+    from clusttraj_b200 import _engine
+
+    return _engine.make_opts(no_hydrogen=kw.get("noh", False), solute_natoms=kw.get("ns"),
+                             reorder=kw.get("reorder", False), reorder_solvent_only=kw.get("rs", False),
+                             final_kabsch=kw.get("fk", False), weight_solute=kw.get("ws"))
+
+
+# --------------------------------------------------------------------------------------------- CPU oracle
+def cpu_oracle_rate(atoms, coords, kw, rows, cores):
+    """pairs/s of the oracle (oracle/distmat_restated.py) over `rows` x all later columns on `cores` processes."""
+    from oracle import distmat_restated as O
+    from oracle import rmsd_restated as R
+
+    for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[v] = "1"  # README.md:126-134 of the reference recommends single-threaded BLAS per worker
+    t0 = time.perf_counter()
+    vec = O.build_distance_matrix(atoms, coords, noh=kw.get("noh", False),
+                                  reorder=R.reorder_hungarian if kw.get("reorder") else None,
+                                  reorder_solvent_only=kw.get("rs", False), nsatoms=kw.get("ns"),
+                                  weight_solute=kw.get("ws"), final_kabsch=kw.get("fk", False), rows=rows,
+                                  n_workers=cores)
+    dt = time.perf_counter() - t0
+    return len(vec) / dt, len(vec), dt, vec
+
+
+def sample_rows(M, n_rows, budget_pairs, seed=0):
+    """Random rows whose total length stays near the pair budget (bounded CPU sample)."""
+    rng = np.random.default_rng(seed)
+    rows, total = [], 0
+    for r in rng.permutation(M - 1):
+        rows.append(int(r))
+        total += M - 1 - int(r)
+        if len(rows) >= n_rows or total >= budget_pairs:
+            break
+    return sorted(rows)
+
+
+# --------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.tmp,
+                                         stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, power, reasons, smmax = [], [], set(), None
+        for line in self.tmp.read().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smmax = float(f[2]); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.tmp.name)
+        if sm:
+            # "under load" = samples in the upper half of the power range seen during the timed region
+            p = np.array(power); s = np.array(sm)
+            busy = s[p >= (p.min() + p.max()) / 2] if p.max() > p.min() else s
+            out.update(sm_mhz=float(np.median(busy)), sm_max_mhz=smmax, reasons=sorted(reasons), samples=len(sm),
+                       power_w_max=float(p.max()))
+        return out
+
+
+# --------------------------------------------------------------------------------------------- arms
+def run_reference_arm(args, rank, world):
+    """The reference's CPU implementation of the path (oracle port; the as-shipped package cannot run here:
+    its rmsd / openbabel dependencies are not installable offline) on all host cores, bounded sample per step."""
+    if rank != 0:
+        return
+    from oracle import distmat_restated as O
+
+    name = args.workload
+    M0, _, kw, desc = WORKLOADS[name]
+    M = int(round(M0 * np.sqrt(world)))
+    cores = O.cpu_count()
+    atoms, coords = make_workload(name, M)
+    budget = 250_000 if not kw.get("reorder") else 12_000
+    times, pairs = [], 0
+    for step in range(args.warmup + args.steps):
+        rows = sample_rows(M, 4 * cores, budget, seed=step)
+        rate, n, dt, _ = cpu_oracle_rate(atoms, coords, kw, rows, cores)
+        if step >= args.warmup:
+            times.append(dt); pairs += n
+    value = pairs / sum(times)
+    line = {
+        "impl": "reference", "metric": "rmsd_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{name}: {desc}; M={M}", "frames": M, "atoms": int(coords.shape[1]),
+                   "mode": kw, "sample": f"{4 * cores} random rows x all later columns per step (<= {budget} pairs)"},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
+                         "sample": f"{pairs} pairs over {args.steps} steps; frames held in memory "
+                                   "(the reference re-parses the file per pair)"},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200_arm(args, rank, world, local_rank):
+    import torch
+
+    from clusttraj_b200 import _engine
+    from clusttraj_b200.distmat import slab_bounds
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    name = args.workload
+    M0, _, kw, desc = WORKLOADS[name]
+    M = int(round(M0 * np.sqrt(world)))  # weak scaling: every GPU keeps the single-GPU pair count
+    atoms, coords = make_workload(name, M)
+    N = coords.shape[1]
+    K = kept_atoms(atoms, kw)
+    cuts = slab_bounds(M, world)
+    r0, r1 = cuts[rank], cuts[rank + 1]
+    eng = _engine.Engine(local_rank)
+    opts = engine_opts(kw)
+    my_pairs = int(eng._lib.ct_rows_pairs(M, r0, r1))
+
+    pinned_in = _engine.pinned_empty(coords.size).reshape(coords.shape)
+    pinned_in[...] = coords
+    pinned_out = _engine.pinned_empty(my_pairs)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- kernel-only leg: coordinates resident in HBM, slab left in HBM -------------------------------
+    eng.load_frames(pinned_in, atoms, opts)
+    launches = 0
+    gram_ms, step_ms = [], []
+    clocks = None
+    for step in range(args.warmup + args.steps):
+        flush.zero_()
+        if step == args.warmup:
+            barrier()
+            sampler = ClockSampler(local_rank) if rank == 0 else None
+            wall0 = time.perf_counter()
+        pack_ms = eng.pack_resident()
+        _, _, st = eng.rmsd_rows_device(r0, r1)
+        if step >= args.warmup:
+            step_ms.append(pack_ms + st["kernel_ms"])
+            gram_ms.append(st["gram_ms"] if st["gram_ms"] > 0 else st["pair_ms"])
+            launches += int(st["launches"]) + 2
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - wall0)
+    if rank == 0 and sampler is not None:
+        clocks = sampler.stop()
+    flagged = int(st["flagged"])
+    dev_ms = max_over_ranks(sum(step_ms))          # device time of the K steps, max over ranks
+    total_pairs = sum_over_ranks(float(my_pairs))
+    value = total_pairs * args.steps / (dev_ms * 1e-3)
+
+    # ---- end-to-end leg: host buffers in, host buffers out, through the C ABI -------------------------
+    e2e_ms = []
+    for step in range(args.warmup + args.steps):
+        flush.zero_()
+        barrier()
+        t0 = time.perf_counter()
+        eng.load_frames(pinned_in, atoms, opts)           # H2D of the step's input + K1
+        _, st2 = eng.rmsd_rows(r0, r1, pinned_out)        # K2 + fix-up, slab streamed to pinned host memory
+        dt = 1e3 * (time.perf_counter() - t0)
+        if step >= args.warmup:
+            e2e_ms.append(dt)  # host wall clock around the two synchronous C-ABI calls
+    barrier()
+    e2e_total = max_over_ranks(sum(e2e_ms))
+    e2e_value = total_pairs * args.steps / (e2e_total * 1e-3)
+    checksum = float(pinned_out[: min(my_pairs, 1 << 20)].sum())
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ----------------------------------------------------------------
+    peak_tf, peak_src = 37.1, "fallback: nominal B200 FP64"
+    if os.path.exists(FP64_PEAK_FILE):
+        with open(FP64_PEAK_FILE) as fh:
+            peak_tf = float(json.load(fh)["dmma884_sustained_tflops"])
+        peak_src = "measured DMMA m8n8k4 microbenchmark on this pool (profiles/r01_fp64_peak_microbench.json); " \
+                   "MEASURED_PEAKS.json has no FP64 entry"
+    mean_gram_ms = float(np.mean(gram_ms))
+    if kw.get("reorder"):
+        # per-pair kernel: HBM traffic 2 frames in + 8 B out per pair, latency bound
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
+            os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0}
+        bytes_per_launch = my_pairs * (2 * K * 24 + 8)
+        achieved = bytes_per_launch / (mean_gram_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": achieved / peaks["hbm_gbs"], "traffic": None, "kernel": "pair_kernel",
+                    "note": "latency/shared-memory bound assignment solver; HBM figure reported for completeness"}
+    else:
+        flop_per_launch = 18.0 * K * my_pairs
+        achieved = flop_per_launch / (mean_gram_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                    "frac": achieved / peak_tf, "traffic": None, "kernel": "gram_rmsd_kernel",
+                    "flop_per_pair": 18 * K, "pairs_per_launch": my_pairs, "launch_ms": mean_gram_ms,
+                    "peak_source": peak_src,
+                    "note": "FP64 tensor pipe (DMMA.8x8x4); algorithmic flops = 18*K per output pair, epilogue "
+                            "and padded/diagonal-block work not counted"}
+    traffic_file = os.path.join(ROOT, "profiles", "r01_gram_traffic.json")
+    if os.path.exists(traffic_file) and not kw.get("reorder") and name == "cfg2":
+        roofline["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+
+    # ---- CPU baseline (bounded sample of the same workload, rank 0, N = 1 only) ---------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import distmat_restated as O
+
+        cores = O.cpu_count()
+        budget = 1_500_000 if not kw.get("reorder") else 16_000
+        rows = sample_rows(M, 8 * cores, budget)
+        rate, n, dt, vec = cpu_oracle_rate(atoms, coords, kw, rows, cores)
+        # the sampled rows double as a parity check of the bench's own output
+        eng.load_frames(pinned_in, atoms, opts)
+        worst = 0.0
+        pos = 0
+        for r in rows:
+            line, _ = eng.rmsd_rows(r, r + 1)
+            worst = max(worst, float(np.abs(line - vec[pos: pos + len(line)]).max()))
+            pos += len(line)
+        cpu = {"value": rate, "unit": "pairs/s", "cores": cores, "kind": "port",
+               "sample": f"{len(rows)} random rows x all later columns = {n} pairs in {dt:.1f} s; oracle port with "
+                         "frames in memory, multiprocessing.Pool over rows like distmat.py:73-76",
+               "max_abs_diff_vs_gpu": worst}
+
+    line = {
+        "metric": "rmsd_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{name}: {desc}; M={M} (= {M0} x sqrt(n_gpus)), N={N}, K={K}", "frames": M,
+                   "atoms": int(N), "kept_atoms": K, "mode": kw, "pairs_total": int(total_pairs),
+                   "sharding": "equal-area row slabs, no collective on the data path",
+                   "l2": "256 MiB buffer zeroed between steps (L2 flush); the 1.6 GB output also exceeds L2"},
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(coords.nbytes + atoms.nbytes),
+                "d2h_bytes_per_step": int(8 * my_pairs), "ms_per_step": e2e_total / args.steps,
+                "note": "ct_load_frames (pinned H2D + K1) + ct_rmsd_rows (K2, fix-up, chunked D2H into pinned "
+                        "host memory, overlapped)"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "wall_ms_timed_region": wall_ms,
+        "flagged_pairs_per_step": flagged,
+        "checksum": checksum,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under it, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29517"), __file__] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+    else:
+        run_b200_arm(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -42,7 +42,7 @@ class ct_stats(C.Structure):
 EXPORTS = [
     "ct_version", "ct_device_count", "ct_last_error", "ct_engine_create", "ct_engine_destroy", "ct_host_alloc",
     "ct_host_free", "ct_load_frames", "ct_rows_pairs", "ct_rmsd_rows", "ct_rmsd_rows_device", "ct_copy_slab",
-    "ct_rmsd_condensed", "ct_pair_values", "ct_get_stats",
+    "ct_rmsd_condensed", "ct_pair_values", "ct_get_stats", "ct_pack_resident",
 ]
 
 _lib = None
@@ -85,6 +85,7 @@ def load_library(build_if_missing=True):
                                           C.c_void_p, P(ct_stats)]
         lib.ct_pair_values.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, P(ct_stats)]
         lib.ct_get_stats.argtypes = [C.c_void_p, P(ct_stats)]
+        lib.ct_pack_resident.argtypes = [C.c_void_p, P(ct_stats)]
         _lib = lib
         return lib
 
@@ -158,6 +159,12 @@ class Engine:
                                              coords.shape[1], C.byref(opts)), "ct_load_frames")
         self.M, self.N = coords.shape[0], coords.shape[1]
         self.K = int(self.stats()["kept_atoms"])
+
+    def pack_resident(self):
+        """Re-run K1 (centre + pack) on the coordinates already on the GPU; returns its device time in ms."""
+        st = ct_stats()
+        self._check(self._lib.ct_pack_resident(self._h, C.byref(st)), "ct_pack_resident")
+        return st.pack_ms
 
     def rows_pairs(self, row_begin, row_end):
         return int(self._lib.ct_rows_pairs(self.M, row_begin, row_end))

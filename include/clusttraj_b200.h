@@ -76,6 +76,10 @@ int ct_host_free(void* ptr);
 int ct_load_frames(ct_engine* e, const double* coords, const int32_t* atomic_nums, int64_t M, int32_t N,
                    const ct_opts* opts);
 
+/* Re-run the centre/pack kernels (K1) on the coordinates already resident on the GPU (kernel-only
+ * timing of the whole hot path without the host->device copy). */
+int ct_pack_resident(ct_engine* e, ct_stats* stats);
+
 /* Number of matrix entries in rows [row_begin,row_end): sum over i of (M-1-i). */
 int64_t ct_rows_pairs(int64_t M, int64_t row_begin, int64_t row_end);
 
