@@ -218,7 +218,7 @@ int ct_load_frames(ct_engine* e, const double* coords, const int32_t* atomic_num
 
     e->M = M; e->N = N; e->K = K; e->natoms = natoms;
     e->m_pad = (int)((M + 63) / 64 * 64);
-    const int k_pad = (K + ct::KC - 1) / ct::KC * ct::KC;
+    const int k_pad = (K + 3) / 4 * 4;  // the Gram kernel handles a half-filled last stage
     e->kq_total = k_pad / 4;
 
     int rc;
@@ -276,7 +276,7 @@ static int compute_rows_async(ct_engine* e, int row_begin, int row_end, double* 
         CT_CUDA(e, cudaMemsetAsync(e->d_fix_count, 0, sizeof(unsigned int), e->s_compute));
         ct::GramParams p;
         p.packed = e->d_packed; p.G = e->d_G; p.out = dst; p.idx_base = idx_base; p.M = (int)e->M;
-        p.kq_total = e->kq_total; p.n_stage = e->kq_total / ct::KQ_STAGE;
+        p.kq_total = e->kq_total; p.n_stage = (e->kq_total + ct::KQ_STAGE - 1) / ct::KQ_STAGE;
         p.row_begin = row_begin; p.row_end = row_end;
         p.inv_k = 1.0 / (double)e->K; p.flag_rel = e->flag_rel;
         p.fix.pairs = e->d_fix_pairs; p.fix.count = e->d_fix_count; p.fix.capacity = e->fix_cap;

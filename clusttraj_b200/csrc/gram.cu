@@ -12,8 +12,9 @@
 // Data movement: cp.async.bulk (TMA, 1-D) brings one KC-atom stage of each 32-frame tile as a single
 // contiguous 6 KiB run into a STAGES-deep shared-memory ring guarded by mbarriers; loads run STAGES-1
 // stages ahead across block boundaries, so the epilogue of one block overlaps the first loads of the
-// next.  Results are staged through shared memory and leave as 256 B-coalesced row segments of the
-// condensed vector.
+// next.  Warps never meet at a block-wide barrier in the steady state: each warp releases a ring slot
+// on an "empty" mbarrier and thread 0 refills it PREFETCH stages ahead.  Every lane stores its own
+// pairs straight into the condensed vector (the row segments of neighbouring lanes/warps merge in L2).
 #include "common.cuh"
 #include "solve3x3.cuh"
 
@@ -28,8 +29,9 @@ struct GramCfg {
     static constexpr int THREADS = 32 * WI * WJ;
     static constexpr int STAGE_DOUBLES = (NTI + NTJ) * TILE_STAGE_DOUBLES;
     static constexpr int STAGE_BYTES = STAGE_DOUBLES * 8;
-    static constexpr int OUT_STRIDE = TJ + 8;  // doubles; +8 keeps 16 B stores conflict-free per quarter-warp
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + TI * OUT_STRIDE * 8 + STAGES * 8 + 16;
+    static constexpr int PREFETCH = STAGES - 2;  // a slot is refilled two consumer iterations after its use
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 16;
+    static_assert(STAGES >= 3, "need at least three ring slots");
     static_assert(TI % FT == 0 && TJ % FT == 0, "block sides must be whole packed tiles");
     static_assert(TJ % TI == 0, "column side must be a multiple of the row side");
 };
@@ -59,15 +61,15 @@ __global__ void __launch_bounds__(Cfg::THREADS, (Cfg::THREADS <= 256) ? 2 : 1) g
     constexpr int MA = Cfg::MA, MB = Cfg::MB, STAGES = Cfg::STAGES, TI = Cfg::TI, TJ = Cfg::TJ;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* stage_buf = reinterpret_cast<double*>(smem_raw);
-    double* outs = stage_buf + STAGES * Cfg::STAGE_DOUBLES;
-    uint64_t* full = reinterpret_cast<uint64_t*>(outs + TI * Cfg::OUT_STRIDE);
+    uint64_t* full = reinterpret_cast<uint64_t*>(stage_buf + STAGES * Cfg::STAGE_DOUBLES);
+    uint64_t* empty = full + STAGES;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wi = warp % Cfg::WI, wj = warp / Cfg::WI;
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], Cfg::THREADS / 32); }
         fence_barrier_init();
     }
     __syncthreads();
@@ -77,6 +79,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, (Cfg::THREADS <= 256) ? 2 : 1) g
     const int ti_end = (last_row + TI - 1) / TI;
     const int ntj = (p.M + TJ - 1) / TJ;
     const int n_stage = p.n_stage;
+    const bool odd_tail = (p.kq_total & 1) != 0;
     const size_t tile_doubles = (size_t)p.kq_total * 3 * FT * 4;  // one 32-frame tile, all atoms
 
     // ---- producer state (thread 0 only): runs STAGES-1 pipeline stages ahead of the consumers -----
@@ -87,22 +90,25 @@ __global__ void __launch_bounds__(Cfg::THREADS, (Cfg::THREADS <= 256) ? 2 : 1) g
     auto issue_load = [&]() {
         if (!lw.valid()) return;
         const int slot = lg % STAGES;
+        if (lg >= STAGES) mbar_wait(&empty[slot], ((lg / STAGES) - 1) & 1);  // every warp released the slot
         double* dst = stage_buf + slot * Cfg::STAGE_DOUBLES;
-        mbar_expect_tx(&full[slot], Cfg::STAGE_BYTES);
+        // the last stage of a block holds a single k4 group when the padded atom count is 4 (mod 8)
+        const uint32_t bytes = (lk == n_stage - 1 && odd_tail) ? TILE_STAGE_BYTES / 2 : TILE_STAGE_BYTES;
+        mbar_expect_tx(&full[slot], bytes * (Cfg::NTI + Cfg::NTJ));
         const size_t koff = (size_t)lk * TILE_STAGE_DOUBLES;
 #pragma unroll
         for (int t = 0; t < Cfg::NTI; ++t)
             bulk_g2s(dst + t * TILE_STAGE_DOUBLES, p.packed + (size_t)(lw.ti * Cfg::NTI + t) * tile_doubles + koff,
-                     TILE_STAGE_BYTES, &full[slot]);
+                     bytes, &full[slot]);
 #pragma unroll
         for (int t = 0; t < Cfg::NTJ; ++t)
             bulk_g2s(dst + (Cfg::NTI + t) * TILE_STAGE_DOUBLES,
-                     p.packed + (size_t)(lw.tj * Cfg::NTJ + t) * tile_doubles + koff, TILE_STAGE_BYTES, &full[slot]);
+                     p.packed + (size_t)(lw.tj * Cfg::NTJ + t) * tile_doubles + koff, bytes, &full[slot]);
         ++lg;
         if (++lk == n_stage) { lk = 0; lw.advance(gridDim.x); }
     };
     if (tid == 0) {
-        for (int s = 0; s < STAGES - 1; ++s) issue_load();
+        for (int s = 0; s < Cfg::PREFETCH; ++s) issue_load();
     }
 
     // ---- consumers ------------------------------------------------------------------------------------
@@ -136,12 +142,13 @@ __global__ void __launch_bounds__(Cfg::THREADS, (Cfg::THREADS <= 256) ? 2 : 1) g
 #pragma unroll 1
         for (int k = 0; k < n_stage; ++k, ++g) {
             const int slot = g % STAGES;
+            if (tid == 0) issue_load();  // stage g + PREFETCH
             mbar_wait(&full[slot], (g / STAGES) & 1);
-            __syncthreads();  // every warp has finished stage g-1, whose slot the next load overwrites
-            if (tid == 0) issue_load();
             const double* sb = stage_buf + slot * Cfg::STAGE_DOUBLES;
+            const int nkq = (k == n_stage - 1 && odd_tail) ? 1 : KQ_STAGE;
 #pragma unroll
             for (int kq = 0; kq < KQ_STAGE; ++kq) {
+                if (kq >= nkq) break;
                 double fa[MA][3], fb[MB][3];
 #pragma unroll
                 for (int ma = 0; ma < MA; ++ma)
@@ -161,58 +168,63 @@ __global__ void __launch_bounds__(Cfg::THREADS, (Cfg::THREADS <= 256) ? 2 : 1) g
                             for (int cb = 0; cb < 3; ++cb)
                                 dmma884(acc[ma][mb][ca][cb][0], acc[ma][mb][ca][cb][1], fa[ma][ca], fb[mb][cb]);
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[slot]);  // this warp no longer reads the slot
         }
 
-        // ---- epilogue: each lane owns the 3x3 covariance of 2*MA*MB frame pairs -----------------------
+        // ---- epilogue: each lane owns the 3x3 covariance of NP = 2*MA*MB frame pairs; all of them are
+        // solved in lockstep (see largest_root_lockstep) ---------------------------------------------------
         const int i0 = cw.ti * TI, j0 = cw.tj * TJ;
+        constexpr int NP = 2 * MA * MB;
+        double qa[NP], qb[NP], qd[NP], hg[NP], lam[NP];
 #pragma unroll
         for (int ma = 0; ma < MA; ++ma) {
-            const int il = (wi * MA + ma) * 8 + (lane >> 2);
-            const int i = i0 + il;
-            const double gi = p.G[i];
+            const double gi = p.G[i0 + (wi * MA + ma) * 8 + (lane >> 2)];
 #pragma unroll
             for (int mb = 0; mb < MB; ++mb) {
-                const int jl = (wj * MB + mb) * 8 + 2 * (lane & 3);
-                const double2 gj = *reinterpret_cast<const double2*>(p.G + j0 + jl);
-                double2 res;
+                const double2 gj = *reinterpret_cast<const double2*>(p.G + j0 + (wj * MB + mb) * 8 + 2 * (lane & 3));
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
+                    const int q = (ma * MB + mb) * 2 + e;
                     double s[9];
 #pragma unroll
                     for (int ca = 0; ca < 3; ++ca)
 #pragma unroll
                         for (int cb = 0; cb < 3; ++cb) s[ca * 3 + cb] = acc[ma][mb][ca][cb][e];
-                    const double gs = gi + (e ? gj.y : gj.x);
-                    double a, b, d, lam;
-                    quartic_invariants(s, a, b, d);
-                    const bool ok = largest_root(a, b, d, 0.5 * gs, lam);
-                    const double E = fma(-2.0, lam, gs);
+                    quartic_invariants(s, qa[q], qb[q], qd[q]);
+                    hg[q] = 0.5 * (gi + (e ? gj.y : gj.x));
+                }
+            }
+        }
+        const unsigned okmask = largest_root_lockstep<NP>(qa, qb, qd, hg, lam);
+#pragma unroll
+        for (int ma = 0; ma < MA; ++ma) {
+            const int il = (wi * MA + ma) * 8 + (lane >> 2);
+            const int i = i0 + il;
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb) {
+                const int jl = (wj * MB + mb) * 8 + 2 * (lane & 3);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int q = (ma * MB + mb) * 2 + e;
+                    const double E = 2.0 * (hg[q] - lam[q]);
                     // sqrt(E/K): FP32 rsqrt seed + one FP64 Newton step (relative error ~1e-13)
                     const double v = fmax(E, 0.0) * p.inv_k;
                     const float y = rsqrtf(fmaxf((float)v, 1e-37f));
                     double r = v * (double)y;
                     r = fma(0.5 * (double)y, fma(-r, r, v), r);
                     const int j = j0 + jl + e;
-                    if ((!ok || E < p.flag_rel * gs) && i < j && j < p.M && i >= p.row_begin && i < p.row_end) {
+                    const bool ok = (okmask >> q) & 1u;
+                    if ((!ok || E < 2.0 * p.flag_rel * hg[q]) && i < j && j < p.M && i >= p.row_begin && i < p.row_end) {
                         const unsigned int t = atomicAdd(p.fix.count, 1u);
                         if (t < p.fix.capacity) p.fix.pairs[t] = make_int2(i, j);
                         else r = -1.0;  // list full: mark the entry, the fix-up kernel scans for it
                     }
-                    if (e) res.y = r; else res.x = r;
+                    if (i < j && j < p.M && i >= p.row_begin && i < last_row)
+                        p.out[condensed_row_base(p.M, i) - p.idx_base + (j - i - 1)] = r;
                 }
-                *reinterpret_cast<double2*>(outs + il * Cfg::OUT_STRIDE + jl) = res;
             }
         }
-        __syncthreads();
-        // coalesced write-out: one warp per row segment of the condensed vector
-        for (int r = warp; r < TI; r += Cfg::THREADS / 32) {
-            const int i = i0 + r;
-            if (i < p.row_begin || i >= last_row) continue;
-            const long long base = condensed_row_base(p.M, i) - p.idx_base - i - 1;
-            const int jlo = max(j0, i + 1), jhi = min(j0 + TJ, p.M);
-            for (int j = jlo + lane; j < jhi; j += 32) p.out[base + j] = outs[r * Cfg::OUT_STRIDE + (j - j0)];
-        }
-        // the next block's first stage is separated from these smem reads by the __syncthreads in its k loop
     }
 }
 
@@ -245,8 +257,8 @@ static cudaError_t launch_gram_cfg(const GramParams& p, int sm_count, cudaStream
     return cudaGetLastError();
 }
 
-using GramDefault = GramCfg<4, 2, 1, 2, 4>;   // 32 x 32 frame pairs, 8 warps, 2 CTAs / SM
-using GramWide = GramCfg<4, 4, 1, 2, 4>;      // 32 x 64 frame pairs, 16 warps, 1 CTA / SM
+using GramDefault = GramCfg<4, 2, 1, 2, 6>;   // 32 x 32 frame pairs, 8 warps, 2 CTAs / SM
+using GramWide = GramCfg<4, 4, 1, 2, 5>;      // 32 x 64 frame pairs, 16 warps, 1 CTA / SM
 
 cudaError_t launch_gram(const GramParams& p, int variant, int sm_count, cudaStream_t stream) {
     if (variant == 1) return launch_gram_cfg<GramWide>(p, sm_count, stream);

@@ -81,6 +81,88 @@ __device__ __forceinline__ bool largest_root(double a, double b, double d, doubl
     return ok && (lam == lam);
 }
 
+// The same solve for NP independent pairs held by one thread, advanced in lockstep so that the
+// dependent FP64 chains of different pairs interleave (the FP64 pipe is shared with the DMMAs of the
+// other resident warps, so a single dependent chain is stretched by pipe contention; NP-way ILP hides
+// it).  ok_mask bit p is set when pair p settled.
+template <int NP>
+__device__ __forceinline__ unsigned largest_root_lockstep(const double (&a)[NP], const double (&b)[NP],
+                                                          const double (&d)[NP], const double (&half_g)[NP],
+                                                          double (&lam)[NP]) {
+    float l0[NP], af[NP], df2[NP], bf4[NP], x[NP];
+    unsigned live = 0;  // pairs still iterating
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        const float af0 = (float)a[p];
+        float l = fminf((float)half_g[p], sqrtf(3.0f * af0)) * 1.000001f;
+        if (!(l > 0.0f)) l = 1.0f;  // S == 0: every root is 0; the FP64 check below rejects non-zero a
+        l0[p] = l;
+        const float sc = __frcp_rn(l);
+        const float sc2 = sc * sc;
+        af[p] = af0 * sc2;
+        df2[p] = 2.0f * ((float)d[p] * sc2 * sc);
+        bf4[p] = 4.0f * ((float)b[p] * sc2 * sc2);
+        x[p] = 1.0f;
+        live |= 1u << p;
+    }
+#pragma unroll 1
+    for (int it = 0; it < 14 && live; ++it) {
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            const float t = fmaf(x[p], x[p], -af[p]);
+            const float f = fmaf(t, t, fmaf(-4.0f * df2[p], x[p], -bf4[p]));
+            const float fq = fmaf(x[p], t, -df2[p]);
+            const float step = 0.25f * __fdividef(f, fq);
+            const bool act = (live >> p) & 1u;
+            const bool good = fq > 0.0f;
+            if (act && good) x[p] -= step;
+            if (!good || fabsf(step) <= 3e-7f * x[p]) live &= ~(1u << p);
+        }
+    }
+    double m2d[NP], m4b[NP], step[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        lam[p] = (double)x[p] * (double)l0[p];
+        m2d[p] = -2.0 * d[p];
+        m4b[p] = -4.0 * b[p];
+    }
+    // two polishing steps for everybody, then (rarely) more for the stragglers
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            const double t = fma(lam[p], lam[p], -a[p]);
+            const double f = fma(t, t, fma(4.0 * m2d[p], lam[p], m4b[p]));
+            const double fq = fma(lam[p], t, m2d[p]);
+            const float r = 0.25f * __frcp_rn((float)fq);
+            step[p] = f * (double)r;
+            lam[p] -= step[p];
+        }
+    }
+    unsigned ok = 0;
+#pragma unroll
+    for (int p = 0; p < NP; ++p)
+        if (fabs(step[p]) <= 1e-13 * lam[p]) ok |= 1u << p;
+    if (ok != (1u << NP) - 1u) {
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            if ((ok >> p) & 1u) continue;
+            if (a[p] == 0.0) { lam[p] = 0.0; ok |= 1u << p; continue; }
+#pragma unroll 1
+            for (int it = 0; it < 22; ++it) {
+                const double t = fma(lam[p], lam[p], -a[p]);
+                const double f = fma(t, t, fma(4.0 * m2d[p], lam[p], m4b[p]));
+                const double fq = fma(lam[p], t, m2d[p]);
+                const float r = 0.25f * __frcp_rn((float)fq);
+                const double st = f * (double)r;
+                lam[p] -= st;
+                if (fabs(st) <= 1e-13 * lam[p]) { ok |= 1u << p; break; }
+            }
+        }
+    }
+    return ok;
+}
+
 // Cyclic Jacobi on a symmetric 4x4 matrix (in registers, fully unrolled indices).  On return A holds the
 // eigenvalues on its diagonal and the columns of V the eigenvectors.
 __device__ __forceinline__ void jacobi4(double (&A)[4][4], double (&V)[4][4]) {
