@@ -9,13 +9,10 @@ namespace ct {
 // packed[tile][kq][c][f][a]  (float64)   tile = frame / 32, f = frame % 32, kq = atom / 4, a = atom % 4,
 // c = x,y,z.  One (tile, kq, c) block is 32 frames x 4 atoms = 1 KiB and is exactly the pair of
 // operand fragments four m8n8k4 DMMAs read (lane l <-> frame l/4, atom l%4), so fragment loads are one
-// conflict-free 256 B LDS.64 per warp, and one pipeline stage of a tile (KC atoms) is ONE contiguous
-// 6 KiB run in HBM that a single cp.async.bulk (TMA) moves.
-constexpr int FT = 32;                                   // frames per packed tile
-constexpr int KC = 8;                                    // atoms per pipeline stage
-constexpr int KQ_STAGE = KC / 4;                         // k4 groups per stage
-constexpr int TILE_STAGE_DOUBLES = KQ_STAGE * 3 * FT * 4;  // 768
-constexpr int TILE_STAGE_BYTES = TILE_STAGE_DOUBLES * 8;   // 6144
+// conflict-free 256 B LDS.64 per warp, and one pipeline stage of a tile (KQS k4 groups) is ONE contiguous
+// run in HBM (KQS x 3 KiB) that a single cp.async.bulk (TMA) moves.
+constexpr int FT = 32;                          // frames per packed tile
+constexpr int KQ_DOUBLES = 3 * FT * 4;          // one k4 group of one tile: 384 doubles = 3 KiB
 
 struct FixList {
     int2* pairs;            // flagged (i, j)
@@ -30,7 +27,6 @@ struct GramParams {
     long long idx_base;
     int M;                  // frames
     int kq_total;           // padded atoms / 4
-    int n_stage;            // pipeline stages per tile = padded atoms / KC
     int row_begin, row_end; // rows of the matrix to produce
     double inv_k;           // 1 / kept atoms
     double flag_rel;        // pairs with E < flag_rel * (G_i + G_j) are re-done by the explicit path
@@ -57,6 +53,19 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {  // non-blocking probe
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(

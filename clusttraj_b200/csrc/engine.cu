@@ -276,7 +276,7 @@ static int compute_rows_async(ct_engine* e, int row_begin, int row_end, double* 
         CT_CUDA(e, cudaMemsetAsync(e->d_fix_count, 0, sizeof(unsigned int), e->s_compute));
         ct::GramParams p;
         p.packed = e->d_packed; p.G = e->d_G; p.out = dst; p.idx_base = idx_base; p.M = (int)e->M;
-        p.kq_total = e->kq_total; p.n_stage = (e->kq_total + ct::KQ_STAGE - 1) / ct::KQ_STAGE;
+        p.kq_total = e->kq_total;
         p.row_begin = row_begin; p.row_end = row_end;
         p.inv_k = 1.0 / (double)e->K; p.flag_rel = e->flag_rel;
         p.fix.pairs = e->d_fix_pairs; p.fix.count = e->d_fix_count; p.fix.capacity = e->fix_cap;

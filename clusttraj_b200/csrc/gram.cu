@@ -20,9 +20,12 @@
 
 namespace ct {
 
-template <int WI_, int WJ_, int MA_, int MB_, int STAGES_>
+template <int WI_, int WJ_, int MA_, int MB_, int STAGES_, int KQS_>
 struct GramCfg {
     static constexpr int WI = WI_, WJ = WJ_, MA = MA_, MB = MB_, STAGES = STAGES_;
+    static constexpr int KQS = KQS_;                               // k4 groups (4 atoms each) per pipeline stage
+    static constexpr int TILE_STAGE_DOUBLES = KQS * KQ_DOUBLES;    // one tile, one stage
+    static constexpr int TILE_STAGE_BYTES = TILE_STAGE_DOUBLES * 8;
     static constexpr int TI = 8 * MA * WI;  // frames per block, row side
     static constexpr int TJ = 8 * MB * WJ;  // frames per block, column side
     static constexpr int NTI = TI / FT, NTJ = TJ / FT;
@@ -58,7 +61,8 @@ struct BlockWalker {
 
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::THREADS, (Cfg::THREADS <= 256) ? 2 : 1) gram_rmsd_kernel(const GramParams p) {
-    constexpr int MA = Cfg::MA, MB = Cfg::MB, STAGES = Cfg::STAGES, TI = Cfg::TI, TJ = Cfg::TJ;
+    constexpr int MA = Cfg::MA, MB = Cfg::MB, STAGES = Cfg::STAGES, TI = Cfg::TI, TJ = Cfg::TJ, KQS = Cfg::KQS;
+    constexpr int TILE_STAGE_DOUBLES = Cfg::TILE_STAGE_DOUBLES;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* stage_buf = reinterpret_cast<double*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(stage_buf + STAGES * Cfg::STAGE_DOUBLES);
@@ -78,8 +82,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, (Cfg::THREADS <= 256) ? 2 : 1) g
     const int last_row = min(p.row_end, p.M - 1);  // row M-1 owns no entries
     const int ti_end = (last_row + TI - 1) / TI;
     const int ntj = (p.M + TJ - 1) / TJ;
-    const int n_stage = p.n_stage;
-    const bool odd_tail = (p.kq_total & 1) != 0;
+    const int n_stage = (p.kq_total + KQS - 1) / KQS;
+    const int tail_kq = p.kq_total - (n_stage - 1) * KQS;  // k4 groups in the last stage of a block (1..KQS)
     const size_t tile_doubles = (size_t)p.kq_total * 3 * FT * 4;  // one 32-frame tile, all atoms
 
     // ---- producer state (thread 0 only): runs STAGES-1 pipeline stages ahead of the consumers -----
@@ -92,8 +96,8 @@ __global__ void __launch_bounds__(Cfg::THREADS, (Cfg::THREADS <= 256) ? 2 : 1) g
         const int slot = lg % STAGES;
         if (lg >= STAGES) mbar_wait(&empty[slot], ((lg / STAGES) - 1) & 1);  // every warp released the slot
         double* dst = stage_buf + slot * Cfg::STAGE_DOUBLES;
-        // the last stage of a block holds a single k4 group when the padded atom count is 4 (mod 8)
-        const uint32_t bytes = (lk == n_stage - 1 && odd_tail) ? TILE_STAGE_BYTES / 2 : TILE_STAGE_BYTES;
+        // the last stage of a block may be partly filled (atoms are padded to 4, not to a whole stage)
+        const uint32_t bytes = (lk == n_stage - 1 ? tail_kq : KQS) * (KQ_DOUBLES * 8);
         mbar_expect_tx(&full[slot], bytes * (Cfg::NTI + Cfg::NTJ));
         const size_t koff = (size_t)lk * TILE_STAGE_DOUBLES;
 #pragma unroll
@@ -112,7 +116,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, (Cfg::THREADS <= 256) ? 2 : 1) g
     }
 
     // ---- consumers ------------------------------------------------------------------------------------
-    // fragment offsets inside a stage (doubles): tile*768 + (kq*3+c)*128 + (8-frame block in tile)*32 + lane
+    // fragment offsets inside a stage (doubles): tile*TILE_STAGE_DOUBLES + (kq*3+c)*128 + (8-frame block)*32 + lane
     int offA[MA], offB[MB];
 #pragma unroll
     for (int ma = 0; ma < MA; ++ma) {
@@ -128,6 +132,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, (Cfg::THREADS <= 256) ? 2 : 1) g
     BlockWalker<Cfg> cw;
     cw.init(ti_begin, ti_end, ntj, blockIdx.x);
     unsigned int g = 0;  // stages consumed so far
+    bool ready = false;  // outcome of the early probe of the next stage's "full" barrier
     for (; cw.valid(); cw.advance(gridDim.x)) {
         double acc[MA][MB][3][3][2];
 #pragma unroll
@@ -143,11 +148,14 @@ __global__ void __launch_bounds__(Cfg::THREADS, (Cfg::THREADS <= 256) ? 2 : 1) g
         for (int k = 0; k < n_stage; ++k, ++g) {
             const int slot = g % STAGES;
             if (tid == 0) issue_load();  // stage g + PREFETCH
-            mbar_wait(&full[slot], (g / STAGES) & 1);
+            if (!ready) mbar_wait(&full[slot], (g / STAGES) & 1);
+            // probe the next stage now; the answer is consumed after this stage's DMMAs (hides the
+            // ~90-cycle mbarrier round trip)
+            ready = mbar_test(&full[(g + 1) % STAGES], ((g + 1) / STAGES) & 1);
             const double* sb = stage_buf + slot * Cfg::STAGE_DOUBLES;
-            const int nkq = (k == n_stage - 1 && odd_tail) ? 1 : KQ_STAGE;
+            const int nkq = (k == n_stage - 1) ? tail_kq : KQS;
 #pragma unroll
-            for (int kq = 0; kq < KQ_STAGE; ++kq) {
+            for (int kq = 0; kq < KQS; ++kq) {
                 if (kq >= nkq) break;
                 double fa[MA][3], fb[MB][3];
 #pragma unroll
@@ -231,15 +239,12 @@ __global__ void __launch_bounds__(Cfg::THREADS, (Cfg::THREADS <= 256) ? 2 : 1) g
 // ---- host-side launcher ---------------------------------------------------------------------------
 template <class Cfg>
 static cudaError_t launch_gram_cfg(const GramParams& p, int sm_count, cudaStream_t stream) {
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gram_rmsd_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             Cfg::SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    // per-device attribute: set on every launch (several engines / devices may live in one process)
+    cudaError_t e = cudaFuncSetAttribute(gram_rmsd_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
     int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gram_rmsd_kernel<Cfg>, Cfg::THREADS,
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gram_rmsd_kernel<Cfg>, Cfg::THREADS,
                                                                   Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
@@ -257,11 +262,15 @@ static cudaError_t launch_gram_cfg(const GramParams& p, int sm_count, cudaStream
     return cudaGetLastError();
 }
 
-using GramDefault = GramCfg<4, 2, 1, 2, 6>;   // 32 x 32 frame pairs, 8 warps, 2 CTAs / SM
-using GramWide = GramCfg<4, 4, 1, 2, 5>;      // 32 x 64 frame pairs, 16 warps, 1 CTA / SM
+using GramDefault = GramCfg<4, 2, 1, 2, 4, 4>;  // 32 x 32 frame pairs, 8 warps, 2 CTAs / SM, 16 atoms / stage
+using GramWide = GramCfg<4, 4, 1, 2, 4, 4>;     // 32 x 64 frame pairs, 16 warps, 1 CTA / SM
+using GramK8 = GramCfg<4, 2, 1, 2, 6, 2>;       // as default with 8 atoms / stage, deeper ring
+using GramK24 = GramCfg<4, 2, 1, 2, 3, 6>;      // 24 atoms / stage
 
 cudaError_t launch_gram(const GramParams& p, int variant, int sm_count, cudaStream_t stream) {
     if (variant == 1) return launch_gram_cfg<GramWide>(p, sm_count, stream);
+    if (variant == 2) return launch_gram_cfg<GramK8>(p, sm_count, stream);
+    if (variant == 3) return launch_gram_cfg<GramK24>(p, sm_count, stream);
     return launch_gram_cfg<GramDefault>(p, sm_count, stream);
 }
 
