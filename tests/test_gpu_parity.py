@@ -199,6 +199,20 @@ def test_hungarian_config4_shape_sample(eng):
     assert (perms == want_p).all()
 
 
+def test_hungarian_large_block_generic_solver(eng):
+    """An element block above 256 atoms takes the shared-memory-state solver instead of the register one."""
+    rng = np.random.default_rng(4)
+    base = rng.uniform(-12, 12, size=(300, 3))
+    frames = np.stack([(base + rng.normal(0, 0.25, size=base.shape))[rng.permutation(300)] for _ in range(4)])
+    atoms = np.full(300, 6, np.int32)
+    pairs = [(0, 1), (0, 3), (1, 2), (2, 3)]
+    eng.load_frames(frames, atoms, engine_opts(reorder=True))
+    vals, perms, _ = eng.pair_values(pairs, want_perms=True)
+    want_v, want_p = oracle_pairs(atoms, frames, pairs, reorder=True)
+    assert (perms == want_p).all()
+    assert np.abs(vals - want_v).max() <= 1e-9
+
+
 def test_row_slabs_concatenate(eng):
     from clusttraj_b200.synth import make_trajectory
 
