@@ -301,3 +301,71 @@ def test_config2_full_size_properties(eng):
     eng.load_frames(coords[:2048], atoms, engine_opts())
     still, _ = eng.rmsd_rows(0, 64)
     assert np.abs(moved - still).max() < 1e-9
+
+
+def _sampled_device_check(eng, atoms, coords, kw, n_samples, tol, seed=0):
+    """Whole matrix left on the GPU; random entries copied back and compared with the oracle."""
+    M = len(coords)
+    eng.load_frames(coords, atoms, engine_opts(**kw))
+    ptr, n, st = eng.rmsd_rows_device(0, M)
+    assert n == M * (M - 1) // 2 and st["pairs"] == n
+    rng = np.random.default_rng(seed)
+    pairs = []
+    while len(pairs) < n_samples:
+        a, b = (int(v) for v in rng.integers(0, M, size=2))
+        if a != b:
+            pairs.append((min(a, b), max(a, b)))
+    pairs += [(0, 1), (1, 2), (0, M - 1), (M - 2, M - 1)]
+    got = np.array([eng.copy_slab(condensed_index(M, i, j), 1)[0] for i, j in pairs])
+    want, _ = oracle_pairs(atoms, coords, pairs, **kw)
+    assert np.abs(got - want).max() <= tol, np.abs(got - want).max()
+    # a strided sweep over the slab: finite, non-negative, no fix-up marker left behind
+    stride = max(1, n // 64)
+    for off in range(0, n - 4096, stride):
+        blk = eng.copy_slab(off, 4096)
+        assert np.isfinite(blk).all() and blk.min() >= 0.0
+    return st
+
+
+def test_config3_full_size(eng):
+    """BASELINE config 3: 50k frames x 300 atoms, -n (K = 150), 1.25e9 pairs, slab kept on the GPU."""
+    from clusttraj_b200.synth import make_trajectory
+
+    atoms, coords = make_trajectory(50000, 300, seed=20250603)
+    st = _sampled_device_check(eng, atoms, coords, dict(noh=True), 120, 1e-9)
+    assert st["kept_atoms"] == 150 and st["flagged"] >= 3
+
+
+def test_config5_full_size_single_gpu(eng):
+    """BASELINE config 5's matrix (100k frames x 300 atoms, plain, 5e9 pairs = 40 GB) on ONE GPU."""
+    from clusttraj_b200.synth import make_trajectory
+
+    atoms, coords = make_trajectory(100000, 300, seed=20250605)
+    st = _sampled_device_check(eng, atoms, coords, dict(), 120, 1e-9)
+    assert st["pairs"] == 4999950000
+
+
+def test_config4_full_size_hungarian(eng):
+    """BASELINE config 4: 10k frames, 60 solute + 300 solvent atoms, -ns 60 -e hungarian (5e7 pairs).
+    Frames 1..3 are frame 0 with its solvent atoms relabelled (same-element permutation) plus 1e-4 A noise:
+    the reorder must undo the relabelling (known permutation) and give an RMSD at the noise level."""
+    from clusttraj_b200.synth import make_solute_solvent
+
+    atoms, coords = make_solute_solvent(10000, n_solute=60, n_solvent_mol=100, seed=20250604)
+    rng = np.random.default_rng(1)
+    known = []
+    for k in (1, 2, 3):
+        perm = np.arange(360)
+        for z in np.unique(atoms[60:]):
+            idx = 60 + np.where(atoms[60:] == z)[0]
+            perm[idx] = rng.permutation(idx)
+        coords[k] = coords[0][perm] + rng.normal(0, 1e-4, size=(360, 3))
+        known.append(perm)
+    kw = dict(reorder=True, ns=60)
+    st = _sampled_device_check(eng, atoms, coords, kw, 24, 1e-9, seed=3)
+    assert st["lsap_steps"] > 300 * st["pairs"]
+    vals, perms, _ = eng.pair_values([(0, 1), (0, 2), (0, 3)], want_perms=True)
+    assert vals.max() < 1e-3
+    for k in range(3):
+        # perms[k][p] = index in frame k+1 of the atom that ends at position p; frame k+1 = frame 0[known]
+        assert (known[k][perms[k]] == np.arange(360)).all()

@@ -1,0 +1,164 @@
+"""CPU tests: the C-ABI library loads and exports every symbol the header declares, the host-side logic
+(slab partition, option parsing, trajectory reader, reorder handles) and the loud failure without a GPU."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "clusttraj_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ct_[a-z_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from clusttraj_b200 import _engine
+
+    lib = _engine.load_library()
+    names = _declared_symbols()
+    assert len(names) >= 15
+    for name in names:
+        assert hasattr(lib, name), name
+    assert set(_engine.EXPORTS) == set(names)
+    assert b"sm_100a" in lib.ct_version()
+
+
+def test_rows_pairs_matches_condensed_layout():
+    from clusttraj_b200 import _engine
+
+    lib = _engine.load_library()
+    for M in (1, 2, 3, 17, 1000):
+        total = M * (M - 1) // 2
+        assert lib.ct_rows_pairs(M, 0, M) == total
+        acc = 0
+        for r in range(M):
+            n = lib.ct_rows_pairs(M, r, r + 1)
+            assert n == M - 1 - r
+            acc += n
+        assert acc == total
+    assert lib.ct_rows_pairs(100, 40, 40) == 0
+
+
+def test_no_gpu_fails_loudly():
+    from clusttraj_b200 import _engine
+
+    if _engine.device_count() > 0:
+        pytest.skip("a GPU is visible")
+    with pytest.raises(_engine.EngineError, match="no CUDA device"):
+        _engine.Engine(0)
+    from clusttraj_b200.distmat import build_distance_matrix
+    from clusttraj_b200.io import ClustOptions
+
+    opt = ClustOptions(trajfile=os.path.join(ROOT, "tests", "golden", "ref_testtraj.xyz"), no_hydrogen=True,
+                       solute_natoms=17, reorder_excl=np.asarray([], np.int32))
+    with pytest.raises(_engine.EngineError):
+        build_distance_matrix(opt)
+
+
+def test_product_never_imports_the_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py may touch oracle/."""
+    pkg = os.path.join(ROOT, "clusttraj_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+
+
+@pytest.mark.parametrize("M,parts", [(2, 1), (10, 3), (20000, 8), (100000, 8), (57, 7)])
+def test_slab_bounds_equal_area(M, parts):
+    from clusttraj_b200.distmat import slab_bounds
+
+    cuts = slab_bounds(M, parts)
+    assert cuts[0] == 0 and cuts[-1] == M and len(cuts) == parts + 1
+    assert all(a <= b for a, b in zip(cuts, cuts[1:]))
+    area = [b * M - b * (b + 1) // 2 - (a * M - a * (a + 1) // 2) for a, b in zip(cuts, cuts[1:])]
+    total = M * (M - 1) // 2
+    assert sum(area) == total
+    if M >= 1000:
+        assert max(area) - min(area) <= 2 * M  # within one row of perfectly equal
+
+
+def test_xyz_round_trip(tmp_path):
+    from clusttraj_b200.synth import make_trajectory
+    from clusttraj_b200.xyz import read_trajectory, write_xyz
+
+    z, x = make_trajectory(5, 9, seed=3)
+    path = str(tmp_path / "t.xyz")
+    write_xyz(path, z, x)
+    atoms, coords = read_trajectory(path)
+    assert atoms.shape == (5, 9) and (atoms == z).all()
+    assert np.array_equal(coords, x)  # 5-decimal coordinates survive the text round trip
+
+
+def test_reference_fixture_reads_like_the_oracle_reader(golden_dir):
+    from clusttraj_b200.xyz import read_xyz
+    from oracle.xyz_min import read_xyz as oracle_read
+
+    a, c = read_xyz(os.path.join(golden_dir, "ref_testtraj.xyz"))
+    oa, oc = oracle_read(os.path.join(golden_dir, "ref_testtraj.xyz"))
+    assert a.shape == (3, 41) and np.array_equal(a, oa) and np.array_equal(c, oc)
+    assert (a[0] == 1).sum() == 26 and (a[0] == 6).sum() == 10 and (a[0] == 8).sum() == 5
+
+
+def test_cli_options_follow_the_reference(tmp_path, golden_dir):
+    """Mirrors the reference's test_io.py expectations for the hot-path fields."""
+    from clusttraj_b200 import reorder
+    from clusttraj_b200.io import ClustOptions, configure_runtime
+
+    traj = os.path.join(golden_dir, "ref_testtraj.xyz")
+    common = ["--log", str(tmp_path / "c.log"), "-oc", str(tmp_path / "clusters.dat"), "-od", str(tmp_path / "d.npy")]
+    opt = configure_runtime([traj, "-rmsd", "1.0"] + common)
+    assert isinstance(opt, ClustOptions)
+    assert opt.trajfile == traj and opt.min_rmsd == 1.0 and opt.method == "average" and opt.n_workers == 4
+    assert opt.reorder_alg is None and opt.reorder is False and opt.no_hydrogen is False
+    assert opt.reorder_excl.dtype == np.int32 and opt.reorder_excl.size == 0
+    assert opt.summary_name == str(tmp_path / "clusters.out")
+    opt = configure_runtime([traj, "-rmsd", "1.0", "-e", "-ns", "17", "-eex", "1", "2", "5", "-ws", "0.8", "-rs",
+                             "--final-kabsch"] + common)
+    assert opt.reorder_alg is reorder.reorder_hungarian and opt.reorder_alg_name == "hungarian"
+    assert list(opt.reorder_excl) == [0, 1, 4] and opt.exclusions is True  # CLI is 1-based, options 0-based
+    assert opt.solute_natoms == 17 and opt.weight_solute == 0.8 and opt.reorder_solvent_only and opt.final_kabsch
+    opt = configure_runtime([traj, "-nc", "2", "-e", "--reorder-alg", "inertia-hungarian"] + common)
+    assert opt.reorder_alg is None and opt.n_clusters == 2  # accepted but bound to nothing, as in the reference
+    for bad in (["-rmsd", "1.0", "-m", "nonsense"], ["-rmsd", "1.0", "-rs"], ["-rmsd", "1.0", "-ws", "0.5"],
+                ["-rmsd", "1.0", "-n", "-e", "-eex", "1"], ["-rmsd", "1.0", "-ns", "17", "-ws", "1.5"], []):
+        with pytest.raises(SystemExit):
+            configure_runtime([traj] + bad + common)
+    open(tmp_path / "d.npy", "w").close()
+    with pytest.raises(FileExistsError):
+        configure_runtime([traj, "-rmsd", "1.0"] + common)
+    configure_runtime([traj, "-rmsd", "1.0", "-f"] + common)
+
+
+def test_reorder_handles():
+    from clusttraj_b200 import reorder
+
+    assert reorder.reorder_mode_of(None) == 0
+    assert reorder.reorder_mode_of(reorder.reorder_hungarian) == 1
+
+    def reorder_hungarian(a, b, c, d):  # e.g. rmsd.reorder_hungarian held by a user's ClustOptions
+        return None
+
+    assert reorder.reorder_mode_of(reorder_hungarian) == 1
+    with pytest.raises(NotImplementedError):
+        reorder.reorder_mode_of(lambda *a: None)
+    with pytest.raises(NotImplementedError):
+        reorder.reorder_hungarian(None, None, None, None)
+
+
+def test_classify_on_golden_vector(tmp_path, ref_golden_distmat):
+    """Reference test_classify.py:30-52: ward linkage of the golden matrix."""
+    from clusttraj_b200.io import ClustOptions
+    from clusttraj_b200.main import classify
+
+    opt = ClustOptions(method="ward", min_rmsd=1.0, opt_order=False, out_clust_name=str(tmp_path / "c.dat"))
+    Z, clusters = classify(opt, ref_golden_distmat)
+    assert np.allclose(Z, [[0.0, 1.0, 2.94126393, 2.0], [2.0, 3.0, 4.6348889, 3.0]])
+    assert list(clusters) == [1, 2, 3]
+    opt.update({"n_clusters": 2})
+    assert list(classify(opt, ref_golden_distmat)[1]) == [1, 1, 2]

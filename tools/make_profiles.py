@@ -1,0 +1,81 @@
+"""Turn the scratch ncu output under gpurun_out/ into the tracked summaries under profiles/.
+
+    python tools/make_profiles.py <round-tag> <gram .ncu-rep> [<pair .ncu-rep>] [<launch list csv>]
+"""
+import csv, io, json, os, subprocess, sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1]
+out_dir = os.path.join(ROOT, "profiles")
+
+
+def raw_metrics(rep):
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    hdr, units = rows[0], rows[1]
+    return [{h: (r[i], units[i]) for i, h in enumerate(hdr)} for r in rows[2:]]
+
+
+KEEP = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_shared_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_fp64.sum", "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "lts__t_bytes.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__cycles_elapsed.avg.per_second"]
+
+
+def to_bytes(v, unit):
+    f = float(v.replace(",", ""))
+    return f * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}.get(unit, 1)
+
+
+def summarise(rep, name):
+    text = [f"# ncu --set full summary of {os.path.basename(rep)} ({name}); produced by tools/make_profiles.py", ""]
+    ms = raw_metrics(rep)
+    for k, m in enumerate(ms):
+        text.append(f"## launch {k}")
+        for key in KEEP:
+            if key in m:
+                text.append(f"{key:80s} {m[key][0]} {m[key][1]}")
+        for key, (v, u) in sorted(m.items()):
+            if key.startswith("smsp__average_warps_issue_stalled") and key.endswith("per_issue_active.ratio") and float(v or 0) >= 0.05:
+                text.append(f"{key:80s} {v}")
+        text.append("")
+    summ = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), rep], capture_output=True, text=True).stdout
+    text.append("## stall samples (tools/ncu_summary.py)")
+    text.append(summ)
+    path = os.path.join(out_dir, f"{tag}_{name}_ncu_summary.txt")
+    open(path, "w").write("\n".join(text))
+    print("wrote", path)
+    return ms
+
+
+ms = summarise(sys.argv[2], "gram")
+m = ms[-1]
+traffic = to_bytes(*m["dram__bytes_read.sum"]) + to_bytes(*m["dram__bytes_write.sum"])
+json.dump({"kernel": "gram_rmsd_kernel", "workload": "cfg2 20000 x 100 plain, one launch = whole matrix",
+           "dram_bytes_read": to_bytes(*m["dram__bytes_read.sum"]), "dram_bytes_write": to_bytes(*m["dram__bytes_write.sum"]),
+           "dram_bytes_per_launch": traffic, "duration_ms_under_ncu": float(m["gpu__time_duration.sum"][0]),
+           "source": os.path.basename(sys.argv[2])}, open(os.path.join(out_dir, f"{tag}_gram_traffic.json"), "w"), indent=1)
+if len(sys.argv) > 3 and sys.argv[3] != "-":
+    summarise(sys.argv[3], "pair")
+if len(sys.argv) > 4:
+    rows = list(csv.reader(open(sys.argv[4])))
+    hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+    hdr = rows[hi]; kn = hdr.index("Kernel Name"); mv = hdr.index("Metric Value")
+    agg = {}
+    for r in rows[hi + 1:]:
+        if len(r) <= mv: continue
+        name = r[kn].split("(")[0]
+        a = agg.setdefault(name, [0, 0.0]); a[0] += 1; a[1] += float(r[mv].replace(",", ""))
+    tot = sum(a[1] for a in agg.values())
+    lines = ["# per-kernel device time of one `bench.py --steps 2 --warmup 3 --no-cpu-baseline` run under",
+             "# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare SHARES)",
+             f"{'kernel':70s} {'launches':>8s} {'total_ms':>10s} {'share':>7s}"]
+    for name, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        lines.append(f"{name[:70]:70s} {n:8d} {t / 1e6:10.3f} {100 * t / tot:6.1f}%")
+    open(os.path.join(out_dir, f"{tag}_launch_shares.txt"), "w").write("\n".join(lines) + "\n")
+    import shutil
+    shutil.copy(sys.argv[4], os.path.join(out_dir, f"{tag}_launches_ncu.csv"))
+    print("\n".join(lines))
