@@ -22,14 +22,14 @@ struct FixList {
 
 struct GramParams {
     const double* packed;   // tile-major centred coordinates
-    const double* G;        // per-frame sum of squares, padded to whole tiles
+    const double* G;        // per-frame HALF sum of squares (0.5 * sum |x|^2), padded to whole tiles
     double* out;            // condensed slab; element idx(i,j) lives at out[idx(i,j) - idx_base]
     long long idx_base;
     int M;                  // frames
     int kq_total;           // padded atoms / 4
     int row_begin, row_end; // rows of the matrix to produce
-    double inv_k;           // 1 / kept atoms
-    double flag_rel;        // pairs with E < flag_rel * (G_i + G_j) are re-done by the explicit path
+    double inv_k2;          // 2 / kept atoms
+    double flag_rel;        // pairs with E < flag_rel * (G_i + G_j) are re-done by the explicit-rotation path
     FixList fix;
 };
 
@@ -85,6 +85,18 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                      smem_u32(dst_smem)),
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+
+// shared-memory sequence counters (absolute block numbers, so a waiter may be any number of phases ahead)
+__device__ __forceinline__ void seq_publish(unsigned int* ctr, unsigned int v) {
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(ctr)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void seq_wait_ge(const unsigned int* ctr, unsigned int v) {
+    unsigned int cur;
+    do {
+        asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(cur) : "r"(smem_u32(ctr)) : "memory");
+        if (cur < v) __nanosleep(32);
+    } while (cur < v);
 }
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {

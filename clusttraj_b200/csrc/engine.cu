@@ -56,7 +56,7 @@ struct ct_engine {
     cudaEvent_t ev_chunk_done[2] = {nullptr, nullptr}, ev_copy_done[2] = {nullptr, nullptr};
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
     ct_stats stats{};
-    int gram_variant = 0;
+    int gram_variant = -1;  // -1 = choose by atom count (gram.cu:launch_gram)
     size_t chunk_entries = (size_t)32 << 20;  // 256 MiB of float64 per streaming chunk
     double flag_rel = 1e-9;
 };
@@ -278,7 +278,7 @@ static int compute_rows_async(ct_engine* e, int row_begin, int row_end, double* 
         p.packed = e->d_packed; p.G = e->d_G; p.out = dst; p.idx_base = idx_base; p.M = (int)e->M;
         p.kq_total = e->kq_total;
         p.row_begin = row_begin; p.row_end = row_end;
-        p.inv_k = 1.0 / (double)e->K; p.flag_rel = e->flag_rel;
+        p.inv_k2 = 2.0 / (double)e->K; p.flag_rel = e->flag_rel;
         p.fix.pairs = e->d_fix_pairs; p.fix.count = e->d_fix_count; p.fix.capacity = e->fix_cap;
         CT_CUDA(e, ct::launch_gram(p, e->gram_variant, e->sm_count, e->s_compute));
         if (after_main) CT_CUDA(e, cudaEventRecord(after_main, e->s_compute));
@@ -361,15 +361,18 @@ int ct_rmsd_rows(ct_engine* e, int64_t row_begin, int64_t row_end, double* out, 
     {
         int64_t r = row_begin;
         const int64_t last = std::min<int64_t>(row_end, e->M - 1);
+        // the first chunks are small so that the device->host stream starts early, then they double
+        int64_t target = std::max<int64_t>((int64_t)e->chunk_entries / 16, 1);
         while (r < last) {
             int64_t acc = 0, r2 = r;
-            while (r2 < last && acc < (int64_t)e->chunk_entries) {
+            while (r2 < last && acc < target) {
                 int64_t nxt = std::min<int64_t>(last, (r2 / align + 1) * align);
                 acc += ct_rows_pairs(e->M, r2, nxt);
                 r2 = nxt;
             }
             cuts.push_back(r2);
             r = r2;
+            target = std::min<int64_t>(target * 2, (int64_t)e->chunk_entries);
         }
     }
     size_t biggest = 1;

@@ -4,7 +4,7 @@
 //
 //   centre_kernel : one CTA per frame.  Gathers the kept atoms, subtracts the centroid of the first
 //                   `ncen` kept atoms (all of them, or the solute with -ns), writes the centred frame
-//                   as [K][3] float64 (read by the per-pair kernels) and G[m] = sum |x|^2.
+//                   as [K][3] float64 (read by the per-pair kernels) and G[m] = 0.5 * sum |x|^2.
 //   tile_pack_kernel : re-lays the centred frames into the tile-major layout of common.cuh (one thread
 //                   per output element, fully coalesced stores, zero padding in atoms and frames).
 #include "common.cuh"
@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(128) centre_kernel(const double* __restrict__ 
     __syncthreads();
     if (lane == 0) red[warp][3] = g;
     __syncthreads();
-    if (tid == 0) G[m] = red[0][3] + red[1][3] + red[2][3] + red[3][3];
+    if (tid == 0) G[m] = 0.5 * (red[0][3] + red[1][3] + red[2][3] + red[3][3]);  // the Gram epilogue wants G/2
 }
 
 __global__ void __launch_bounds__(256) tile_pack_kernel(const double* __restrict__ centred, int M, int K,

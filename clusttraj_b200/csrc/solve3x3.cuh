@@ -81,10 +81,12 @@ __device__ __forceinline__ bool largest_root(double a, double b, double d, doubl
     return ok && (lam == lam);
 }
 
-// The same solve for NP independent pairs held by one thread, advanced in lockstep so that the
-// dependent FP64 chains of different pairs interleave (the FP64 pipe is shared with the DMMAs of the
-// other resident warps, so a single dependent chain is stretched by pipe contention; NP-way ILP hides
-// it).  ok_mask bit p is set when pair p settled.
+// The same solve for NP independent pairs held by one thread, advanced in lockstep.  The FP64 pipe is shared
+// with the DMMAs of the MMA warps, so every FP64 instruction issued here queues behind 16-cycle DMMAs: the
+// FP64 instruction count per pair is what bounds the epilogue, and it is kept minimal — one polishing
+// Newton step (quadratic: an FP32-converged start with relative error ~1e-7 lands at ~1e-13) accepted when
+// the step itself is below 1e-6 * lambda; only lanes that fail the test iterate further.
+// ok_mask bit p is set when pair p settled.
 template <int NP>
 __device__ __forceinline__ unsigned largest_root_lockstep(const double (&a)[NP], const double (&b)[NP],
                                                           const double (&d)[NP], const double (&half_g)[NP],
@@ -95,7 +97,7 @@ __device__ __forceinline__ unsigned largest_root_lockstep(const double (&a)[NP],
     for (int p = 0; p < NP; ++p) {
         const float af0 = (float)a[p];
         float l = fminf((float)half_g[p], sqrtf(3.0f * af0)) * 1.000001f;
-        if (!(l > 0.0f)) l = 1.0f;  // S == 0: every root is 0; the FP64 check below rejects non-zero a
+        if (!(l > 0.0f)) l = 1.0f;  // S == 0: every root is 0; handled by the a == 0 test below
         l0[p] = l;
         const float sc = __frcp_rn(l);
         const float sc2 = sc * sc;
@@ -119,42 +121,33 @@ __device__ __forceinline__ unsigned largest_root_lockstep(const double (&a)[NP],
             if (!good || fabsf(step) <= 3e-7f * x[p]) live &= ~(1u << p);
         }
     }
-    double m2d[NP], m4b[NP], step[NP];
+    unsigned ok = 0;
+    double d2[NP], d8[NP], b4[NP];
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
-        lam[p] = (double)x[p] * (double)l0[p];
-        m2d[p] = -2.0 * d[p];
-        m4b[p] = -4.0 * b[p];
+        d2[p] = 2.0 * d[p];
+        d8[p] = 8.0 * d[p];
+        b4[p] = 4.0 * b[p];
+        double l = (double)(x[p] * l0[p]);  // FP32 product: only the starting point of the FP64 step
+        const double t = fma(l, l, -a[p]);
+        const double f = fma(t, t, -fma(d8[p], l, b4[p]));
+        const double fq = fma(l, t, -d2[p]);
+        const double step = f * (double)(0.25f * __frcp_rn((float)fq));
+        l -= step;
+        lam[p] = l;
+        if (fabs(step) <= 1e-6 * l) ok |= 1u << p;
     }
-    // two polishing steps for everybody, then (rarely) more for the stragglers
-#pragma unroll
-    for (int it = 0; it < 2; ++it) {
-#pragma unroll
-        for (int p = 0; p < NP; ++p) {
-            const double t = fma(lam[p], lam[p], -a[p]);
-            const double f = fma(t, t, fma(4.0 * m2d[p], lam[p], m4b[p]));
-            const double fq = fma(lam[p], t, m2d[p]);
-            const float r = 0.25f * __frcp_rn((float)fq);
-            step[p] = f * (double)r;
-            lam[p] -= step[p];
-        }
-    }
-    unsigned ok = 0;
-#pragma unroll
-    for (int p = 0; p < NP; ++p)
-        if (fabs(step[p]) <= 1e-13 * lam[p]) ok |= 1u << p;
     if (ok != (1u << NP) - 1u) {
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
             if ((ok >> p) & 1u) continue;
             if (a[p] == 0.0) { lam[p] = 0.0; ok |= 1u << p; continue; }
 #pragma unroll 1
-            for (int it = 0; it < 22; ++it) {
+            for (int it = 0; it < 24; ++it) {
                 const double t = fma(lam[p], lam[p], -a[p]);
-                const double f = fma(t, t, fma(4.0 * m2d[p], lam[p], m4b[p]));
-                const double fq = fma(lam[p], t, m2d[p]);
-                const float r = 0.25f * __frcp_rn((float)fq);
-                const double st = f * (double)r;
+                const double f = fma(t, t, -fma(d8[p], lam[p], b4[p]));
+                const double fq = fma(lam[p], t, -d2[p]);
+                const double st = f * (double)(0.25f * __frcp_rn((float)fq));
                 lam[p] -= st;
                 if (fabs(st) <= 1e-13 * lam[p]) { ok |= 1u << p; break; }
             }
