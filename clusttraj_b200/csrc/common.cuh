@@ -33,6 +33,21 @@ struct GramParams {
     FixList fix;
 };
 
+// parameters of the int8 tensor-core (tcgen05) Gram kernel, ozaki.cu
+struct OzParams {
+    const uint8_t* packA;   // [ti][kb][slice][kc16 (8)][row group (16)][8 rows][16 B]
+    const uint8_t* packB;   // [tj][kb][slice][kc16 (8)][row group (12)][8 rows][16 B]
+    const double* Gq;       // half sums of squares of the QUANTISED coordinates, real units
+    const double* qinfo;    // [0] = 2^(-2f), [1] = f, [2] = max |x|
+    double* out;
+    long long idx_base;
+    long long total_blocks;
+    int M, nkb, last_chunks;   // K-blocks; 32-atom chunks in the last K-block (1..4)
+    int row_begin, row_end;
+    double inv_k2, flag_rel;
+    FixList fix;
+};
+
 __host__ __device__ __forceinline__ long long condensed_row_base(long long M, long long i) {
     // index of (i, i+1) in SciPy's condensed order (clusttraj/distmat.py:78 flattens rows in order)
     return M * i - (i * (i + 1)) / 2;

@@ -16,6 +16,14 @@ cudaError_t launch_pack(const double* raw, const int* keep, int M, int N, int K,
                         double* centred, double* G, double* packed, int sm_count, cudaStream_t stream);
 cudaError_t launch_gram(const GramParams& p, int variant, int sm_count, cudaStream_t stream);
 int gram_row_align(int variant);
+// int8 tensor-core (tcgen05) variant of the Gram kernel, ozaki.cu
+size_t oz_packA_bytes(int M, int K);
+size_t oz_packB_bytes(int M, int K);
+size_t oz_g_entries(int M);
+int oz_row_align();
+cudaError_t launch_quant_pack(const double* centred, int M, int K, uint8_t* packA, uint8_t* packB, double* Gq, double* qinfo,
+                              unsigned long long* maxbits, int sm_count, cudaStream_t stream);
+cudaError_t launch_gram_i8(OzParams p, int K, int sm_count, cudaStream_t stream);
 cudaError_t launch_fixup(const double* centred, int M, int K, const FixList& fix, double* out, long long idx_base,
                          long long n_entries, unsigned long long* flagged_total, int sm_count, cudaStream_t stream);
 struct PairPlan;
@@ -47,6 +55,14 @@ struct ct_engine {
     double* d_centred = nullptr; size_t centred_cap = 0;
     double* d_G = nullptr; size_t g_cap = 0;
     double* d_packed = nullptr; size_t packed_cap = 0;
+    // int8 tensor-core path (ozaki.cu): digit slices in both operand layouts, G of the quantised coordinates
+    bool use_i8 = false;
+    uint8_t* d_packA = nullptr; size_t packA_cap = 0;
+    uint8_t* d_packB = nullptr; size_t packB_cap = 0;
+    double* d_Gq = nullptr; size_t gq_cap = 0;
+    double* d_qinfo = nullptr;               // [0] 2^-2f, [1] f, [2] max |x|
+    unsigned long long* d_maxbits = nullptr;
+    double quant_f = 0.0;
     ct::PairPlanHost* plan = nullptr;
     // outputs
     double* d_slab = nullptr; size_t slab_cap = 0;       // whole-slab device buffer (rows_device)
@@ -132,6 +148,8 @@ int ct_engine_create(int device, ct_engine** out) {
     CT_CUDA((ct_engine*)nullptr, cudaMalloc(&e->d_fix_pairs, sizeof(int2) * e->fix_cap));
     CT_CUDA((ct_engine*)nullptr, cudaMalloc(&e->d_fix_count, sizeof(unsigned int)));
     CT_CUDA((ct_engine*)nullptr, cudaMalloc(&e->d_counters, sizeof(unsigned long long) * 4));
+    CT_CUDA((ct_engine*)nullptr, cudaMalloc(&e->d_qinfo, sizeof(double) * 4));
+    CT_CUDA((ct_engine*)nullptr, cudaMalloc(&e->d_maxbits, sizeof(unsigned long long)));
     const char* v = getenv("CLUSTTRAJ_B200_GRAM_VARIANT");
     if (v) e->gram_variant = atoi(v);
     const char* ce = getenv("CLUSTTRAJ_B200_CHUNK_ENTRIES");
@@ -147,6 +165,7 @@ void ct_engine_destroy(ct_engine* e) {
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     cudaFree(e->d_raw); cudaFree(e->d_keep); cudaFree(e->d_centred); cudaFree(e->d_G); cudaFree(e->d_packed);
+    cudaFree(e->d_packA); cudaFree(e->d_packB); cudaFree(e->d_Gq); cudaFree(e->d_qinfo); cudaFree(e->d_maxbits);
     cudaFree(e->d_slab); cudaFree(e->d_chunk[0]); cudaFree(e->d_chunk[1]);
     cudaFree(e->d_fix_pairs); cudaFree(e->d_fix_count); cudaFree(e->d_counters);
     for (int k = 0; k < 2; ++k) { cudaEventDestroy(e->ev_chunk_done[k]); cudaEventDestroy(e->ev_copy_done[k]); }
@@ -226,17 +245,31 @@ int ct_load_frames(ct_engine* e, const double* coords, const int32_t* atomic_num
     if ((rc = ensure(e, e->d_keep, e->keep_cap, (size_t)K))) return rc;
     if ((rc = ensure(e, e->d_centred, e->centred_cap, (size_t)M * K * 3))) return rc;
     if ((rc = ensure(e, e->d_G, e->g_cap, (size_t)e->m_pad))) return rc;
-    if (e->use_gram)
+    e->use_i8 = e->use_gram && e->gram_variant == 10;
+    if (e->use_gram && !e->use_i8)
         if ((rc = ensure(e, e->d_packed, e->packed_cap, (size_t)e->m_pad * k_pad * 3))) return rc;
+    if (e->use_i8) {
+        if ((rc = ensure(e, e->d_packA, e->packA_cap, ct::oz_packA_bytes((int)M, K)))) return rc;
+        if ((rc = ensure(e, e->d_packB, e->packB_cap, ct::oz_packB_bytes((int)M, K)))) return rc;
+        if ((rc = ensure(e, e->d_Gq, e->gq_cap, ct::oz_g_entries((int)M)))) return rc;
+    }
 
     CT_CUDA(e, cudaEventRecord(e->ev_a, e->s_compute));
     CT_CUDA(e, cudaMemcpyAsync(e->d_raw, coords, sizeof(double) * (size_t)M * N * 3, cudaMemcpyHostToDevice, e->s_compute));
     CT_CUDA(e, cudaMemcpyAsync(e->d_keep, keep.data(), sizeof(int) * (size_t)K, cudaMemcpyHostToDevice, e->s_compute));
     CT_CUDA(e, cudaEventRecord(e->ev_b, e->s_compute));
     CT_CUDA(e, ct::launch_pack(e->d_raw, e->d_keep, (int)M, N, K, ncen, e->m_pad, e->kq_total, e->d_centred, e->d_G,
-                               e->use_gram ? e->d_packed : nullptr, e->sm_count, e->s_compute));
+                               (e->use_gram && !e->use_i8) ? e->d_packed : nullptr, e->sm_count, e->s_compute));
+    if (e->use_i8)
+        CT_CUDA(e, ct::launch_quant_pack(e->d_centred, (int)M, K, e->d_packA, e->d_packB, e->d_Gq, e->d_qinfo, e->d_maxbits,
+                                         e->sm_count, e->s_compute));
     CT_CUDA(e, cudaEventRecord(e->ev_c, e->s_compute));
     CT_CUDA(e, cudaStreamSynchronize(e->s_compute));  // `keep` (host vector) must outlive the copy
+    if (e->use_i8) {
+        double qi[4];
+        CT_CUDA(e, cudaMemcpy(qi, e->d_qinfo, sizeof qi, cudaMemcpyDeviceToHost));
+        e->quant_f = qi[1];
+    }
     float ms = 0.f;
     CT_CUDA(e, cudaEventElapsedTime(&ms, e->ev_a, e->ev_b)); e->stats.h2d_ms = ms;
     CT_CUDA(e, cudaEventElapsedTime(&ms, e->ev_b, e->ev_c)); e->stats.pack_ms = ms;
@@ -259,7 +292,10 @@ int ct_pack_resident(ct_engine* e, ct_stats* stats) {
     const int ncen = e->opts.solute_natoms ? e->natoms : e->K;
     CT_CUDA(e, cudaEventRecord(e->ev_a, e->s_compute));
     CT_CUDA(e, ct::launch_pack(e->d_raw, e->d_keep, (int)e->M, e->N, e->K, ncen, e->m_pad, e->kq_total, e->d_centred, e->d_G,
-                               e->use_gram ? e->d_packed : nullptr, e->sm_count, e->s_compute));
+                               (e->use_gram && !e->use_i8) ? e->d_packed : nullptr, e->sm_count, e->s_compute));
+    if (e->use_i8)
+        CT_CUDA(e, ct::launch_quant_pack(e->d_centred, (int)e->M, e->K, e->d_packA, e->d_packB, e->d_Gq, e->d_qinfo,
+                                         e->d_maxbits, e->sm_count, e->s_compute));
     CT_CUDA(e, cudaEventRecord(e->ev_b, e->s_compute));
     CT_CUDA(e, cudaStreamSynchronize(e->s_compute));
     float ms = 0.f;
@@ -272,7 +308,20 @@ int ct_pack_resident(ct_engine* e, ct_stats* stats) {
 // One chunk of rows into `dst` (device), asynchronously on s_compute.
 static int compute_rows_async(ct_engine* e, int row_begin, int row_end, double* dst, long long idx_base,
                               long long n_entries, int64_t* launches, cudaEvent_t after_main = nullptr) {
-    if (e->use_gram) {
+    if (e->use_i8) {
+        CT_CUDA(e, cudaMemsetAsync(e->d_fix_count, 0, sizeof(unsigned int), e->s_compute));
+        ct::OzParams p{};
+        p.packA = e->d_packA; p.packB = e->d_packB; p.Gq = e->d_Gq; p.qinfo = e->d_qinfo;
+        p.out = dst; p.idx_base = idx_base; p.M = (int)e->M;
+        p.row_begin = row_begin; p.row_end = row_end;
+        p.inv_k2 = 2.0 / (double)e->K; p.flag_rel = e->flag_rel;
+        p.fix.pairs = e->d_fix_pairs; p.fix.count = e->d_fix_count; p.fix.capacity = e->fix_cap;
+        CT_CUDA(e, ct::launch_gram_i8(p, e->K, e->sm_count, e->s_compute));
+        if (after_main) CT_CUDA(e, cudaEventRecord(after_main, e->s_compute));
+        CT_CUDA(e, ct::launch_fixup(e->d_centred, (int)e->M, e->K, p.fix, dst, idx_base, n_entries, e->d_counters,
+                                    e->sm_count, e->s_compute));
+        *launches += 2;
+    } else if (e->use_gram) {
         CT_CUDA(e, cudaMemsetAsync(e->d_fix_count, 0, sizeof(unsigned int), e->s_compute));
         ct::GramParams p;
         p.packed = e->d_packed; p.G = e->d_G; p.out = dst; p.idx_base = idx_base; p.M = (int)e->M;
@@ -355,7 +404,7 @@ int ct_rmsd_rows(ct_engine* e, int64_t row_begin, int64_t row_end, double* out, 
     CT_CUDA(e, cudaSetDevice(e->device));
     // Row chunks of about chunk_entries matrix entries, aligned to the Gram block height so that no
     // block of frame pairs is computed twice; chunk c+1 is computed while chunk c streams to the host.
-    const int align = e->use_gram ? ct::gram_row_align(e->gram_variant) : 1;
+    const int align = e->use_i8 ? ct::oz_row_align() : (e->use_gram ? ct::gram_row_align(e->gram_variant) : 1);
     std::vector<int64_t> cuts;
     cuts.push_back(row_begin);
     {

@@ -1,0 +1,477 @@
+// K2' — the same all-pairs cross-covariance + fused RMSD epilogue as gram.cu, but with the contraction on
+// the 5th-generation tensor cores (tcgen05.mma kind::i8, accumulators in TMEM) instead of the FP64 DMMA
+// pipe.  B200 has no FP64 tcgen05 kind, so the FP64 Gram product is rebuilt EXACTLY from integer pieces
+// (the "Ozaki scheme" for matrix products on integer tensor cores):
+//
+//   * every centred coordinate is rounded once to a 31-bit fixed-point number X = rint(x * 2^f), f chosen
+//     per run from max|x| (quantum 2^-f ~ 6e-8 A for a 40 A molecule).  That is a rigid perturbation of the
+//     INPUT by at most half a quantum per coordinate, so the RMSD moves by at most ~2^-f whatever the
+//     cancellation in G_i + G_j - 2 lambda (RMSD is 1-Lipschitz in the rms displacement);
+//   * X is cut into four balanced base-256 digits (int8 slices, X = sum_s d_s 256^(3-s));
+//   * sum_k X_i X_j = sum_{s,t} 256^(6-s-t) sum_k d_s d_t: every digit product sum is an int8 GEMM whose int32
+//     accumulator is exact (|.| < 2^25), the products with the same s+t ("level") share one accumulator;
+//     level 6 (d_3 d_3, weight 1) is below the FP64 rounding of the result and is dropped: 15 GEMMs;
+//   * the epilogue recombines the six levels in FP64 (exact int -> double conversions, weights 2^(8(6-q)-2f)),
+//     takes G from the SAME quantised coordinates, and solves the 3x3 problem as gram.cu does.
+//
+// Shape on the tensor core: one tcgen05.mma is M=128 x N=96 x K=32 (int8).  The 128 A rows are 40 frames:
+// warp-quarter w, lane 3g+a  <->  frame 10w+g, coordinate a (two zero rows per quarter), so the three rows of a
+// frame's covariance sit in three adjacent TMEM lanes of ONE epilogue warp; the 96 B rows are 32 frames x 3
+// coordinates.  A CTA owns a contiguous run of (40 x 32)-frame blocks of the upper triangle (row-major), so the A
+// operand stays in shared memory while B streams.  Operands are stored in HBM already in the canonical
+// no-swizzle K-major core-matrix order (8 rows x 16 bytes contiguous), so a pipeline stage is a handful of 1-D
+// cp.async.bulk copies and the shared-memory descriptors need no swizzle.
+//
+// Roles (384 threads, one CTA per SM): warp 0 = bulk-copy producer, warp 1 = MMA issuer (one lane), warp 2 =
+// TMEM allocator, warps 4-11 = epilogue (two warpgroups, 48 accumulator columns = 16 frame pairs per lane each).
+// TMEM: two buffers of 2 levels x 96 columns; the MMA warp fills one "level pair" while the epilogue drains the other.
+#include "common.cuh"
+#include "solve3x3.cuh"
+
+namespace ct {
+
+constexpr int OZ_FI = 40;                    // frames per A (row) tile
+constexpr int OZ_FJ = 32;                    // frames per B (column) tile
+constexpr int OZ_M = 128, OZ_N = 96;         // MMA tile
+constexpr int OZ_KB = 128;                   // atoms per K-block (= bytes per operand row per slice per stage)
+constexpr int OZ_SLICES = 4;
+constexpr int OZ_A_SLICE = OZ_M * OZ_KB;     // 16 KiB
+constexpr int OZ_B_SLICE = OZ_N * OZ_KB;     // 12 KiB
+constexpr int OZ_A_BYTES = OZ_SLICES * OZ_A_SLICE;
+constexpr int OZ_B_BYTES = OZ_SLICES * OZ_B_SLICE;
+constexpr int OZ_STAGE_BYTES = OZ_A_BYTES + OZ_B_BYTES;   // 112 KiB
+constexpr int OZ_STAGES = 2;
+constexpr int OZ_THREADS = 384;
+constexpr int OZ_SMEM_BYTES = OZ_STAGES * OZ_STAGE_BYTES + 128;
+constexpr int OZ_TMEM_COLS = 512;
+constexpr int OZ_NPAIR = 3;                  // level pairs (levels 0..5)
+
+
+// ---- tcgen05 / TMEM PTX ------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor, K-major, no swizzle: core matrix = 8 rows x 16 bytes, contiguous (128 B);
+// LBO = byte distance between the two 16-byte K halves of one MMA, SBO = byte distance between 8-row groups.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = (uint64_t)((addr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version of sm_100
+    return d;
+}
+// Instruction descriptor of kind::i8: D = s32, A = B = signed 8 bit, both K-major, dense.
+constexpr uint32_t OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_N >> 3) << 17) | ((uint32_t)(OZ_M >> 4) << 24);
+
+// ---- block walk ------------------------------------------------------------------------------------------------
+// Blocks (ti, tj) of the upper triangle: rows [40 ti, 40 ti + 40) x columns [32 tj, 32 tj + 32), needed when some
+// j > i falls inside, i.e. tj >= (40 ti + 1) / 32.  Row-major enumeration; a CTA takes a contiguous run.
+struct OzWalker {
+    int ti, tj, ntj;
+    long long left;
+    __host__ __device__ static int first_tj(int ti) { return (OZ_FI * ti + 1) / OZ_FJ; }
+    __device__ void init(int ti_begin, int ntj_, long long start, long long count) {
+        ntj = ntj_; left = count; ti = ti_begin;
+        long long s = start;
+        for (;;) {
+            const long long n = ntj - first_tj(ti);
+            if (s < n) break;
+            s -= n; ++ti;
+        }
+        tj = first_tj(ti) + (int)s;
+    }
+    __device__ bool valid() const { return left > 0; }
+    __device__ void next() {
+        --left;
+        if (++tj >= ntj) { ++ti; tj = first_tj(ti); }
+    }
+};
+
+// exact  e * 256 + o  ->  double  without an I2F.F64: add the integer to the bit pattern of 2^52 + 2^51
+__device__ __forceinline__ double level_pair(int e, int o) {
+    const long long v = (long long)e * 256 + (long long)o;  // |v| < 2^34
+    const int hi = (int)(v >> 32) + 0x43380000;
+    return __hiloint2double(hi, (int)(unsigned)(v & 0xffffffffLL)) - 6755399441055744.0;
+}
+
+__device__ __forceinline__ double sel3(int k, double x0, double x1, double x2) { return k == 0 ? x0 : (k == 1 ? x1 : x2); }
+
+__global__ void __launch_bounds__(OZ_THREADS, 1) gram_i8_kernel(const OzParams p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OZ_STAGES * OZ_STAGE_BYTES);
+    uint64_t* full = bars;            // [2] stage loaded (tx bytes)
+    uint64_t* empty = bars + 2;       // [2] stage consumed (tcgen05.commit)
+    uint64_t* tfull = bars + 4;       // [2] TMEM level pair complete (tcgen05.commit)
+    uint64_t* tempty = bars + 6;      // [2] TMEM level pair drained (8 epilogue warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ti_begin = p.row_begin / OZ_FI;
+    const int ntj = (p.M + OZ_FJ - 1) / OZ_FJ;
+    const long long blk_start = p.total_blocks * blockIdx.x / gridDim.x;
+    const long long blk_count = p.total_blocks * (blockIdx.x + 1) / gridDim.x - blk_start;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&full[s], 1); mbar_init(&empty[s], 1);
+            mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, OZ_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        if (warp == 0 && lane == 0) {
+            // ---- producer: 1-D bulk copies of pre-laid-out operand slices -------------------------------------
+            OzWalker w;
+            w.init(ti_begin, ntj, blk_start, blk_count);
+            int stage = 0; uint32_t phase = 0;
+            long long tagA[2] = {-1, -1};
+            for (; w.valid(); w.next()) {
+                for (int kb = 0; kb < p.nkb; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    const int nch = (kb == p.nkb - 1) ? p.last_chunks : 4;
+                    const long long tag = (long long)w.ti * p.nkb + kb;
+                    const bool loadA = tagA[stage] != tag;
+                    tagA[stage] = tag;
+                    const uint32_t a_bytes = (uint32_t)nch * (OZ_A_SLICE / 4), b_bytes = (uint32_t)nch * (OZ_B_SLICE / 4);
+                    mbar_expect_tx(&full[stage], OZ_SLICES * ((loadA ? a_bytes : 0u) + b_bytes));
+                    unsigned char* sA = smem + stage * OZ_STAGE_BYTES;
+                    unsigned char* sB = sA + OZ_A_BYTES;
+                    const uint8_t* gA = p.packA + ((size_t)w.ti * p.nkb + kb) * OZ_A_BYTES;
+                    const uint8_t* gB = p.packB + ((size_t)w.tj * p.nkb + kb) * OZ_B_BYTES;
+#pragma unroll
+                    for (int s = 0; s < OZ_SLICES; ++s) {
+                        if (loadA) bulk_g2s(sA + s * OZ_A_SLICE, gA + s * OZ_A_SLICE, a_bytes, &full[stage]);
+                        bulk_g2s(sB + s * OZ_B_SLICE, gB + s * OZ_B_SLICE, b_bytes, &full[stage]);
+                    }
+                    stage ^= 1; if (stage == 0) phase ^= 1;
+                }
+            }
+        } else if (warp == 1) {
+            // ---- MMA issuer ------------------------------------------------------------------------------------
+            int stage = 0; uint32_t phase = 0;
+            int tb = 0; uint32_t tphase = 0;
+            const long long n_stage = blk_count * p.nkb;
+            for (long long it = 0; it < n_stage; ++it) {
+                const int kb = (int)(it % p.nkb);
+                const int nch = (kb == p.nkb - 1) ? p.last_chunks : 4;
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                const uint32_t aBase = smem_u32(smem + stage * OZ_STAGE_BYTES);
+                const uint32_t bBase = aBase + OZ_A_BYTES;
+#pragma unroll 1
+                for (int pr = 0; pr < OZ_NPAIR; ++pr) {
+                    mbar_wait(&tempty[tb], tphase ^ 1);
+                    tc_fence_after();
+                    if (lane == 0) {
+#pragma unroll 1
+                        for (int lv = 0; lv < 2; ++lv) {
+                            const int q = 2 * pr + lv;
+                            const uint32_t d = tmem_base + (uint32_t)(tb * 2 * OZ_N + lv * OZ_N);
+                            uint32_t acc = 0;
+                            const int s_lo = q > 3 ? q - 3 : 0, s_hi = q < 3 ? q : 3;
+#pragma unroll 1
+                            for (int s = s_lo; s <= s_hi; ++s) {
+                                const int t = q - s;
+#pragma unroll 1
+                                for (int kc = 0; kc < nch; ++kc) {
+                                    // one MMA covers 32 atoms = two 16-byte K halves; a K half of all rows is
+                                    // (rows/8) core matrices = 2048 B (A) / 1536 B (B)
+                                    const uint64_t ad = smem_desc(aBase + s * OZ_A_SLICE + kc * 2 * (OZ_M * 16), OZ_M * 16, 128);
+                                    const uint64_t bd = smem_desc(bBase + t * OZ_B_SLICE + kc * 2 * (OZ_N * 16), OZ_N * 16, 128);
+                                    umma_i8(d, ad, bd, OZ_IDESC, acc);
+                                    acc = 1;
+                                }
+                            }
+                        }
+                        umma_commit(&tfull[tb]);
+                    }
+                    __syncwarp();
+                    tb ^= 1; if (tb == 0) tphase ^= 1;
+                }
+                if (lane == 0) umma_commit(&empty[stage]);
+                __syncwarp();
+                stage ^= 1; if (stage == 0) phase ^= 1;
+            }
+        }
+    } else {
+        // ---- epilogue warps ------------------------------------------------------------------------------------
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        const int quarter = warp & 3;            // TMEM lanes 32 * quarter .. + 31
+        const int half = (warp - 4) >> 2;        // accumulator columns 48 * half .. + 47 = frames 16 * half .. + 15
+        const int g = lane / 3, a = lane - 3 * g;
+        const bool row_ok = lane < 30;
+        const int src1 = (lane - a + (a + 1) % 3) & 31, src2 = (lane - a + (a + 2) % 3) & 31;
+        const int u1 = (a + 2) % 3, u2 = (a + 1) % 3;   // which of the three pairs this lane SENDS in shuffle 1 / 2
+        const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 48);
+        const double s2 = p.qinfo[0];
+        const double sc[OZ_NPAIR] = {s2 * 1099511627776.0, s2 * 16777216.0, s2 * 256.0};   // 2^40, 2^24, 2^8
+        const int last_row = min(p.row_end, p.M - 1);
+        OzWalker w;
+        w.init(ti_begin, ntj, blk_start, blk_count);
+        int tb = 0; uint32_t tphase = 0;
+        for (; w.valid(); w.next()) {
+            double acc[48];
+#pragma unroll
+            for (int n = 0; n < 48; ++n) acc[n] = 0.0;
+            for (int kb = 0; kb < p.nkb; ++kb) {
+#pragma unroll
+                for (int pr = 0; pr < OZ_NPAIR; ++pr) {
+                    mbar_wait(&tfull[tb], tphase);
+                    tc_fence_after();
+                    const uint32_t t0 = tlane + (uint32_t)(tb * 2 * OZ_N);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        uint32_t ev[16], od[16];
+                        tmem_ld16(t0 + c * 16, ev);
+                        tmem_ld16(t0 + OZ_N + c * 16, od);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int n = 0; n < 16; ++n)
+                            acc[c * 16 + n] = fma(level_pair((int)ev[n], (int)od[n]), sc[pr], acc[c * 16 + n]);
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[tb]);
+                    tb ^= 1; if (tb == 0) tphase ^= 1;
+                }
+            }
+            // ---- 3x3 solve: lanes 3g, 3g+1, 3g+2 hold the three rows of the covariances of frame i with 16 frames j;
+            // lane a takes the pairs jj = 3m + a and collects the two other rows with shuffles.  The rows arrive in
+            // cyclic order (a, a+1, a+2), which leaves |S|^2, |cof S|^2 and det S unchanged.
+            const int i = w.ti * OZ_FI + quarter * 10 + g;
+            const int j0 = w.tj * OZ_FJ + half * 16;
+            const double gi = p.Gq[i];
+            const bool row_mine = row_ok && i >= p.row_begin && i < last_row;
+            const long long row_off = condensed_row_base(p.M, i) - p.idx_base - i - 1;
+#pragma unroll
+            for (int batch = 0; batch < 2; ++batch) {
+                double qa[3], qb[3], qd[3], hg[3], lam[3];
+#pragma unroll
+                for (int mm = 0; mm < 3; ++mm) {
+                    const int m = batch * 3 + mm;
+                    double s9[9];
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) {
+                        const double r0 = acc[9 * m + b];
+                        const double r1 = (9 * m + 3 + b < 48) ? acc[(9 * m + 3 + b) % 48] : 0.0;
+                        const double r2 = (9 * m + 6 + b < 48) ? acc[(9 * m + 6 + b) % 48] : 0.0;
+                        s9[b] = sel3(a, r0, r1, r2);
+                        s9[3 + b] = __shfl_sync(0xffffffffu, sel3(u1, r0, r1, r2), src1);
+                        s9[6 + b] = __shfl_sync(0xffffffffu, sel3(u2, r0, r1, r2), src2);
+                    }
+                    quartic_invariants(s9, qa[mm], qb[mm], qd[mm]);
+                    const int j = j0 + 3 * m + a;
+                    hg[mm] = gi + p.Gq[j];
+                }
+                const unsigned okmask = largest_root_lockstep<3>(qa, qb, qd, hg, lam);
+#pragma unroll
+                for (int mm = 0; mm < 3; ++mm) {
+                    const int jj = 3 * (batch * 3 + mm) + a;
+                    const int j = j0 + jj;
+                    const double eh = hg[mm] - lam[mm];
+                    const double v = fmax(eh, 0.0) * p.inv_k2;
+                    const float y = rsqrtf(fmaxf((float)v, 1e-37f));
+                    double r = v * (double)y;
+                    r = fma(fma(-r, r, v), (double)(0.5f * y), r);
+                    const bool ok = (okmask >> mm) & 1u;
+                    const bool mine = row_mine && jj < 16 && i < j && j < p.M;
+                    if ((!ok || eh < p.flag_rel * hg[mm]) && mine) {
+                        const unsigned int t = atomicAdd(p.fix.count, 1u);
+                        if (t < p.fix.capacity) p.fix.pairs[t] = make_int2(i, j);
+                        else r = -1.0;
+                    }
+                    if (mine) p.out[row_off + j] = r;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, OZ_TMEM_COLS);
+}
+
+// ---- quantise + slice + lay out ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) maxabs_kernel(const double* __restrict__ x, long long n, unsigned long long* out) {
+    double m = 0.0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) m = fmax(m, fabs(x[k]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(m));  // m >= 0: bit order = value order
+}
+
+// f such that |X| = |rint(x 2^f)| <= 2^30 for every coordinate
+__device__ __forceinline__ int quant_exponent(unsigned long long maxbits) {
+    const double m = __longlong_as_double((long long)maxbits);
+    if (!(m > 0.0)) return 30;
+    int e;
+    frexp(m, &e);  // m = frac * 2^e, frac in [0.5, 1)  =>  m < 2^e
+    return 30 - e;
+}
+
+__global__ void quant_info_kernel(const unsigned long long* maxbits, double* qinfo) {
+    const int f = quant_exponent(*maxbits);
+    qinfo[0] = ldexp(1.0, -2 * f);
+    qinfo[1] = (double)f;
+    qinfo[2] = __longlong_as_double((long long)*maxbits);
+}
+
+// one thread = 16 consecutive atoms of one coordinate of one frame -> one 16-byte run per slice in each layout
+__global__ void __launch_bounds__(256) quant_pack_kernel(const double* __restrict__ centred, int M, int K, int nkb,
+                                                         const unsigned long long* __restrict__ maxbits,
+                                                         uint8_t* __restrict__ packA, uint8_t* __restrict__ packB) {
+    const int groups = nkb * 8;  // 16-atom groups per row
+    const long long total = (long long)M * 3 * groups;
+    const double scale = ldexp(1.0, quant_exponent(*maxbits));
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += stride) {
+        const int g16 = (int)(o % groups);
+        const long long rest = o / groups;
+        const int c = (int)(rest % 3);
+        const int fr = (int)(rest / 3);
+        uint32_t w[4][4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) w[s][q] = 0u;
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            const int k = g16 * 16 + t;
+            int X = 0;
+            if (k < K) X = (int)rint(centred[((size_t)fr * K + k) * 3 + c] * scale);
+            // balanced base-256 digits, most significant first in slice 0
+            const int d3 = (int)(signed char)(X & 0xff); X = (X - d3) >> 8;
+            const int d2 = (int)(signed char)(X & 0xff); X = (X - d2) >> 8;
+            const int d1 = (int)(signed char)(X & 0xff); X = (X - d1) >> 8;
+            const int d0 = X;
+            const int sh = (t & 3) * 8;
+            w[0][t >> 2] |= (uint32_t)(d0 & 0xff) << sh;
+            w[1][t >> 2] |= (uint32_t)(d1 & 0xff) << sh;
+            w[2][t >> 2] |= (uint32_t)(d2 & 0xff) << sh;
+            w[3][t >> 2] |= (uint32_t)(d3 & 0xff) << sh;
+        }
+        const int kb = g16 >> 3, kc16 = g16 & 7;
+        {
+            const int ti = fr / OZ_FI, fi = fr - ti * OZ_FI;
+            const int row = (fi / 10) * 32 + (fi % 10) * 3 + c;
+            uint8_t* dst = packA + ((size_t)ti * nkb + kb) * OZ_A_BYTES + (size_t)kc16 * (OZ_M * 16) + (row >> 3) * 128 + (row & 7) * 16;
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+                *reinterpret_cast<uint4*>(dst + s * OZ_A_SLICE) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
+        }
+        {
+            const int tj = fr / OZ_FJ, fj = fr - tj * OZ_FJ;
+            const int row = fj * 3 + c;
+            uint8_t* dst = packB + ((size_t)tj * nkb + kb) * OZ_B_BYTES + (size_t)kc16 * (OZ_N * 16) + (row >> 3) * 128 + (row & 7) * 16;
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+                *reinterpret_cast<uint4*>(dst + s * OZ_B_SLICE) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
+        }
+    }
+}
+
+// half sum of squares of the quantised coordinates (what the integer Gram product is consistent with)
+__global__ void __launch_bounds__(128) quant_g_kernel(const double* __restrict__ centred, int M, int K,
+                                                      const unsigned long long* __restrict__ maxbits, double* __restrict__ Gq) {
+    const int fr = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (fr >= M) return;
+    const int f = quant_exponent(*maxbits);
+    const double scale = ldexp(1.0, f);
+    const double* src = centred + (size_t)fr * K * 3;
+    double g = 0.0;
+    for (int k = lane; k < 3 * K; k += 32) {
+        const double X = rint(src[k] * scale);
+        g = fma(X, X, g);
+    }
+    g = warp_sum(g);
+    if (lane == 0) Gq[fr] = 0.5 * g * ldexp(1.0, -2 * f);
+}
+
+size_t oz_packA_bytes(int M, int K) { return (size_t)((M + OZ_FI - 1) / OZ_FI) * ((K + OZ_KB - 1) / OZ_KB) * OZ_A_BYTES; }
+size_t oz_packB_bytes(int M, int K) { return (size_t)((M + OZ_FJ - 1) / OZ_FJ) * ((K + OZ_KB - 1) / OZ_KB) * OZ_B_BYTES; }
+size_t oz_g_entries(int M) {
+    const size_t a = (size_t)((M + OZ_FI - 1) / OZ_FI) * OZ_FI, b = (size_t)((M + OZ_FJ - 1) / OZ_FJ) * OZ_FJ;
+    return (a > b ? a : b) + 64;
+}
+int oz_row_align() { return OZ_FI; }
+
+cudaError_t launch_quant_pack(const double* centred, int M, int K, uint8_t* packA, uint8_t* packB, double* Gq, double* qinfo,
+                              unsigned long long* maxbits, int sm_count, cudaStream_t stream) {
+    const int nkb = (K + OZ_KB - 1) / OZ_KB;
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(maxbits, 0, sizeof(unsigned long long), stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(packA, 0, oz_packA_bytes(M, K), stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(packB, 0, oz_packB_bytes(M, K), stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(Gq, 0, sizeof(double) * oz_g_entries(M), stream)) != cudaSuccess) return e;
+    const long long n = (long long)M * K * 3;
+    long long blocks = (n + 255) / 256;
+    if (blocks > (long long)sm_count * 8) blocks = (long long)sm_count * 8;
+    maxabs_kernel<<<(unsigned)blocks, 256, 0, stream>>>(centred, n, maxbits);
+    quant_info_kernel<<<1, 1, 0, stream>>>(maxbits, qinfo);
+    const long long total = (long long)M * 3 * nkb * 8;
+    blocks = (total + 255) / 256;
+    if (blocks > (long long)sm_count * 16) blocks = (long long)sm_count * 16;
+    quant_pack_kernel<<<(unsigned)blocks, 256, 0, stream>>>(centred, M, K, nkb, maxbits, packA, packB);
+    quant_g_kernel<<<(M + 3) / 4, 128, 0, stream>>>(centred, M, K, maxbits, Gq);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gram_i8(OzParams p, int K, int sm_count, cudaStream_t stream) {
+    p.nkb = (K + OZ_KB - 1) / OZ_KB;
+    const int tail = K - (p.nkb - 1) * OZ_KB;
+    p.last_chunks = (tail + 31) / 32;
+    const int ti_begin = p.row_begin / OZ_FI;
+    const int last_row = p.row_end < p.M - 1 ? p.row_end : p.M - 1;
+    const int ti_end = (last_row + OZ_FI - 1) / OZ_FI;
+    const long long ntj = (p.M + OZ_FJ - 1) / OZ_FJ;
+    long long blocks = 0;
+    for (int ti = ti_begin; ti < ti_end; ++ti) blocks += ntj - OzWalker::first_tj(ti);
+    if (blocks <= 0) return cudaSuccess;
+    p.total_blocks = blocks;
+    cudaError_t e = cudaFuncSetAttribute(gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    const long long grid = blocks < sm_count ? blocks : sm_count;
+    gram_i8_kernel<<<(unsigned)grid, OZ_THREADS, OZ_SMEM_BYTES, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace ct
