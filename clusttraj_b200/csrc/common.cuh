@@ -36,7 +36,8 @@ struct GramParams {
 // parameters of the int8 tensor-core (tcgen05) Gram kernel, ozaki.cu
 struct OzParams {
     const uint8_t* packA;   // [ti][kb][slice][kc16 (8)][row group (16)][8 rows][16 B]
-    const uint8_t* packB;   // [tj][kb][slice][kc16 (8)][row group (12)][8 rows][16 B]
+    const uint8_t* packB;
+    const uint8_t* packT;   // [ti][128 rows][slice][128 B] (single K-block only): the A tile as TMEM lanes read it   // [tj][kb][slice][kc16 (8)][row group (12)][8 rows][16 B]
     const double* Gq;       // half sums of squares of the QUANTISED coordinates, real units
     const double* qinfo;    // [0] = 2^(-2f), [1] = f, [2] = max |x|
     double* out;
@@ -44,6 +45,8 @@ struct OzParams {
     long long total_blocks;
     int M, nkb, last_chunks;   // K-blocks; 32-atom chunks in the last K-block (1..4)
     int row_begin, row_end;
+    unsigned long long* prof;  // optional per-CTA cycle counters [grid][8] (development)
+    int dbg;                   // development switches (bit 0: skip the 3x3 solve, 1: skip the accumulate math, 2: skip the MMAs)
     double inv_k2, flag_rel;
     FixList fix;
 };
@@ -92,6 +95,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+// Same, with a suspend-time hint: the waiting warp sleeps in hardware (up to `ns`) instead of re-issuing the
+// probe every few cycles, which would take issue slots from the warps it is waiting for.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns = 20000u) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(ns)
         : "memory");
 }
 // 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP).

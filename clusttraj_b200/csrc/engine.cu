@@ -21,8 +21,8 @@ size_t oz_packA_bytes(int M, int K);
 size_t oz_packB_bytes(int M, int K);
 size_t oz_g_entries(int M);
 int oz_row_align();
-cudaError_t launch_quant_pack(const double* centred, int M, int K, uint8_t* packA, uint8_t* packB, double* Gq, double* qinfo,
-                              unsigned long long* maxbits, int sm_count, cudaStream_t stream);
+cudaError_t launch_quant_pack(const double* centred, int M, int K, uint8_t* packA, uint8_t* packB, uint8_t* packT, double* Gq,
+                              double* qinfo, unsigned long long* maxbits, int sm_count, cudaStream_t stream);
 cudaError_t launch_gram_i8(OzParams p, int K, int sm_count, cudaStream_t stream);
 cudaError_t launch_fixup(const double* centred, int M, int K, const FixList& fix, double* out, long long idx_base,
                          long long n_entries, unsigned long long* flagged_total, int sm_count, cudaStream_t stream);
@@ -59,10 +59,12 @@ struct ct_engine {
     bool use_i8 = false;
     uint8_t* d_packA = nullptr; size_t packA_cap = 0;
     uint8_t* d_packB = nullptr; size_t packB_cap = 0;
+    uint8_t* d_packT = nullptr; size_t packT_cap = 0;
     double* d_Gq = nullptr; size_t gq_cap = 0;
     double* d_qinfo = nullptr;               // [0] 2^-2f, [1] f, [2] max |x|
     unsigned long long* d_maxbits = nullptr;
     double quant_f = 0.0;
+    unsigned long long* d_prof = nullptr;
     ct::PairPlanHost* plan = nullptr;
     // outputs
     double* d_slab = nullptr; size_t slab_cap = 0;       // whole-slab device buffer (rows_device)
@@ -165,7 +167,7 @@ void ct_engine_destroy(ct_engine* e) {
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     cudaFree(e->d_raw); cudaFree(e->d_keep); cudaFree(e->d_centred); cudaFree(e->d_G); cudaFree(e->d_packed);
-    cudaFree(e->d_packA); cudaFree(e->d_packB); cudaFree(e->d_Gq); cudaFree(e->d_qinfo); cudaFree(e->d_maxbits);
+    cudaFree(e->d_packA); cudaFree(e->d_packB); cudaFree(e->d_packT); cudaFree(e->d_Gq); cudaFree(e->d_qinfo); cudaFree(e->d_maxbits);
     cudaFree(e->d_slab); cudaFree(e->d_chunk[0]); cudaFree(e->d_chunk[1]);
     cudaFree(e->d_fix_pairs); cudaFree(e->d_fix_count); cudaFree(e->d_counters);
     for (int k = 0; k < 2; ++k) { cudaEventDestroy(e->ev_chunk_done[k]); cudaEventDestroy(e->ev_copy_done[k]); }
@@ -251,6 +253,7 @@ int ct_load_frames(ct_engine* e, const double* coords, const int32_t* atomic_num
     if (e->use_i8) {
         if ((rc = ensure(e, e->d_packA, e->packA_cap, ct::oz_packA_bytes((int)M, K)))) return rc;
         if ((rc = ensure(e, e->d_packB, e->packB_cap, ct::oz_packB_bytes((int)M, K)))) return rc;
+        if ((rc = ensure(e, e->d_packT, e->packT_cap, ct::oz_packA_bytes((int)M, K)))) return rc;
         if ((rc = ensure(e, e->d_Gq, e->gq_cap, ct::oz_g_entries((int)M)))) return rc;
     }
 
@@ -261,8 +264,8 @@ int ct_load_frames(ct_engine* e, const double* coords, const int32_t* atomic_num
     CT_CUDA(e, ct::launch_pack(e->d_raw, e->d_keep, (int)M, N, K, ncen, e->m_pad, e->kq_total, e->d_centred, e->d_G,
                                (e->use_gram && !e->use_i8) ? e->d_packed : nullptr, e->sm_count, e->s_compute));
     if (e->use_i8)
-        CT_CUDA(e, ct::launch_quant_pack(e->d_centred, (int)M, K, e->d_packA, e->d_packB, e->d_Gq, e->d_qinfo, e->d_maxbits,
-                                         e->sm_count, e->s_compute));
+        CT_CUDA(e, ct::launch_quant_pack(e->d_centred, (int)M, K, e->d_packA, e->d_packB, e->d_packT, e->d_Gq, e->d_qinfo,
+                                         e->d_maxbits, e->sm_count, e->s_compute));
     CT_CUDA(e, cudaEventRecord(e->ev_c, e->s_compute));
     CT_CUDA(e, cudaStreamSynchronize(e->s_compute));  // `keep` (host vector) must outlive the copy
     if (e->use_i8) {
@@ -294,7 +297,7 @@ int ct_pack_resident(ct_engine* e, ct_stats* stats) {
     CT_CUDA(e, ct::launch_pack(e->d_raw, e->d_keep, (int)e->M, e->N, e->K, ncen, e->m_pad, e->kq_total, e->d_centred, e->d_G,
                                (e->use_gram && !e->use_i8) ? e->d_packed : nullptr, e->sm_count, e->s_compute));
     if (e->use_i8)
-        CT_CUDA(e, ct::launch_quant_pack(e->d_centred, (int)e->M, e->K, e->d_packA, e->d_packB, e->d_Gq, e->d_qinfo,
+        CT_CUDA(e, ct::launch_quant_pack(e->d_centred, (int)e->M, e->K, e->d_packA, e->d_packB, e->d_packT, e->d_Gq, e->d_qinfo,
                                          e->d_maxbits, e->sm_count, e->s_compute));
     CT_CUDA(e, cudaEventRecord(e->ev_b, e->s_compute));
     CT_CUDA(e, cudaStreamSynchronize(e->s_compute));
@@ -311,12 +314,25 @@ static int compute_rows_async(ct_engine* e, int row_begin, int row_end, double* 
     if (e->use_i8) {
         CT_CUDA(e, cudaMemsetAsync(e->d_fix_count, 0, sizeof(unsigned int), e->s_compute));
         ct::OzParams p{};
-        p.packA = e->d_packA; p.packB = e->d_packB; p.Gq = e->d_Gq; p.qinfo = e->d_qinfo;
+        p.packA = e->d_packA; p.packB = e->d_packB; p.packT = e->d_packT; p.Gq = e->d_Gq; p.qinfo = e->d_qinfo;
         p.out = dst; p.idx_base = idx_base; p.M = (int)e->M;
         p.row_begin = row_begin; p.row_end = row_end;
         p.inv_k2 = 2.0 / (double)e->K; p.flag_rel = e->flag_rel;
         p.fix.pairs = e->d_fix_pairs; p.fix.count = e->d_fix_count; p.fix.capacity = e->fix_cap;
+        { const char* dv = getenv("CLUSTTRAJ_B200_OZ_DBG"); p.dbg = dv ? atoi(dv) : 0; }
+        const bool prof = getenv("CLUSTTRAJ_B200_OZ_PROF") != nullptr;
+        if (prof && !e->d_prof) CT_CUDA(e, cudaMalloc(&e->d_prof, sizeof(unsigned long long) * 8 * 1024));
+        p.prof = prof ? e->d_prof : nullptr;
         CT_CUDA(e, ct::launch_gram_i8(p, e->K, e->sm_count, e->s_compute));
+        if (prof) {  // development: per-role cycle counters of CTA 0 and the CTA in the middle of the grid
+            std::vector<unsigned long long> h(8 * 1024);
+            CT_CUDA(e, cudaStreamSynchronize(e->s_compute));
+            CT_CUDA(e, cudaMemcpy(h.data(), e->d_prof, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost));
+            for (int c : {0, e->sm_count / 2})
+                fprintf(stderr, "[oz prof cta %d] p0 %llu p1 %llu | mma wait_full %llu wait_tempty %llu total %llu | "
+                                "epi wait_tfull %llu p6 %llu total %llu  (ts: p0/p1 = solver wait_cfull/total, p6 = acc wait_cempty)\n", c, h[c * 8 + 0], h[c * 8 + 1], h[c * 8 + 2],
+                        h[c * 8 + 3], h[c * 8 + 4], h[c * 8 + 5], h[c * 8 + 6], h[c * 8 + 7]);
+        }
         if (after_main) CT_CUDA(e, cudaEventRecord(after_main, e->s_compute));
         CT_CUDA(e, ct::launch_fixup(e->d_centred, (int)e->M, e->K, p.fix, dst, idx_base, n_entries, e->d_counters,
                                     e->sm_count, e->s_compute));

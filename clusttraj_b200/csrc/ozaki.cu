@@ -80,6 +80,34 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "r"(taddr)
         : "memory");
 }
+// A operand in TMEM (".ts"): row m of A in TMEM lane m, 32 int8 of K per 8 columns
+__device__ __forceinline__ void umma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+        "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+        "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor, K-major, no swizzle: core matrix = 8 rows x 16 bytes, contiguous (128 B);
@@ -164,9 +192,13 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) gram_i8_kernel(const OzParams p
             w.init(ti_begin, ntj, blk_start, blk_count);
             int stage = 0; uint32_t phase = 0;
             long long tagA[2] = {-1, -1};
+            long long t_wait = 0;
+            const long long t_begin = clock64();
             for (; w.valid(); w.next()) {
                 for (int kb = 0; kb < p.nkb; ++kb) {
+                    const long long t0 = clock64();
                     mbar_wait(&empty[stage], phase ^ 1);
+                    t_wait += clock64() - t0;
                     const int nch = (kb == p.nkb - 1) ? p.last_chunks : 4;
                     const long long tag = (long long)w.ti * p.nkb + kb;
                     const bool loadA = tagA[stage] != tag;
@@ -185,51 +217,66 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) gram_i8_kernel(const OzParams p
                     stage ^= 1; if (stage == 0) phase ^= 1;
                 }
             }
+            if (p.prof) { p.prof[blockIdx.x * 8 + 0] = t_wait; p.prof[blockIdx.x * 8 + 1] = clock64() - t_begin; }
         } else if (warp == 1) {
             // ---- MMA issuer ------------------------------------------------------------------------------------
             int stage = 0; uint32_t phase = 0;
             int tb = 0; uint32_t tphase = 0;
             const long long n_stage = blk_count * p.nkb;
+            long long t_full = 0, t_tempty = 0;
+            const long long t_begin = clock64();
             for (long long it = 0; it < n_stage; ++it) {
                 const int kb = (int)(it % p.nkb);
                 const int nch = (kb == p.nkb - 1) ? p.last_chunks : 4;
+                const long long t0 = clock64();
                 mbar_wait(&full[stage], phase);
+                t_full += clock64() - t0;
                 tc_fence_after();
                 const uint32_t aBase = smem_u32(smem + stage * OZ_STAGE_BYTES);
                 const uint32_t bBase = aBase + OZ_A_BYTES;
-#pragma unroll 1
+                // descriptor words: only the 14-bit address field changes from one MMA to the next
+                constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);                 // SBO = 128 B, version 1
+                const uint32_t a_lo = ((uint32_t)(OZ_M * 16 >> 4) << 16) | (aBase >> 4);  // LBO = one K half of all rows
+                const uint32_t b_lo = ((uint32_t)(OZ_N * 16 >> 4) << 16) | (bBase >> 4);
+#pragma unroll
                 for (int pr = 0; pr < OZ_NPAIR; ++pr) {
+                    const long long t1 = clock64();
                     mbar_wait(&tempty[tb], tphase ^ 1);
+                    t_tempty += clock64() - t1;
                     tc_fence_after();
-                    if (lane == 0) {
-#pragma unroll 1
+                    if (lane == 0 && !(p.dbg & 4)) {
+#pragma unroll
                         for (int lv = 0; lv < 2; ++lv) {
                             const int q = 2 * pr + lv;
                             const uint32_t d = tmem_base + (uint32_t)(tb * 2 * OZ_N + lv * OZ_N);
-                            uint32_t acc = 0;
                             const int s_lo = q > 3 ? q - 3 : 0, s_hi = q < 3 ? q : 3;
-#pragma unroll 1
+#pragma unroll
                             for (int s = s_lo; s <= s_hi; ++s) {
-                                const int t = q - s;
-#pragma unroll 1
-                                for (int kc = 0; kc < nch; ++kc) {
-                                    // one MMA covers 32 atoms = two 16-byte K halves; a K half of all rows is
-                                    // (rows/8) core matrices = 2048 B (A) / 1536 B (B)
-                                    const uint64_t ad = smem_desc(aBase + s * OZ_A_SLICE + kc * 2 * (OZ_M * 16), OZ_M * 16, 128);
-                                    const uint64_t bd = smem_desc(bBase + t * OZ_B_SLICE + kc * 2 * (OZ_N * 16), OZ_N * 16, 128);
-                                    umma_i8(d, ad, bd, OZ_IDESC, acc);
-                                    acc = 1;
+#pragma unroll
+                                for (int kc = 0; kc < 4; ++kc) {
+                                    if (kc < nch) {
+                                        // one MMA = 32 atoms = two 16-byte K halves of (rows / 8) core matrices each
+                                        const uint64_t ad = ((uint64_t)DESC_HI << 32) |
+                                                            (a_lo + (uint32_t)((s * OZ_A_SLICE + kc * 2 * OZ_M * 16) >> 4));
+                                        const uint64_t bd = ((uint64_t)DESC_HI << 32) |
+                                                            (b_lo + (uint32_t)(((q - s) * OZ_B_SLICE + kc * 2 * OZ_N * 16) >> 4));
+                                        umma_i8(d, ad, bd, OZ_IDESC, (s > s_lo || kc > 0) ? 1u : 0u);
+                                    }
                                 }
                             }
                         }
-                        umma_commit(&tfull[tb]);
                     }
+                    if (lane == 0) umma_commit(&tfull[tb]);
                     __syncwarp();
                     tb ^= 1; if (tb == 0) tphase ^= 1;
                 }
                 if (lane == 0) umma_commit(&empty[stage]);
                 __syncwarp();
                 stage ^= 1; if (stage == 0) phase ^= 1;
+            }
+            if (p.prof && lane == 0) {
+                p.prof[blockIdx.x * 8 + 2] = t_full; p.prof[blockIdx.x * 8 + 3] = t_tempty;
+                p.prof[blockIdx.x * 8 + 4] = clock64() - t_begin;
             }
         }
     } else {
@@ -248,6 +295,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) gram_i8_kernel(const OzParams p
         OzWalker w;
         w.init(ti_begin, ntj, blk_start, blk_count);
         int tb = 0; uint32_t tphase = 0;
+        long long t_tfull = 0, t_solve = 0, t_ld = 0;
+        const long long t_begin = clock64();
         for (; w.valid(); w.next()) {
             double acc[48];
 #pragma unroll
@@ -255,18 +304,35 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) gram_i8_kernel(const OzParams p
             for (int kb = 0; kb < p.nkb; ++kb) {
 #pragma unroll
                 for (int pr = 0; pr < OZ_NPAIR; ++pr) {
+                    const long long tw = clock64();
                     mbar_wait(&tfull[tb], tphase);
+                    t_tfull += clock64() - tw;
                     tc_fence_after();
                     const uint32_t t0 = tlane + (uint32_t)(tb * 2 * OZ_N);
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        uint32_t ev[16], od[16];
-                        tmem_ld16(t0 + c * 16, ev);
-                        tmem_ld16(t0 + OZ_N + c * 16, od);
+                    if (!(p.dbg & 2)) {
+                        uint32_t ev[2][16], od[2][16];
+                        const long long tl0 = clock64();
+                        tmem_ld16(t0, ev[0]);
+                        tmem_ld16(t0 + OZ_N, od[0]);
                         tmem_wait_ld();
+                        t_ld += clock64() - tl0;
 #pragma unroll
-                        for (int n = 0; n < 16; ++n)
-                            acc[c * 16 + n] = fma(level_pair((int)ev[n], (int)od[n]), sc[pr], acc[c * 16 + n]);
+                        for (int c = 0; c < 3; ++c) {
+                            if (c + 1 < 3) {  // the next 16 columns travel while these are converted
+                                tmem_ld16(t0 + (c + 1) * 16, ev[(c + 1) & 1]);
+                                tmem_ld16(t0 + OZ_N + (c + 1) * 16, od[(c + 1) & 1]);
+                            }
+                            if (p.dbg & 8) {  // development: TMEM loads only
+                                uint32_t x = 0;
+#pragma unroll
+                                for (int n = 0; n < 16; ++n) x ^= ev[c & 1][n] ^ od[c & 1][n];
+                                acc[c] += __hiloint2double(0, (int)x);
+                            } else
+#pragma unroll
+                            for (int n = 0; n < 16; ++n)
+                                acc[c * 16 + n] = fma(level_pair((int)ev[c & 1][n], (int)od[c & 1][n]), sc[pr], acc[c * 16 + n]);
+                            if (c + 1 < 3) { const long long tl1 = clock64(); tmem_wait_ld(); t_ld += clock64() - tl1; }
+                        }
                     }
                     tc_fence_before();
                     __syncwarp();
@@ -277,50 +343,313 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) gram_i8_kernel(const OzParams p
             // ---- 3x3 solve: lanes 3g, 3g+1, 3g+2 hold the three rows of the covariances of frame i with 16 frames j;
             // lane a takes the pairs jj = 3m + a and collects the two other rows with shuffles.  The rows arrive in
             // cyclic order (a, a+1, a+2), which leaves |S|^2, |cof S|^2 and det S unchanged.
+            if (p.dbg & 1) continue;
+            const long long ts = clock64();
             const int i = w.ti * OZ_FI + quarter * 10 + g;
             const int j0 = w.tj * OZ_FJ + half * 16;
             const double gi = p.Gq[i];
             const bool row_mine = row_ok && i >= p.row_begin && i < last_row;
             const long long row_off = condensed_row_base(p.M, i) - p.idx_base - i - 1;
+            double qa[6], qb[6], qd[6], hg[6], lam[6];
 #pragma unroll
-            for (int batch = 0; batch < 2; ++batch) {
-                double qa[3], qb[3], qd[3], hg[3], lam[3];
+            for (int m = 0; m < 6; ++m) {
+                double s9[9];
 #pragma unroll
-                for (int mm = 0; mm < 3; ++mm) {
-                    const int m = batch * 3 + mm;
-                    double s9[9];
-#pragma unroll
-                    for (int b = 0; b < 3; ++b) {
-                        const double r0 = acc[9 * m + b];
-                        const double r1 = (9 * m + 3 + b < 48) ? acc[(9 * m + 3 + b) % 48] : 0.0;
-                        const double r2 = (9 * m + 6 + b < 48) ? acc[(9 * m + 6 + b) % 48] : 0.0;
-                        s9[b] = sel3(a, r0, r1, r2);
-                        s9[3 + b] = __shfl_sync(0xffffffffu, sel3(u1, r0, r1, r2), src1);
-                        s9[6 + b] = __shfl_sync(0xffffffffu, sel3(u2, r0, r1, r2), src2);
-                    }
-                    quartic_invariants(s9, qa[mm], qb[mm], qd[mm]);
-                    const int j = j0 + 3 * m + a;
-                    hg[mm] = gi + p.Gq[j];
+                for (int b = 0; b < 3; ++b) {
+                    const double r0 = acc[9 * m + b];
+                    const double r1 = (9 * m + 3 + b < 48) ? acc[(9 * m + 3 + b) % 48] : 0.0;
+                    const double r2 = (9 * m + 6 + b < 48) ? acc[(9 * m + 6 + b) % 48] : 0.0;
+                    s9[b] = sel3(a, r0, r1, r2);
+                    s9[3 + b] = __shfl_sync(0xffffffffu, sel3(u1, r0, r1, r2), src1);
+                    s9[6 + b] = __shfl_sync(0xffffffffu, sel3(u2, r0, r1, r2), src2);
                 }
-                const unsigned okmask = largest_root_lockstep<3>(qa, qb, qd, hg, lam);
+                const int jj = 3 * m + a;
+                const int j = j0 + jj;
+                const bool live = row_ok && jj < 16 && j < p.M;
+                if (!live) {
+                    // idle lanes / padding: a well-conditioned stand-in (identity) so that no lane drags its warp
+                    // through the solver's slow path; the result is never stored
 #pragma unroll
-                for (int mm = 0; mm < 3; ++mm) {
-                    const int jj = 3 * (batch * 3 + mm) + a;
-                    const int j = j0 + jj;
-                    const double eh = hg[mm] - lam[mm];
-                    const double v = fmax(eh, 0.0) * p.inv_k2;
-                    const float y = rsqrtf(fmaxf((float)v, 1e-37f));
-                    double r = v * (double)y;
-                    r = fma(fma(-r, r, v), (double)(0.5f * y), r);
-                    const bool ok = (okmask >> mm) & 1u;
-                    const bool mine = row_mine && jj < 16 && i < j && j < p.M;
-                    if ((!ok || eh < p.flag_rel * hg[mm]) && mine) {
-                        const unsigned int t = atomicAdd(p.fix.count, 1u);
-                        if (t < p.fix.capacity) p.fix.pairs[t] = make_int2(i, j);
-                        else r = -1.0;
-                    }
-                    if (mine) p.out[row_off + j] = r;
+                    for (int k = 0; k < 9; ++k) s9[k] = (k % 4 == 0) ? 1.0 : 0.0;
                 }
+                quartic_invariants(s9, qa[m], qb[m], qd[m]);
+                hg[m] = live ? gi + p.Gq[j] : 3.0;  // half sums: G_i = G_j = 3 for the identity stand-in
+            }
+            const unsigned okmask = largest_root_lockstep<6>(qa, qb, qd, hg, lam);
+#pragma unroll
+            for (int m = 0; m < 6; ++m) {
+                const int jj = 3 * m + a;
+                const int j = j0 + jj;
+                const double eh = hg[m] - lam[m];
+                const double v = fmax(eh, 0.0) * p.inv_k2;
+                const float y = rsqrtf(fmaxf((float)v, 1e-37f));
+                double r = v * (double)y;
+                r = fma(fma(-r, r, v), (double)(0.5f * y), r);
+                const bool ok = (okmask >> m) & 1u;
+                const bool mine = row_mine && jj < 16 && i < j && j < p.M;
+                if ((!ok || eh < p.flag_rel * hg[m]) && mine) {
+                    const unsigned int t = atomicAdd(p.fix.count, 1u);
+                    if (t < p.fix.capacity) p.fix.pairs[t] = make_int2(i, j);
+                    else r = -1.0;
+                }
+                if (mine) p.out[row_off + j] = r;
+            }
+            t_solve += clock64() - ts;
+        }
+        if (p.prof && warp == 4 && lane == 0) {
+            p.prof[blockIdx.x * 8 + 5] = t_tfull; p.prof[blockIdx.x * 8 + 6] = t_solve;
+            p.prof[blockIdx.x * 8 + 7] = clock64() - t_begin;
+            p.prof[blockIdx.x * 8 + 0] = t_ld;  // (overwrites the producer's wait counter)
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, OZ_TMEM_COLS);
+}
+
+
+// ---- K <= 128 atoms: A operand resident in TMEM, dedicated solver warps -------------------------------------
+// With the whole contraction in one K-block the A tile (40 frames x 4 slices x 128 B = 64 KiB) is exactly 128 TMEM
+// columns, next to the 384 accumulator columns.  It is written there once per row of blocks (tcgen05.st, straight
+// from global memory, by the warps that own the TMEM lanes) and every MMA takes it from TMEM (".ts"), so shared
+// memory only carries the streaming B tiles: the MMA no longer reads more than the 128 B/clk shared memory can
+// deliver, and the freed 130 KiB hold a hand-off buffer between the warps that turn integer levels into FP64
+// covariances and four solver warps.  The hand-off is also the transposition the row-per-lane accumulator layout
+// needs: accumulate warps write (frame i, coordinate a) rows, a solver lane reads the whole 3x3 of one pair, lanes
+// run along j, so the RMSD stores are 256-byte contiguous runs of the condensed vector.
+constexpr int TS_THREADS = 640;                       // 4 control warps + 16 epilogue warps
+constexpr int TS_WG_PITCH = 72;                       // doubles per frame row of a warpgroup's hand-off region: 8 pairs x 9
+constexpr int TS_SCRATCH_BYTES = 4 * OZ_FI * TS_WG_PITCH * 8;
+constexpr int TS_SMEM_BYTES = 2 * OZ_B_BYTES + TS_SCRATCH_BYTES + 256;
+constexpr int TS_ACOL = 4 * OZ_N;                     // first TMEM column of the A operand (after two level-pair buffers)
+constexpr int TS_ROW_BYTES = OZ_SLICES * OZ_KB;       // one A row in HBM: [slice][128 B]
+
+__global__ void __launch_bounds__(TS_THREADS, 1) gram_i8_ts_kernel(const OzParams p) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    double* scratch = reinterpret_cast<double*>(smem + 2 * OZ_B_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * OZ_B_BYTES + TS_SCRATCH_BYTES);
+    uint64_t* bfull = bars;           // [2] B stage loaded
+    uint64_t* bempty = bars + 2;      // [2] B stage consumed
+    uint64_t* tfull = bars + 4;       // [2] level pair complete in TMEM
+    uint64_t* tempty = bars + 6;      // [2] level pair drained
+    uint64_t* a_ready = bars + 8;     // A tile of the current block row is in TMEM (4 warps)
+    uint64_t* a_free = bars + 9;      // every MMA of the previous block row has completed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ti_begin = p.row_begin / OZ_FI;
+    const int ntj = (p.M + OZ_FJ - 1) / OZ_FJ;
+    const long long blk_start = p.total_blocks * blockIdx.x / gridDim.x;
+    const long long blk_count = p.total_blocks * (blockIdx.x + 1) / gridDim.x - blk_start;
+    const int nch = p.last_chunks;    // 32-atom chunks in the (single) K-block
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1);
+            mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 16);
+        }
+        mbar_init(a_ready, 4); mbar_init(a_free, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, OZ_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+        if (warp == 0 && lane == 0) {
+            // ---- producer: the B tile of every block, four slices ------------------------------------------------
+            OzWalker w;
+            w.init(ti_begin, ntj, blk_start, blk_count);
+            int stage = 0; uint32_t phase = 0;
+            const uint32_t b_bytes = (uint32_t)nch * (OZ_B_SLICE / 4);
+            for (; w.valid(); w.next()) {
+                mbar_wait_sleep(&bempty[stage], phase ^ 1, 2000u);
+                mbar_expect_tx(&bfull[stage], OZ_SLICES * b_bytes);
+                unsigned char* dst = smem + stage * OZ_B_BYTES;
+                const uint8_t* src = p.packB + (size_t)w.tj * OZ_B_BYTES;
+#pragma unroll
+                for (int s = 0; s < OZ_SLICES; ++s) bulk_g2s(dst + s * OZ_B_SLICE, src + s * OZ_B_SLICE, b_bytes, &bfull[stage]);
+                stage ^= 1; if (stage == 0) phase ^= 1;
+            }
+        } else if (warp == 1) {
+            // ---- MMA issuer -----------------------------------------------------------------------------------------
+            OzWalker w;
+            w.init(ti_begin, ntj, blk_start, blk_count);
+            int stage = 0; uint32_t phase = 0;
+            int tb = 0; uint32_t tphase = 0;
+            int cur_ti = -1; uint32_t a_phase = 0;
+            constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
+            for (; w.valid(); w.next()) {
+                if (w.ti != cur_ti) {
+                    // new block row: the accumulate warps replace the A tile once the MMAs that read the old one are done
+                    if (cur_ti >= 0 && lane == 0) umma_commit(a_free);
+                    __syncwarp();
+                    mbar_wait(a_ready, a_phase); a_phase ^= 1;
+                    tc_fence_after();
+                    cur_ti = w.ti;
+                }
+                mbar_wait(&bfull[stage], phase);
+                tc_fence_after();
+                const uint32_t b_lo = ((uint32_t)(OZ_N * 16 >> 4) << 16) | (smem_u32(smem + stage * OZ_B_BYTES) >> 4);
+#pragma unroll
+                for (int pr = 0; pr < OZ_NPAIR; ++pr) {
+                    mbar_wait(&tempty[tb], tphase ^ 1);
+                    tc_fence_after();
+                    if (lane == 0) {
+#pragma unroll
+                        for (int lv = 0; lv < 2; ++lv) {
+                            const int q = 2 * pr + lv;
+                            const uint32_t d = tmem_base + (uint32_t)(tb * 2 * OZ_N + lv * OZ_N);
+                            const int s_lo = q > 3 ? q - 3 : 0, s_hi = q < 3 ? q : 3;
+#pragma unroll
+                            for (int s = s_lo; s <= s_hi; ++s) {
+#pragma unroll
+                                for (int kc = 0; kc < 4; ++kc) {
+                                    if (kc < nch) {
+                                        const uint64_t bd = ((uint64_t)DESC_HI << 32) |
+                                                            (b_lo + (uint32_t)(((q - s) * OZ_B_SLICE + kc * 2 * OZ_N * 16) >> 4));
+                                        umma_i8_ts(d, tmem_base + (uint32_t)(TS_ACOL + s * 32 + kc * 8), bd, OZ_IDESC,
+                                                   (s > s_lo || kc > 0) ? 1u : 0u);
+                                    }
+                                }
+                            }
+                        }
+                        umma_commit(&tfull[tb]);
+                    }
+                    __syncwarp();
+                    tb ^= 1; if (tb == 0) tphase ^= 1;
+                }
+                if (lane == 0) umma_commit(&bempty[stage]);
+                __syncwarp();
+                stage ^= 1; if (stage == 0) phase ^= 1;
+            }
+        }
+    } else {
+        // ---- epilogue warps (4 warpgroups): warpgroup wg owns accumulator columns 24 wg .. 24 wg + 23 = 8 column frames ----
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+        const int quarter = warp & 3;                 // TMEM lanes 32 * quarter .. + 31
+        const int wg = (warp - 4) >> 2;               // 0..3
+        const int wt = tid - 128 - wg * 128;          // thread index inside the warpgroup
+        const int g = lane / 3, a = lane - 3 * g;
+        const bool row_ok = lane < 30;
+        const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        const double s2 = p.qinfo[0];
+        const double sc[OZ_NPAIR] = {s2 * 1099511627776.0, s2 * 16777216.0, s2 * 256.0};
+        double* wg_scratch = scratch + wg * (OZ_FI * TS_WG_PITCH);
+        double* my_row = wg_scratch + (quarter * 10 + g) * TS_WG_PITCH + 3 * a;
+        const int last_row = min(p.row_end, p.M - 1);
+        OzWalker w;
+        w.init(ti_begin, ntj, blk_start, blk_count);
+        int tb = 0; uint32_t tphase = 0;
+        int cur_ti = -1; uint32_t afree_phase = 0;
+        for (; w.valid(); w.next()) {
+            if (wg == 0 && w.ti != cur_ti) {
+                // this warp's 32 A rows of the new block row: global -> registers -> TMEM
+                if (cur_ti >= 0) { mbar_wait(a_free, afree_phase); afree_phase ^= 1; tc_fence_after(); }
+                const uint4* src = reinterpret_cast<const uint4*>(p.packT + ((size_t)w.ti * OZ_M + quarter * 32 + lane) * TS_ROW_BYTES);
+#pragma unroll
+                for (int s = 0; s < OZ_SLICES; ++s) {
+                    uint32_t v[32];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const uint4 x = __ldg(src + s * 8 + k);
+                        v[4 * k] = x.x; v[4 * k + 1] = x.y; v[4 * k + 2] = x.z; v[4 * k + 3] = x.w;
+                    }
+                    tmem_st32(tlane + (uint32_t)(TS_ACOL + s * 32), v);
+                }
+                tmem_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_ready);
+                cur_ti = w.ti;
+            }
+            double acc[24];
+#pragma unroll
+            for (int n = 0; n < 24; ++n) acc[n] = 0.0;
+#pragma unroll
+            for (int pr = 0; pr < OZ_NPAIR; ++pr) {
+                mbar_wait(&tfull[tb], tphase);
+                tc_fence_after();
+                const uint32_t t0 = tlane + (uint32_t)(tb * 2 * OZ_N + wg * 24);
+                uint32_t ev[2][8], od[2][8];
+                tmem_ld8(t0, ev[0]);
+                tmem_ld8(t0 + OZ_N, od[0]);
+                tmem_wait_ld();
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    if (c + 1 < 3) {  // the next 8 columns travel while these are converted
+                        tmem_ld8(t0 + (c + 1) * 8, ev[(c + 1) & 1]);
+                        tmem_ld8(t0 + OZ_N + (c + 1) * 8, od[(c + 1) & 1]);
+                    }
+#pragma unroll
+                    for (int n = 0; n < 8; ++n)
+                        acc[c * 8 + n] = fma(level_pair((int)ev[c & 1][n], (int)od[c & 1][n]), sc[pr], acc[c * 8 + n]);
+                    if (c + 1 < 3) tmem_wait_ld();
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[tb]);
+                tb ^= 1; if (tb == 0) tphase ^= 1;
+            }
+            // ---- transposition through shared memory: rows (frame i, coordinate a) in, whole 3x3 of one pair out ----
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");   // everyone has read the previous block
+            if (row_ok) {
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    my_row[jj * 9 + 0] = acc[3 * jj + 0];
+                    my_row[jj * 9 + 1] = acc[3 * jj + 1];
+                    my_row[jj * 9 + 2] = acc[3 * jj + 2];
+                }
+            }
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
+            // pairs of this warpgroup: q = 8 * i_local + jl, q = wt, wt + 128, wt + 256 (< 320)
+            double qa[3], qb[3], qd[3], hg[3], lam[3];
+            int pi[3], pj[3];
+            bool plive[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const int q = wt + 128 * r;
+                const int il = q >> 3, jl = q & 7;
+                const int i = w.ti * OZ_FI + il, j = w.tj * OZ_FJ + wg * 8 + jl;
+                pi[r] = i; pj[r] = j;
+                const bool live = q < 8 * OZ_FI && i < j && j < p.M;
+                plive[r] = live;
+                double s9[9];
+                if (live) {
+                    const double* src = wg_scratch + q * 9;
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) s9[k] = src[k];
+                    hg[r] = p.Gq[i] + p.Gq[j];
+                } else {
+                    // lower triangle / padding: a well-conditioned stand-in (identity) so that no lane drags its warp
+                    // through the solver's slow path; the result is never stored
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) s9[k] = (k % 4 == 0) ? 1.0 : 0.0;
+                    hg[r] = 3.0;
+                }
+                quartic_invariants(s9, qa[r], qb[r], qd[r]);
+            }
+            const unsigned okmask = largest_root_lockstep<3>(qa, qb, qd, hg, lam);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const int i = pi[r], j = pj[r];
+                const double eh = hg[r] - lam[r];
+                const double v = fmax(eh, 0.0) * p.inv_k2;
+                const float y = rsqrtf(fmaxf((float)v, 1e-37f));
+                double rm = v * (double)y;
+                rm = fma(fma(-rm, rm, v), (double)(0.5f * y), rm);
+                const bool ok = (okmask >> r) & 1u;
+                const bool mine = plive[r] && i >= p.row_begin && i < last_row;
+                if ((!ok || eh < p.flag_rel * hg[r]) && mine) {
+                    const unsigned int t = atomicAdd(p.fix.count, 1u);
+                    if (t < p.fix.capacity) p.fix.pairs[t] = make_int2(i, j);
+                    else rm = -1.0;
+                }
+                if (mine) p.out[condensed_row_base(p.M, i) - p.idx_base - i - 1 + j] = rm;
             }
         }
     }
@@ -358,7 +687,8 @@ __global__ void quant_info_kernel(const unsigned long long* maxbits, double* qin
 // one thread = 16 consecutive atoms of one coordinate of one frame -> one 16-byte run per slice in each layout
 __global__ void __launch_bounds__(256) quant_pack_kernel(const double* __restrict__ centred, int M, int K, int nkb,
                                                          const unsigned long long* __restrict__ maxbits,
-                                                         uint8_t* __restrict__ packA, uint8_t* __restrict__ packB) {
+                                                         uint8_t* __restrict__ packA, uint8_t* __restrict__ packB,
+                                                         uint8_t* __restrict__ packT) {
     const int groups = nkb * 8;  // 16-atom groups per row
     const long long total = (long long)M * 3 * groups;
     const double scale = ldexp(1.0, quant_exponent(*maxbits));
@@ -397,6 +727,12 @@ __global__ void __launch_bounds__(256) quant_pack_kernel(const double* __restric
 #pragma unroll
             for (int s = 0; s < 4; ++s)
                 *reinterpret_cast<uint4*>(dst + s * OZ_A_SLICE) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
+            if (packT) {  // single K-block: [ti][row][slice][128 B], one contiguous 512 B run per TMEM lane
+                uint8_t* dt = packT + ((size_t)ti * OZ_M + row) * (OZ_SLICES * OZ_KB) + kc16 * 16;
+#pragma unroll
+                for (int s = 0; s < 4; ++s)
+                    *reinterpret_cast<uint4*>(dt + s * OZ_KB) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
+            }
         }
         {
             const int tj = fr / OZ_FJ, fj = fr - tj * OZ_FJ;
@@ -434,13 +770,15 @@ size_t oz_g_entries(int M) {
 }
 int oz_row_align() { return OZ_FI; }
 
-cudaError_t launch_quant_pack(const double* centred, int M, int K, uint8_t* packA, uint8_t* packB, double* Gq, double* qinfo,
-                              unsigned long long* maxbits, int sm_count, cudaStream_t stream) {
+cudaError_t launch_quant_pack(const double* centred, int M, int K, uint8_t* packA, uint8_t* packB, uint8_t* packT, double* Gq,
+                              double* qinfo, unsigned long long* maxbits, int sm_count, cudaStream_t stream) {
     const int nkb = (K + OZ_KB - 1) / OZ_KB;
     cudaError_t e;
     if ((e = cudaMemsetAsync(maxbits, 0, sizeof(unsigned long long), stream)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(packA, 0, oz_packA_bytes(M, K), stream)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(packB, 0, oz_packB_bytes(M, K), stream)) != cudaSuccess) return e;
+    if (nkb > 1) packT = nullptr;
+    if (packT && (e = cudaMemsetAsync(packT, 0, oz_packA_bytes(M, K), stream)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(Gq, 0, sizeof(double) * oz_g_entries(M), stream)) != cudaSuccess) return e;
     const long long n = (long long)M * K * 3;
     long long blocks = (n + 255) / 256;
@@ -450,7 +788,7 @@ cudaError_t launch_quant_pack(const double* centred, int M, int K, uint8_t* pack
     const long long total = (long long)M * 3 * nkb * 8;
     blocks = (total + 255) / 256;
     if (blocks > (long long)sm_count * 16) blocks = (long long)sm_count * 16;
-    quant_pack_kernel<<<(unsigned)blocks, 256, 0, stream>>>(centred, M, K, nkb, maxbits, packA, packB);
+    quant_pack_kernel<<<(unsigned)blocks, 256, 0, stream>>>(centred, M, K, nkb, maxbits, packA, packB, packT);
     quant_g_kernel<<<(M + 3) / 4, 128, 0, stream>>>(centred, M, K, maxbits, Gq);
     return cudaGetLastError();
 }
@@ -467,9 +805,15 @@ cudaError_t launch_gram_i8(OzParams p, int K, int sm_count, cudaStream_t stream)
     for (int ti = ti_begin; ti < ti_end; ++ti) blocks += ntj - OzWalker::first_tj(ti);
     if (blocks <= 0) return cudaSuccess;
     p.total_blocks = blocks;
+    const long long grid = blocks < sm_count ? blocks : sm_count;
+    if (p.nkb == 1 && p.packT && !(p.dbg & 16)) {
+        cudaError_t e = cudaFuncSetAttribute(gram_i8_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        gram_i8_ts_kernel<<<(unsigned)grid, TS_THREADS, TS_SMEM_BYTES, stream>>>(p);
+        return cudaGetLastError();
+    }
     cudaError_t e = cudaFuncSetAttribute(gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    const long long grid = blocks < sm_count ? blocks : sm_count;
     gram_i8_kernel<<<(unsigned)grid, OZ_THREADS, OZ_SMEM_BYTES, stream>>>(p);
     return cudaGetLastError();
 }
