@@ -56,6 +56,19 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
+// One lane of a converged warp (elect.sync): with warp-uniform operands the compiler keeps tcgen05 descriptors in
+// uniform registers instead of broadcasting them lane by lane (a ~18-instruction loop per MMA otherwise).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "elect.sync _|P, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -164,7 +177,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) gram_i8_kernel(const OzParams p
     uint64_t* tempty = bars + 6;      // [2] TMEM level pair drained (8 epilogue warps)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int ti_begin = p.row_begin / OZ_FI;
     const int ntj = (p.M + OZ_FJ - 1) / OZ_FJ;
     const long long blk_start = p.total_blocks * blockIdx.x / gridDim.x;
@@ -182,7 +195,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) gram_i8_kernel(const OzParams p
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // provably warp-uniform
 
     if (warp < 4) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -244,7 +257,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) gram_i8_kernel(const OzParams p
                     mbar_wait(&tempty[tb], tphase ^ 1);
                     t_tempty += clock64() - t1;
                     tc_fence_after();
-                    if (lane == 0 && !(p.dbg & 4)) {
+                    const bool leader = elect_one();
+                    if (leader && !(p.dbg & 4)) {
 #pragma unroll
                         for (int lv = 0; lv < 2; ++lv) {
                             const int q = 2 * pr + lv;
@@ -266,11 +280,11 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) gram_i8_kernel(const OzParams p
                             }
                         }
                     }
-                    if (lane == 0) umma_commit(&tfull[tb]);
+                    if (leader) umma_commit(&tfull[tb]);
                     __syncwarp();
                     tb ^= 1; if (tb == 0) tphase ^= 1;
                 }
-                if (lane == 0) umma_commit(&empty[stage]);
+                if (elect_one()) umma_commit(&empty[stage]);
                 __syncwarp();
                 stage ^= 1; if (stage == 0) phase ^= 1;
             }
@@ -418,7 +432,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) gram_i8_kernel(const OzParams p
 // needs: accumulate warps write (frame i, coordinate a) rows, a solver lane reads the whole 3x3 of one pair, lanes
 // run along j, so the RMSD stores are 256-byte contiguous runs of the condensed vector.
 constexpr int TS_THREADS = 640;                       // 4 control warps + 16 epilogue warps
-constexpr int TS_WG_PITCH = 72;                       // doubles per frame row of a warpgroup's hand-off region: 8 pairs x 9
+constexpr int TS_WG_PITCH = 73;                       // doubles per frame row of a warpgroup's hand-off region: 8 pairs x 9,
+                                                      // padded to 9 (mod 16) 8-byte bank units: conflict-free both ways
 constexpr int TS_SCRATCH_BYTES = 4 * OZ_FI * TS_WG_PITCH * 8;
 constexpr int TS_SMEM_BYTES = 2 * OZ_B_BYTES + TS_SCRATCH_BYTES + 256;
 constexpr int TS_ACOL = 4 * OZ_N;                     // first TMEM column of the A operand (after two level-pair buffers)
@@ -436,7 +451,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gram_i8_ts_kernel(const OzParam
     uint64_t* a_free = bars + 9;      // every MMA of the previous block row has completed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int ti_begin = p.row_begin / OZ_FI;
     const int ntj = (p.M + OZ_FJ - 1) / OZ_FJ;
     const long long blk_start = p.total_blocks * blockIdx.x / gridDim.x;
@@ -456,7 +471,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gram_i8_ts_kernel(const OzParam
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // provably warp-uniform
 
     if (warp < 4) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
@@ -486,7 +501,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gram_i8_ts_kernel(const OzParam
             for (; w.valid(); w.next()) {
                 if (w.ti != cur_ti) {
                     // new block row: the accumulate warps replace the A tile once the MMAs that read the old one are done
-                    if (cur_ti >= 0 && lane == 0) umma_commit(a_free);
+                    if (cur_ti >= 0 && elect_one()) umma_commit(a_free);
                     __syncwarp();
                     mbar_wait(a_ready, a_phase); a_phase ^= 1;
                     tc_fence_after();
@@ -499,7 +514,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gram_i8_ts_kernel(const OzParam
                 for (int pr = 0; pr < OZ_NPAIR; ++pr) {
                     mbar_wait(&tempty[tb], tphase ^ 1);
                     tc_fence_after();
-                    if (lane == 0) {
+                    if (elect_one()) {
 #pragma unroll
                         for (int lv = 0; lv < 2; ++lv) {
                             const int q = 2 * pr + lv;
@@ -523,7 +538,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gram_i8_ts_kernel(const OzParam
                     __syncwarp();
                     tb ^= 1; if (tb == 0) tphase ^= 1;
                 }
-                if (lane == 0) umma_commit(&bempty[stage]);
+                if (elect_one()) umma_commit(&bempty[stage]);
                 __syncwarp();
                 stage ^= 1; if (stage == 0) phase ^= 1;
             }
@@ -567,6 +582,14 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gram_i8_ts_kernel(const OzParam
                 if (lane == 0) mbar_arrive(a_ready);
                 cur_ti = w.ti;
             }
+            // G of this thread's pairs (the pass/slot mapping below): fetched now, used after the accumulate phase
+            const double gj = p.Gq[w.tj * OZ_FJ + wg * 8 + (lane & 7)];
+            double gi[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const int slot = 4 * ((wt >> 5) + 4 * r) + (lane >> 3);
+                gi[r] = p.Gq[w.ti * OZ_FI + (slot / 5) + 8 * (slot % 5)];
+            }
             double acc[24];
 #pragma unroll
             for (int n = 0; n < 24; ++n) acc[n] = 0.0;
@@ -576,11 +599,14 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gram_i8_ts_kernel(const OzParam
                 tc_fence_after();
                 const uint32_t t0 = tlane + (uint32_t)(tb * 2 * OZ_N + wg * 24);
                 uint32_t ev[2][8], od[2][8];
-                tmem_ld8(t0, ev[0]);
-                tmem_ld8(t0 + OZ_N, od[0]);
-                tmem_wait_ld();
+                if (!(p.dbg & 2)) {
+                    tmem_ld8(t0, ev[0]);
+                    tmem_ld8(t0 + OZ_N, od[0]);
+                    tmem_wait_ld();
+                }
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
+                    if (p.dbg & 2) break;
                     if (c + 1 < 3) {  // the next 8 columns travel while these are converted
                         tmem_ld8(t0 + (c + 1) * 8, ev[(c + 1) & 1]);
                         tmem_ld8(t0 + OZ_N + (c + 1) * 8, od[(c + 1) & 1]);
@@ -596,6 +622,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gram_i8_ts_kernel(const OzParam
                 tb ^= 1; if (tb == 0) tphase ^= 1;
             }
             // ---- transposition through shared memory: rows (frame i, coordinate a) in, whole 3x3 of one pair out ----
+            if (p.dbg & 1) continue;
             asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");   // everyone has read the previous block
             if (row_ok) {
 #pragma unroll
@@ -606,24 +633,30 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gram_i8_ts_kernel(const OzParam
                 }
             }
             asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
-            // pairs of this warpgroup: q = 8 * i_local + jl, q = wt, wt + 128, wt + 256 (< 320)
+            // Pairs of this warpgroup: 40 rows x 8 columns.  A warp pass takes four 8-row-apart rows (lane = 8 * sub + jl),
+            // so that the 16 lanes of a shared-memory wavefront read 16 different 8-byte bank units (il + jl all different
+            // mod 16) and every row's 8 results are one 64-byte run of the condensed vector.  40 (row class, sub) slots,
+            // four per warp pass: passes 0-9, warp ww of the warpgroup does passes ww, ww + 4, ww + 8.
             double qa[3], qb[3], qd[3], hg[3], lam[3];
             int pi[3], pj[3];
             bool plive[3];
+            double* out_row[3];   // start of condensed row i, shifted so that column j indexes it directly
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
-                const int q = wt + 128 * r;
-                const int il = q >> 3, jl = q & 7;
+                const int pass = (wt >> 5) + 4 * r;
+                const int slot = 4 * pass + (lane >> 3);          // 0..39 (valid) .. 47
+                const int il = (slot / 5) + 8 * (slot % 5), jl = lane & 7;
                 const int i = w.ti * OZ_FI + il, j = w.tj * OZ_FJ + wg * 8 + jl;
                 pi[r] = i; pj[r] = j;
-                const bool live = q < 8 * OZ_FI && i < j && j < p.M;
+                out_row[r] = p.out + (condensed_row_base(p.M, i) - p.idx_base - i - 1);
+                const bool live = slot < OZ_FI && i < j && j < p.M;
                 plive[r] = live;
                 double s9[9];
                 if (live) {
-                    const double* src = wg_scratch + q * 9;
+                    const double* src = wg_scratch + il * TS_WG_PITCH + jl * 9;
 #pragma unroll
                     for (int k = 0; k < 9; ++k) s9[k] = src[k];
-                    hg[r] = p.Gq[i] + p.Gq[j];
+                    hg[r] = gi[r] + gj;
                 } else {
                     // lower triangle / padding: a well-conditioned stand-in (identity) so that no lane drags its warp
                     // through the solver's slow path; the result is never stored
@@ -633,7 +666,14 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gram_i8_ts_kernel(const OzParam
                 }
                 quartic_invariants(s9, qa[r], qb[r], qd[r]);
             }
-            const unsigned okmask = largest_root_lockstep<3>(qa, qb, qd, hg, lam);
+            unsigned okmask;
+            if ((wt >> 5) < 2) {
+                okmask = largest_root_lean<3>(qa, qb, qd, hg, lam);
+            } else {  // passes 10 and 11 do not exist: warps 2 and 3 of the warpgroup have two passes
+                double a2[2] = {qa[0], qa[1]}, b2[2] = {qb[0], qb[1]}, d2[2] = {qd[0], qd[1]}, h2[2] = {hg[0], hg[1]}, l2[2];
+                okmask = largest_root_lean<2>(a2, b2, d2, h2, l2);
+                lam[0] = l2[0]; lam[1] = l2[1]; lam[2] = 0.0;
+            }
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 const int i = pi[r], j = pj[r];
@@ -649,7 +689,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gram_i8_ts_kernel(const OzParam
                     if (t < p.fix.capacity) p.fix.pairs[t] = make_int2(i, j);
                     else rm = -1.0;
                 }
-                if (mine) p.out[condensed_row_base(p.M, i) - p.idx_base - i - 1 + j] = rm;
+                if (mine) out_row[r][j] = rm;
             }
         }
     }
