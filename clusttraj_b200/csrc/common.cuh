@@ -45,8 +45,6 @@ struct OzParams {
     long long total_blocks;
     int M, nkb, last_chunks;   // K-blocks; 32-atom chunks in the last K-block (1..4)
     int row_begin, row_end;
-    unsigned long long* prof;  // optional per-CTA cycle counters [grid][8] (development)
-    int dbg;                   // development switches (bit 0: skip the 3x3 solve, 1: skip the accumulate math, 2: skip the MMAs)
     double inv_k2, flag_rel;
     FixList fix;
 };

@@ -64,7 +64,6 @@ struct ct_engine {
     double* d_qinfo = nullptr;               // [0] 2^-2f, [1] f, [2] max |x|
     unsigned long long* d_maxbits = nullptr;
     double quant_f = 0.0;
-    unsigned long long* d_prof = nullptr;
     ct::PairPlanHost* plan = nullptr;
     // outputs
     double* d_slab = nullptr; size_t slab_cap = 0;       // whole-slab device buffer (rows_device)
@@ -319,20 +318,7 @@ static int compute_rows_async(ct_engine* e, int row_begin, int row_end, double* 
         p.row_begin = row_begin; p.row_end = row_end;
         p.inv_k2 = 2.0 / (double)e->K; p.flag_rel = e->flag_rel;
         p.fix.pairs = e->d_fix_pairs; p.fix.count = e->d_fix_count; p.fix.capacity = e->fix_cap;
-        { const char* dv = getenv("CLUSTTRAJ_B200_OZ_DBG"); p.dbg = dv ? atoi(dv) : 0; }
-        const bool prof = getenv("CLUSTTRAJ_B200_OZ_PROF") != nullptr;
-        if (prof && !e->d_prof) CT_CUDA(e, cudaMalloc(&e->d_prof, sizeof(unsigned long long) * 8 * 1024));
-        p.prof = prof ? e->d_prof : nullptr;
         CT_CUDA(e, ct::launch_gram_i8(p, e->K, e->sm_count, e->s_compute));
-        if (prof) {  // development: per-role cycle counters of CTA 0 and the CTA in the middle of the grid
-            std::vector<unsigned long long> h(8 * 1024);
-            CT_CUDA(e, cudaStreamSynchronize(e->s_compute));
-            CT_CUDA(e, cudaMemcpy(h.data(), e->d_prof, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost));
-            for (int c : {0, e->sm_count / 2})
-                fprintf(stderr, "[oz prof cta %d] p0 %llu p1 %llu | mma wait_full %llu wait_tempty %llu total %llu | "
-                                "epi wait_tfull %llu p6 %llu total %llu  (ts: p0/p1 = solver wait_cfull/total, p6 = acc wait_cempty)\n", c, h[c * 8 + 0], h[c * 8 + 1], h[c * 8 + 2],
-                        h[c * 8 + 3], h[c * 8 + 4], h[c * 8 + 5], h[c * 8 + 6], h[c * 8 + 7]);
-        }
         if (after_main) CT_CUDA(e, cudaEventRecord(after_main, e->s_compute));
         CT_CUDA(e, ct::launch_fixup(e->d_centred, (int)e->M, e->K, p.fix, dst, idx_base, n_entries, e->d_counters,
                                     e->sm_count, e->s_compute));

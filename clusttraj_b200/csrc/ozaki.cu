@@ -140,10 +140,10 @@ constexpr uint32_t OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(O
 // j > i falls inside, i.e. tj >= (40 ti + 1) / 32.  Row-major enumeration; a CTA takes a contiguous run.
 struct OzWalker {
     int ti, tj, ntj;
-    long long left;
+    int left;
     __host__ __device__ static int first_tj(int ti) { return (OZ_FI * ti + 1) / OZ_FJ; }
     __device__ void init(int ti_begin, int ntj_, long long start, long long count) {
-        ntj = ntj_; left = count; ti = ti_begin;
+        ntj = ntj_; left = (int)count; ti = ti_begin;
         long long s = start;
         for (;;) {
             const long long n = ntj - first_tj(ti);
@@ -205,13 +205,9 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) gram_i8_kernel(const OzParams p
             w.init(ti_begin, ntj, blk_start, blk_count);
             int stage = 0; uint32_t phase = 0;
             long long tagA[2] = {-1, -1};
-            long long t_wait = 0;
-            const long long t_begin = clock64();
             for (; w.valid(); w.next()) {
                 for (int kb = 0; kb < p.nkb; ++kb) {
-                    const long long t0 = clock64();
                     mbar_wait(&empty[stage], phase ^ 1);
-                    t_wait += clock64() - t0;
                     const int nch = (kb == p.nkb - 1) ? p.last_chunks : 4;
                     const long long tag = (long long)w.ti * p.nkb + kb;
                     const bool loadA = tagA[stage] != tag;
@@ -230,20 +226,15 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) gram_i8_kernel(const OzParams p
                     stage ^= 1; if (stage == 0) phase ^= 1;
                 }
             }
-            if (p.prof) { p.prof[blockIdx.x * 8 + 0] = t_wait; p.prof[blockIdx.x * 8 + 1] = clock64() - t_begin; }
         } else if (warp == 1) {
             // ---- MMA issuer ------------------------------------------------------------------------------------
             int stage = 0; uint32_t phase = 0;
             int tb = 0; uint32_t tphase = 0;
             const long long n_stage = blk_count * p.nkb;
-            long long t_full = 0, t_tempty = 0;
-            const long long t_begin = clock64();
             for (long long it = 0; it < n_stage; ++it) {
                 const int kb = (int)(it % p.nkb);
                 const int nch = (kb == p.nkb - 1) ? p.last_chunks : 4;
-                const long long t0 = clock64();
                 mbar_wait(&full[stage], phase);
-                t_full += clock64() - t0;
                 tc_fence_after();
                 const uint32_t aBase = smem_u32(smem + stage * OZ_STAGE_BYTES);
                 const uint32_t bBase = aBase + OZ_A_BYTES;
@@ -253,12 +244,10 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) gram_i8_kernel(const OzParams p
                 const uint32_t b_lo = ((uint32_t)(OZ_N * 16 >> 4) << 16) | (bBase >> 4);
 #pragma unroll
                 for (int pr = 0; pr < OZ_NPAIR; ++pr) {
-                    const long long t1 = clock64();
                     mbar_wait(&tempty[tb], tphase ^ 1);
-                    t_tempty += clock64() - t1;
                     tc_fence_after();
                     const bool leader = elect_one();
-                    if (leader && !(p.dbg & 4)) {
+                    if (leader) {
 #pragma unroll
                         for (int lv = 0; lv < 2; ++lv) {
                             const int q = 2 * pr + lv;
@@ -288,10 +277,6 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) gram_i8_kernel(const OzParams p
                 __syncwarp();
                 stage ^= 1; if (stage == 0) phase ^= 1;
             }
-            if (p.prof && lane == 0) {
-                p.prof[blockIdx.x * 8 + 2] = t_full; p.prof[blockIdx.x * 8 + 3] = t_tempty;
-                p.prof[blockIdx.x * 8 + 4] = clock64() - t_begin;
-            }
         }
     } else {
         // ---- epilogue warps ------------------------------------------------------------------------------------
@@ -309,8 +294,6 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) gram_i8_kernel(const OzParams p
         OzWalker w;
         w.init(ti_begin, ntj, blk_start, blk_count);
         int tb = 0; uint32_t tphase = 0;
-        long long t_tfull = 0, t_solve = 0, t_ld = 0;
-        const long long t_begin = clock64();
         for (; w.valid(); w.next()) {
             double acc[48];
 #pragma unroll
@@ -318,34 +301,24 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) gram_i8_kernel(const OzParams p
             for (int kb = 0; kb < p.nkb; ++kb) {
 #pragma unroll
                 for (int pr = 0; pr < OZ_NPAIR; ++pr) {
-                    const long long tw = clock64();
                     mbar_wait(&tfull[tb], tphase);
-                    t_tfull += clock64() - tw;
                     tc_fence_after();
                     const uint32_t t0 = tlane + (uint32_t)(tb * 2 * OZ_N);
-                    if (!(p.dbg & 2)) {
+                    {
                         uint32_t ev[2][16], od[2][16];
-                        const long long tl0 = clock64();
                         tmem_ld16(t0, ev[0]);
                         tmem_ld16(t0 + OZ_N, od[0]);
                         tmem_wait_ld();
-                        t_ld += clock64() - tl0;
 #pragma unroll
                         for (int c = 0; c < 3; ++c) {
                             if (c + 1 < 3) {  // the next 16 columns travel while these are converted
                                 tmem_ld16(t0 + (c + 1) * 16, ev[(c + 1) & 1]);
                                 tmem_ld16(t0 + OZ_N + (c + 1) * 16, od[(c + 1) & 1]);
                             }
-                            if (p.dbg & 8) {  // development: TMEM loads only
-                                uint32_t x = 0;
-#pragma unroll
-                                for (int n = 0; n < 16; ++n) x ^= ev[c & 1][n] ^ od[c & 1][n];
-                                acc[c] += __hiloint2double(0, (int)x);
-                            } else
 #pragma unroll
                             for (int n = 0; n < 16; ++n)
                                 acc[c * 16 + n] = fma(level_pair((int)ev[c & 1][n], (int)od[c & 1][n]), sc[pr], acc[c * 16 + n]);
-                            if (c + 1 < 3) { const long long tl1 = clock64(); tmem_wait_ld(); t_ld += clock64() - tl1; }
+                            if (c + 1 < 3) tmem_wait_ld();
                         }
                     }
                     tc_fence_before();
@@ -357,8 +330,6 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) gram_i8_kernel(const OzParams p
             // ---- 3x3 solve: lanes 3g, 3g+1, 3g+2 hold the three rows of the covariances of frame i with 16 frames j;
             // lane a takes the pairs jj = 3m + a and collects the two other rows with shuffles.  The rows arrive in
             // cyclic order (a, a+1, a+2), which leaves |S|^2, |cof S|^2 and det S unchanged.
-            if (p.dbg & 1) continue;
-            const long long ts = clock64();
             const int i = w.ti * OZ_FI + quarter * 10 + g;
             const int j0 = w.tj * OZ_FJ + half * 16;
             const double gi = p.Gq[i];
@@ -408,12 +379,6 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) gram_i8_kernel(const OzParams p
                 }
                 if (mine) p.out[row_off + j] = r;
             }
-            t_solve += clock64() - ts;
-        }
-        if (p.prof && warp == 4 && lane == 0) {
-            p.prof[blockIdx.x * 8 + 5] = t_tfull; p.prof[blockIdx.x * 8 + 6] = t_solve;
-            p.prof[blockIdx.x * 8 + 7] = clock64() - t_begin;
-            p.prof[blockIdx.x * 8 + 0] = t_ld;  // (overwrites the producer's wait counter)
         }
     }
     tc_fence_before();
@@ -474,7 +439,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gram_i8_ts_kernel(const OzParam
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // provably warp-uniform
 
     if (warp < 4) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
         if (warp == 0 && lane == 0) {
             // ---- producer: the B tile of every block, four slices ------------------------------------------------
             OzWalker w;
@@ -545,7 +510,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gram_i8_ts_kernel(const OzParam
         }
     } else {
         // ---- epilogue warps (4 warpgroups): warpgroup wg owns accumulator columns 24 wg .. 24 wg + 23 = 8 column frames ----
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
         const int quarter = warp & 3;                 // TMEM lanes 32 * quarter .. + 31
         const int wg = (warp - 4) >> 2;               // 0..3
         const int wt = tid - 128 - wg * 128;          // thread index inside the warpgroup
@@ -598,23 +563,15 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gram_i8_ts_kernel(const OzParam
                 mbar_wait(&tfull[tb], tphase);
                 tc_fence_after();
                 const uint32_t t0 = tlane + (uint32_t)(tb * 2 * OZ_N + wg * 24);
-                uint32_t ev[2][8], od[2][8];
-                if (!(p.dbg & 2)) {
-                    tmem_ld8(t0, ev[0]);
-                    tmem_ld8(t0 + OZ_N, od[0]);
-                    tmem_wait_ld();
-                }
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    if (p.dbg & 2) break;
-                    if (c + 1 < 3) {  // the next 8 columns travel while these are converted
-                        tmem_ld8(t0 + (c + 1) * 8, ev[(c + 1) & 1]);
-                        tmem_ld8(t0 + OZ_N + (c + 1) * 8, od[(c + 1) & 1]);
-                    }
+                    uint32_t ev[8], od[8];
+                    tmem_ld8(t0 + c * 8, ev);
+                    tmem_ld8(t0 + OZ_N + c * 8, od);
+                    tmem_wait_ld();
 #pragma unroll
                     for (int n = 0; n < 8; ++n)
-                        acc[c * 8 + n] = fma(level_pair((int)ev[c & 1][n], (int)od[c & 1][n]), sc[pr], acc[c * 8 + n]);
-                    if (c + 1 < 3) tmem_wait_ld();
+                        acc[c * 8 + n] = fma(level_pair((int)ev[n], (int)od[n]), sc[pr], acc[c * 8 + n]);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -622,7 +579,6 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gram_i8_ts_kernel(const OzParam
                 tb ^= 1; if (tb == 0) tphase ^= 1;
             }
             // ---- transposition through shared memory: rows (frame i, coordinate a) in, whole 3x3 of one pair out ----
-            if (p.dbg & 1) continue;
             asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");   // everyone has read the previous block
             if (row_ok) {
 #pragma unroll
@@ -846,7 +802,7 @@ cudaError_t launch_gram_i8(OzParams p, int K, int sm_count, cudaStream_t stream)
     if (blocks <= 0) return cudaSuccess;
     p.total_blocks = blocks;
     const long long grid = blocks < sm_count ? blocks : sm_count;
-    if (p.nkb == 1 && p.packT && !(p.dbg & 16)) {
+    if (p.nkb == 1 && p.packT) {
         cudaError_t e = cudaFuncSetAttribute(gram_i8_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         gram_i8_ts_kernel<<<(unsigned)grid, TS_THREADS, TS_SMEM_BYTES, stream>>>(p);
