@@ -32,7 +32,7 @@ class ct_stats(C.Structure):
         ("pack_ms", C.c_double), ("h2d_ms", C.c_double), ("kernel_ms", C.c_double), ("gram_ms", C.c_double),
         ("pair_ms", C.c_double), ("d2h_ms", C.c_double), ("total_ms", C.c_double),
         ("pairs", C.c_int64), ("flagged", C.c_int64), ("launches", C.c_int64), ("kept_atoms", C.c_int64),
-        ("lsap_steps", C.c_int64),
+        ("lsap_steps", C.c_int64), ("gram_path", C.c_int64), ("quant_step", C.c_double),
     ]
 
     def as_dict(self):

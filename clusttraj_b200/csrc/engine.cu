@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -73,7 +74,10 @@ struct ct_engine {
     cudaEvent_t ev_chunk_done[2] = {nullptr, nullptr}, ev_copy_done[2] = {nullptr, nullptr};
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
     ct_stats stats{};
-    int gram_variant = -1;  // -1 = choose by atom count (gram.cu:launch_gram)
+    int gram_variant = -1;  // -1 = auto: int8 tensor-core kernel when the coordinates quantise finely enough, else
+                            // the DMMA kernel (variant by atom count); -2 = DMMA, variant by atom count; 0..3 = force a DMMA
+                            // variant; 10 = force int8
+    int min_quant_f = 22;   // auto mode needs a quantum <= 2^-22 A (|x| < 256 A): worst-case |dRMSD| 4e-7 A
     size_t chunk_entries = (size_t)32 << 20;  // 256 MiB of float64 per streaming chunk
     double flag_rel = 1e-9;
 };
@@ -153,6 +157,8 @@ int ct_engine_create(int device, ct_engine** out) {
     CT_CUDA((ct_engine*)nullptr, cudaMalloc(&e->d_maxbits, sizeof(unsigned long long)));
     const char* v = getenv("CLUSTTRAJ_B200_GRAM_VARIANT");
     if (v) e->gram_variant = atoi(v);
+    const char* mq = getenv("CLUSTTRAJ_B200_MIN_QUANT_BITS");  // test hook: force the fall-back decision
+    if (mq) e->min_quant_f = atoi(mq);
     const char* ce = getenv("CLUSTTRAJ_B200_CHUNK_ENTRIES");
     if (ce && atoll(ce) > 0) e->chunk_entries = (size_t)atoll(ce);
     const char* fc = getenv("CLUSTTRAJ_B200_FIX_CAPACITY");  // test hook: force the list-overflow path
@@ -246,7 +252,7 @@ int ct_load_frames(ct_engine* e, const double* coords, const int32_t* atomic_num
     if ((rc = ensure(e, e->d_keep, e->keep_cap, (size_t)K))) return rc;
     if ((rc = ensure(e, e->d_centred, e->centred_cap, (size_t)M * K * 3))) return rc;
     if ((rc = ensure(e, e->d_G, e->g_cap, (size_t)e->m_pad))) return rc;
-    e->use_i8 = e->use_gram && e->gram_variant == 10;
+    e->use_i8 = e->use_gram && (e->gram_variant == 10 || e->gram_variant == -1);
     if (e->use_gram && !e->use_i8)
         if ((rc = ensure(e, e->d_packed, e->packed_cap, (size_t)e->m_pad * k_pad * 3))) return rc;
     if (e->use_i8) {
@@ -271,7 +277,17 @@ int ct_load_frames(ct_engine* e, const double* coords, const int32_t* atomic_num
         double qi[4];
         CT_CUDA(e, cudaMemcpy(qi, e->d_qinfo, sizeof qi, cudaMemcpyDeviceToHost));
         e->quant_f = qi[1];
+        if (e->gram_variant == -1 && e->quant_f < e->min_quant_f) {
+            // coordinates too far from the centroid for 31-bit fixed point at the accuracy bound: FP64 tensor path
+            e->use_i8 = false;
+            if ((rc = ensure(e, e->d_packed, e->packed_cap, (size_t)e->m_pad * k_pad * 3))) return rc;
+            CT_CUDA(e, ct::launch_pack(e->d_raw, e->d_keep, (int)M, N, K, ncen, e->m_pad, e->kq_total, e->d_centred, e->d_G,
+                                       e->d_packed, e->sm_count, e->s_compute));
+            CT_CUDA(e, cudaStreamSynchronize(e->s_compute));
+        }
     }
+    e->stats.gram_path = e->use_gram ? (e->use_i8 ? 2 : 1) : 0;
+    e->stats.quant_step = e->use_i8 ? ldexp(1.0, -(int)e->quant_f) : 0.0;
     float ms = 0.f;
     CT_CUDA(e, cudaEventElapsedTime(&ms, e->ev_a, e->ev_b)); e->stats.h2d_ms = ms;
     CT_CUDA(e, cudaEventElapsedTime(&ms, e->ev_b, e->ev_c)); e->stats.pack_ms = ms;
@@ -331,7 +347,7 @@ static int compute_rows_async(ct_engine* e, int row_begin, int row_end, double* 
         p.row_begin = row_begin; p.row_end = row_end;
         p.inv_k2 = 2.0 / (double)e->K; p.flag_rel = e->flag_rel;
         p.fix.pairs = e->d_fix_pairs; p.fix.count = e->d_fix_count; p.fix.capacity = e->fix_cap;
-        CT_CUDA(e, ct::launch_gram(p, e->gram_variant, e->sm_count, e->s_compute));
+        CT_CUDA(e, ct::launch_gram(p, e->gram_variant < 0 ? -1 : e->gram_variant, e->sm_count, e->s_compute));
         if (after_main) CT_CUDA(e, cudaEventRecord(after_main, e->s_compute));
         CT_CUDA(e, ct::launch_fixup(e->d_centred, (int)e->M, e->K, p.fix, dst, idx_base, n_entries, e->d_counters,
                                     e->sm_count, e->s_compute));

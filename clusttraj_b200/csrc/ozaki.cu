@@ -719,10 +719,12 @@ __global__ void __launch_bounds__(256) quant_pack_kernel(const double* __restric
         {
             const int ti = fr / OZ_FI, fi = fr - ti * OZ_FI;
             const int row = (fi / 10) * 32 + (fi % 10) * 3 + c;
-            uint8_t* dst = packA + ((size_t)ti * nkb + kb) * OZ_A_BYTES + (size_t)kc16 * (OZ_M * 16) + (row >> 3) * 128 + (row & 7) * 16;
+            if (packA) {
+                uint8_t* dst = packA + ((size_t)ti * nkb + kb) * OZ_A_BYTES + (size_t)kc16 * (OZ_M * 16) + (row >> 3) * 128 + (row & 7) * 16;
 #pragma unroll
-            for (int s = 0; s < 4; ++s)
-                *reinterpret_cast<uint4*>(dst + s * OZ_A_SLICE) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
+                for (int s = 0; s < 4; ++s)
+                    *reinterpret_cast<uint4*>(dst + s * OZ_A_SLICE) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
+            }
             if (packT) {  // single K-block: [ti][row][slice][128 B], one contiguous 512 B run per TMEM lane
                 uint8_t* dt = packT + ((size_t)ti * OZ_M + row) * (OZ_SLICES * OZ_KB) + kc16 * 16;
 #pragma unroll
@@ -771,9 +773,10 @@ cudaError_t launch_quant_pack(const double* centred, int M, int K, uint8_t* pack
     const int nkb = (K + OZ_KB - 1) / OZ_KB;
     cudaError_t e;
     if ((e = cudaMemsetAsync(maxbits, 0, sizeof(unsigned long long), stream)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(packA, 0, oz_packA_bytes(M, K), stream)) != cudaSuccess) return e;
+    if (nkb > 1) packT = nullptr;   // several K-blocks: A streams through shared memory (packA)
+    else packA = nullptr;           // one K-block: A lives in TMEM, loaded from the row-major packT
+    if (packA && (e = cudaMemsetAsync(packA, 0, oz_packA_bytes(M, K), stream)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(packB, 0, oz_packB_bytes(M, K), stream)) != cudaSuccess) return e;
-    if (nkb > 1) packT = nullptr;
     if (packT && (e = cudaMemsetAsync(packT, 0, oz_packA_bytes(M, K), stream)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(Gq, 0, sizeof(double) * oz_g_entries(M), stream)) != cudaSuccess) return e;
     const long long n = (long long)M * K * 3;

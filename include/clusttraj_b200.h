@@ -47,7 +47,7 @@ typedef struct ct_stats {
     double pack_ms;      /* K1 centre/pack kernels of the last ct_load_frames */
     double h2d_ms;       /* host->device copy of the coordinates in the last ct_load_frames */
     double kernel_ms;    /* sum of the hot-path kernel launches (Gram+epilogue, fix-up, per-pair) */
-    double gram_ms;      /* the DMMA Gram + fused epilogue kernel only */
+    double gram_ms;      /* the Gram + fused epilogue kernel only (either path) */
     double pair_ms;      /* per-pair kernel (stepwise / Hungarian modes, fix-up of flagged pairs) */
     double d2h_ms;       /* device->host streaming of the condensed slab (overlapped with compute) */
     double total_ms;     /* first launch to last byte on the host, device clock */
@@ -56,6 +56,9 @@ typedef struct ct_stats {
     int64_t launches;    /* kernel launches issued by the engine in this call */
     int64_t kept_atoms;  /* K: atoms entering the contraction after the mask */
     int64_t lsap_steps;  /* total shortest-augmenting-path scan steps (Hungarian modes) */
+    int64_t gram_path;   /* kernel behind the pure-Kabsch modes: 0 = none (per-pair kernel), 1 = FP64 DMMA Gram kernel,
+                            2 = int8 tcgen05 Gram kernel (exact digit split of 31-bit fixed-point coordinates) */
+    double quant_step;   /* path 2: the fixed-point quantum 2^-f in Angstrom (RMSD moves by at most ~1.8 quanta) */
 } ct_stats;
 
 /* Lifetime.  device = CUDA ordinal.  Fails (never falls back to the CPU) when no device exists. */
