@@ -3,9 +3,10 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg2|cfg3|cfg4|cfg5]
 
-One "step" = one pass of the hot path over one synthetic trajectory: centre/pack (K1), the DMMA Gram
-kernel with its fused RMSD epilogue (K2) and the fix-up of flagged pairs, producing the rank's slab of the
-condensed matrix.  N = 1 runs BASELINE config 2 (20k frames x 100 atoms, plain Kabsch).  N > 1 (torchrun,
+One "step" = one pass of the hot path over one synthetic trajectory: centre/pack (K1), the Gram kernel with
+its fused RMSD epilogue (K2: the int8 tcgen05 kernel by default, the FP64 DMMA kernel with
+CLUSTTRAJ_B200_GRAM_VARIANT=-2) and the fix-up of flagged pairs, producing the rank's slab of the condensed
+matrix.  N = 1 runs BASELINE config 2 (20k frames x 100 atoms, plain Kabsch).  N > 1 (torchrun,
 one rank per GPU) shards ONE matrix over the ranks by equal-area row slabs with no collective on the data
 path; the frame count grows with sqrt(N) so that every GPU keeps config 2's pair count ("weak" scaling).
 
@@ -295,15 +296,42 @@ def run_b200_arm(args, rank, world, local_rank):
     else:
         flop_per_launch = 18.0 * K * my_pairs
         achieved = flop_per_launch / (mean_gram_ms * 1e-3) / 1e12
+        gram_path = int(st["gram_path"])
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": achieved / peak_tf, "traffic": None, "kernel": "gram_rmsd_kernel",
+                    "frac": achieved / peak_tf, "traffic": None,
                     "flop_per_pair": 18 * K, "pairs_per_launch": my_pairs, "launch_ms": mean_gram_ms,
-                    "peak_source": peak_src,
-                    "note": "FP64 tensor pipe (DMMA.8x8x4); algorithmic flops = 18*K per output pair, epilogue "
-                            "and padded/diagonal-block work not counted"}
-    traffic_file = os.path.join(ROOT, "profiles", "r01_gram_traffic.json")
-    if os.path.exists(traffic_file) and not kw.get("reorder") and name == "cfg2":
-        roofline["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+                    "peak_source": peak_src}
+        if gram_path == 2:
+            # int8 tcgen05 kernel: the FP64 contraction is rebuilt exactly from 15 int8 GEMMs (csrc/ozaki.cu), so the
+            # algorithmic FP64 rate may exceed the FP64 pipe's roofline; the int8 tensor pipe's own load is below
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
+                os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"bf16_tflops": 1590.0}
+            ntj = (M + 31) // 32
+            last = min(r1, M - 1)
+            blocks = sum(ntj - (40 * ti + 1) // 32 for ti in range(r0 // 40, (last + 39) // 40))
+            i8_ops = blocks * 15 * ((K + 31) // 32) * 2.0 * 128 * 96 * 32
+            i8_tops = i8_ops / (mean_gram_ms * 1e-3) / 1e12
+            i8_peak = 2.0 * float(peaks["bf16_tflops"])
+            roofline.update(
+                kernel="gram_i8_ts_kernel" if K <= 128 else "gram_i8_kernel",
+                tensor_pipe={"kind": "int8 tcgen05.mma (SASS UTCIMMA), M128 N96 K32", "issued_tops": i8_tops,
+                             "peak_tops": i8_peak, "frac": i8_tops / i8_peak,
+                             "peak_source": "2 x the measured dense bf16 rate of MEASURED_PEAKS.json (int8 runs at twice "
+                                            "the bf16 rate; no int8 figure is measured on this pool)"},
+                quant_step_angstrom=float(st["quant_step"]),
+                note="algorithmic FP64 flops (18*K per output pair) against the measured FP64 DMMA peak: the contraction "
+                     "runs on the int8 tensor pipe as an exact digit-split product of 31-bit fixed-point coordinates, "
+                     "so the fraction is not bounded by 1; the kernel is bound by its FP64 recombination + 3x3 solve "
+                     "epilogue (instruction issue), see profiles/")
+            traffic_file = os.path.join(ROOT, "profiles", "r01_gram_i8_traffic.json")
+        else:
+            roofline.update(
+                kernel="gram_rmsd_ws_kernel" if K > 64 else "gram_rmsd_kernel",
+                note="FP64 tensor pipe (DMMA.8x8x4); algorithmic flops = 18*K per output pair, epilogue "
+                     "and padded/diagonal-block work not counted")
+            traffic_file = os.path.join(ROOT, "profiles", "r01_gram_traffic.json")
+        if os.path.exists(traffic_file) and name == "cfg2":
+            roofline["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
 
     # ---- CPU baseline (bounded sample of the same workload, rank 0, N = 1 only) ---------------------------
     cpu = None

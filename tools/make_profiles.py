@@ -1,11 +1,14 @@
 """Turn the scratch ncu output under gpurun_out/ into the tracked summaries under profiles/.
 
-    python tools/make_profiles.py <round-tag> <gram .ncu-rep> [<pair .ncu-rep>] [<launch list csv>]
+    python tools/make_profiles.py <round-tag> <gram .ncu-rep> [<pair .ncu-rep>|-] [<launch list csv>|-] [<label>]
+
+<label> (default "gram") names the Gram kernel the capture is of: "gram" = FP64 DMMA kernel, "gram_i8" = int8 tcgen05 kernel.
 """
 import csv, io, json, os, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1]
+label = sys.argv[5] if len(sys.argv) > 5 else "gram"
 out_dir = os.path.join(ROOT, "profiles")
 
 
@@ -22,6 +25,9 @@ KEEP = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__b
         "sm__pipe_shared_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed",
         "sm__inst_executed_pipe_fp64.sum", "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
         "lts__t_bytes.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__cycles_elapsed.avg.per_second"]
 
 
@@ -51,16 +57,16 @@ def summarise(rep, name):
     return ms
 
 
-ms = summarise(sys.argv[2], "gram")
+ms = summarise(sys.argv[2], label)
 m = ms[-1]
 traffic = to_bytes(*m["dram__bytes_read.sum"]) + to_bytes(*m["dram__bytes_write.sum"])
-json.dump({"kernel": "gram_rmsd_kernel", "workload": "cfg2 20000 x 100 plain, one launch = whole matrix",
+json.dump({"kernel": m["Kernel Name"][0], "workload": "cfg2 20000 x 100 plain, one launch = whole matrix",
            "dram_bytes_read": to_bytes(*m["dram__bytes_read.sum"]), "dram_bytes_write": to_bytes(*m["dram__bytes_write.sum"]),
            "dram_bytes_per_launch": traffic, "duration_ms_under_ncu": float(m["gpu__time_duration.sum"][0]),
-           "source": os.path.basename(sys.argv[2])}, open(os.path.join(out_dir, f"{tag}_gram_traffic.json"), "w"), indent=1)
+           "source": os.path.basename(sys.argv[2])}, open(os.path.join(out_dir, f"{tag}_{label}_traffic.json"), "w"), indent=1)
 if len(sys.argv) > 3 and sys.argv[3] != "-":
     summarise(sys.argv[3], "pair")
-if len(sys.argv) > 4:
+if len(sys.argv) > 4 and sys.argv[4] != "-":
     rows = list(csv.reader(open(sys.argv[4])))
     hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
     hdr = rows[hi]; kn = hdr.index("Kernel Name"); mv = hdr.index("Metric Value")
@@ -75,7 +81,8 @@ if len(sys.argv) > 4:
              f"{'kernel':70s} {'launches':>8s} {'total_ms':>10s} {'share':>7s}"]
     for name, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         lines.append(f"{name[:70]:70s} {n:8d} {t / 1e6:10.3f} {100 * t / tot:6.1f}%")
-    open(os.path.join(out_dir, f"{tag}_launch_shares.txt"), "w").write("\n".join(lines) + "\n")
+    suffix = "" if label == "gram" else "_" + label
+    open(os.path.join(out_dir, f"{tag}_launch_shares{suffix}.txt"), "w").write("\n".join(lines) + "\n")
     import shutil
-    shutil.copy(sys.argv[4], os.path.join(out_dir, f"{tag}_launches_ncu.csv"))
+    shutil.copy(sys.argv[4], os.path.join(out_dir, f"{tag}_launches_ncu{suffix}.csv"))
     print("\n".join(lines))
