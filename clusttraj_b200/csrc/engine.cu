@@ -22,6 +22,7 @@ size_t oz_packA_bytes(int M, int K);
 size_t oz_packB_bytes(int M, int K);
 size_t oz_g_entries(int M);
 int oz_row_align();
+int oz_kernel_mode(int K);  // 4 / 2: A operand in TMEM (column tiles of 32 / 16 frames); 0: A through shared memory
 cudaError_t launch_quant_pack(const double* centred, int M, int K, uint8_t* packA, uint8_t* packB, uint8_t* packT, double* Gq,
                               double* qinfo, unsigned long long* maxbits, int sm_count, cudaStream_t stream);
 cudaError_t launch_gram_i8(OzParams p, int K, int sm_count, cudaStream_t stream);
@@ -256,9 +257,12 @@ int ct_load_frames(ct_engine* e, const double* coords, const int32_t* atomic_num
     if (e->use_gram && !e->use_i8)
         if ((rc = ensure(e, e->d_packed, e->packed_cap, (size_t)e->m_pad * k_pad * 3))) return rc;
     if (e->use_i8) {
-        if ((rc = ensure(e, e->d_packA, e->packA_cap, ct::oz_packA_bytes((int)M, K)))) return rc;
+        if (ct::oz_kernel_mode(K)) {
+            if ((rc = ensure(e, e->d_packT, e->packT_cap, ct::oz_packA_bytes((int)M, K)))) return rc;
+        } else {
+            if ((rc = ensure(e, e->d_packA, e->packA_cap, ct::oz_packA_bytes((int)M, K)))) return rc;
+        }
         if ((rc = ensure(e, e->d_packB, e->packB_cap, ct::oz_packB_bytes((int)M, K)))) return rc;
-        if ((rc = ensure(e, e->d_packT, e->packT_cap, ct::oz_packA_bytes((int)M, K)))) return rc;
         if ((rc = ensure(e, e->d_Gq, e->gq_cap, ct::oz_g_entries((int)M)))) return rc;
     }
 

@@ -120,6 +120,11 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
         "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
         : "memory");
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+                 "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -396,18 +401,56 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) gram_i8_kernel(const OzParams p
 // covariances and four solver warps.  The hand-off is also the transposition the row-per-lane accumulator layout
 // needs: accumulate warps write (frame i, coordinate a) rows, a solver lane reads the whole 3x3 of one pair, lanes
 // run along j, so the RMSD stores are 256-byte contiguous runs of the condensed vector.
-constexpr int TS_THREADS = 640;                       // 4 control warps + 16 epilogue warps
+// Two shapes, chosen by the padded atom count kp (a multiple of 32, all of the contraction in ONE shared-memory stage):
+//   NWG = 4: column tiles of 32 frames (N = 96), accumulators 384 TMEM columns, A up to 128 columns  -> kp <= 128
+//   NWG = 2: column tiles of 16 frames (N = 48), accumulators 192 TMEM columns, A up to 320 columns  -> kp <= 320
+// NWG is also the number of epilogue warpgroups: each owns 24 accumulator columns = 8 column frames.
+template <int NWG>
+struct TsCfg {
+    static constexpr int FJ = 8 * NWG;                 // frames per column tile
+    static constexpr int N = 3 * FJ;                   // MMA N
+    static constexpr int THREADS = 128 + 128 * NWG;    // 4 control warps + 4 NWG epilogue warps
+    static constexpr int KP_MAX = NWG == 4 ? 128 : 320;
+    static constexpr int ACOL = 4 * N;                 // first TMEM column of the A operand (after two level-pair buffers)
+    static constexpr int B_STAGE = OZ_SLICES * N * KP_MAX;
+    static constexpr int SCRATCH = NWG * OZ_FI * 73 * 8;
+    static constexpr int SMEM = 2 * B_STAGE + SCRATCH + 256;
+    static constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(OZ_M >> 4) << 24);
+    static_assert(ACOL + KP_MAX <= OZ_TMEM_COLS, "accumulators and the A operand must fit the 512 TMEM columns");
+};
 constexpr int TS_WG_PITCH = 73;                       // doubles per frame row of a warpgroup's hand-off region: 8 pairs x 9,
                                                       // padded to 9 (mod 16) 8-byte bank units: conflict-free both ways
-constexpr int TS_SCRATCH_BYTES = 4 * OZ_FI * TS_WG_PITCH * 8;
-constexpr int TS_SMEM_BYTES = 2 * OZ_B_BYTES + TS_SCRATCH_BYTES + 256;
-constexpr int TS_ACOL = 4 * OZ_N;                     // first TMEM column of the A operand (after two level-pair buffers)
-constexpr int TS_ROW_BYTES = OZ_SLICES * OZ_KB;       // one A row in HBM: [slice][128 B]
 
-__global__ void __launch_bounds__(TS_THREADS, 1) gram_i8_ts_kernel(const OzParams p) {
+// upper-triangle block walk for column tiles of FJ frames (see OzWalker)
+template <int FJ>
+struct TsWalker {
+    int ti, tj, ntj;
+    int left;
+    __host__ __device__ static int first_tj(int ti) { return (OZ_FI * ti + 1) / FJ; }
+    __device__ void init(int ti_begin, int ntj_, long long start, long long count) {
+        ntj = ntj_; left = (int)count; ti = ti_begin;
+        long long s = start;
+        for (;;) {
+            const long long n = ntj - first_tj(ti);
+            if (s < n) break;
+            s -= n; ++ti;
+        }
+        tj = first_tj(ti) + (int)s;
+    }
+    __device__ bool valid() const { return left > 0; }
+    __device__ void next() {
+        --left;
+        if (++tj >= ntj) { ++ti; tj = first_tj(ti); }
+    }
+};
+
+template <int NWG>
+__global__ void __launch_bounds__(TsCfg<NWG>::THREADS, 1) gram_i8_ts_kernel(const OzParams p) {
+    using Cfg = TsCfg<NWG>;
+    constexpr int FJ = Cfg::FJ, N = Cfg::N, ACOL = Cfg::ACOL;
     extern __shared__ __align__(1024) unsigned char smem[];
-    double* scratch = reinterpret_cast<double*>(smem + 2 * OZ_B_BYTES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * OZ_B_BYTES + TS_SCRATCH_BYTES);
+    double* scratch = reinterpret_cast<double*>(smem + 2 * Cfg::B_STAGE);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * Cfg::B_STAGE + Cfg::SCRATCH);
     uint64_t* bfull = bars;           // [2] B stage loaded
     uint64_t* bempty = bars + 2;      // [2] B stage consumed
     uint64_t* tfull = bars + 4;       // [2] level pair complete in TMEM
@@ -418,16 +461,17 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gram_i8_ts_kernel(const OzParam
 
     const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int ti_begin = p.row_begin / OZ_FI;
-    const int ntj = (p.M + OZ_FJ - 1) / OZ_FJ;
+    const int ntj = (p.M + FJ - 1) / FJ;
     const long long blk_start = p.total_blocks * blockIdx.x / gridDim.x;
     const long long blk_count = p.total_blocks * (blockIdx.x + 1) / gridDim.x - blk_start;
-    const int nch = p.last_chunks;    // 32-atom chunks in the (single) K-block
+    const int nch = p.last_chunks;    // 32-atom chunks of the contraction (all in one stage)
+    const int kp = 32 * nch;          // padded atoms = bytes per operand row per slice
 
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
             mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1);
-            mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 16);
+            mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4 * NWG);
         }
         mbar_init(a_ready, 4); mbar_init(a_free, 1);
         fence_barrier_init();
@@ -442,22 +486,22 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gram_i8_ts_kernel(const OzParam
         asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
         if (warp == 0 && lane == 0) {
             // ---- producer: the B tile of every block, four slices ------------------------------------------------
-            OzWalker w;
+            TsWalker<FJ> w;
             w.init(ti_begin, ntj, blk_start, blk_count);
             int stage = 0; uint32_t phase = 0;
-            const uint32_t b_bytes = (uint32_t)nch * (OZ_B_SLICE / 4);
+            const uint32_t b_slice = (uint32_t)(N * kp);   // one digit slice of a B tile
             for (; w.valid(); w.next()) {
                 mbar_wait_sleep(&bempty[stage], phase ^ 1, 2000u);
-                mbar_expect_tx(&bfull[stage], OZ_SLICES * b_bytes);
-                unsigned char* dst = smem + stage * OZ_B_BYTES;
-                const uint8_t* src = p.packB + (size_t)w.tj * OZ_B_BYTES;
+                mbar_expect_tx(&bfull[stage], OZ_SLICES * b_slice);
+                unsigned char* dst = smem + stage * Cfg::B_STAGE;
+                const uint8_t* src = p.packB + (size_t)w.tj * (OZ_SLICES * b_slice);
 #pragma unroll
-                for (int s = 0; s < OZ_SLICES; ++s) bulk_g2s(dst + s * OZ_B_SLICE, src + s * OZ_B_SLICE, b_bytes, &bfull[stage]);
+                for (int s = 0; s < OZ_SLICES; ++s) bulk_g2s(dst + s * b_slice, src + s * b_slice, b_slice, &bfull[stage]);
                 stage ^= 1; if (stage == 0) phase ^= 1;
             }
         } else if (warp == 1) {
             // ---- MMA issuer -----------------------------------------------------------------------------------------
-            OzWalker w;
+            TsWalker<FJ> w;
             w.init(ti_begin, ntj, blk_start, blk_count);
             int stage = 0; uint32_t phase = 0;
             int tb = 0; uint32_t tphase = 0;
@@ -474,7 +518,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gram_i8_ts_kernel(const OzParam
                 }
                 mbar_wait(&bfull[stage], phase);
                 tc_fence_after();
-                const uint32_t b_lo = ((uint32_t)(OZ_N * 16 >> 4) << 16) | (smem_u32(smem + stage * OZ_B_BYTES) >> 4);
+                const uint32_t b_lo = ((uint32_t)(N * 16 >> 4) << 16) | (smem_u32(smem + stage * Cfg::B_STAGE) >> 4);
+                const uint32_t b_slice16 = (uint32_t)(N * kp) >> 4, a_slice_cols = (uint32_t)kp >> 2;
 #pragma unroll
                 for (int pr = 0; pr < OZ_NPAIR; ++pr) {
                     mbar_wait(&tempty[tb], tphase ^ 1);
@@ -483,18 +528,17 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gram_i8_ts_kernel(const OzParam
 #pragma unroll
                         for (int lv = 0; lv < 2; ++lv) {
                             const int q = 2 * pr + lv;
-                            const uint32_t d = tmem_base + (uint32_t)(tb * 2 * OZ_N + lv * OZ_N);
+                            const uint32_t d = tmem_base + (uint32_t)(tb * 2 * N + lv * N);
                             const int s_lo = q > 3 ? q - 3 : 0, s_hi = q < 3 ? q : 3;
 #pragma unroll
                             for (int s = s_lo; s <= s_hi; ++s) {
-#pragma unroll
-                                for (int kc = 0; kc < 4; ++kc) {
-                                    if (kc < nch) {
-                                        const uint64_t bd = ((uint64_t)DESC_HI << 32) |
-                                                            (b_lo + (uint32_t)(((q - s) * OZ_B_SLICE + kc * 2 * OZ_N * 16) >> 4));
-                                        umma_i8_ts(d, tmem_base + (uint32_t)(TS_ACOL + s * 32 + kc * 8), bd, OZ_IDESC,
-                                                   (s > s_lo || kc > 0) ? 1u : 0u);
-                                    }
+#pragma unroll 2
+                                for (int kc = 0; kc < nch; ++kc) {
+                                    // one MMA = 32 atoms: A from 8 TMEM columns, B = two 16-byte K halves of N / 8 core matrices
+                                    const uint64_t bd = ((uint64_t)DESC_HI << 32) |
+                                                        (b_lo + (uint32_t)(q - s) * b_slice16 + (uint32_t)(kc * 2 * N));
+                                    umma_i8_ts(d, tmem_base + (uint32_t)ACOL + (uint32_t)s * a_slice_cols + (uint32_t)(kc * 8), bd,
+                                               Cfg::IDESC, (s > s_lo || kc > 0) ? 1u : 0u);
                                 }
                             }
                         }
@@ -510,9 +554,10 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gram_i8_ts_kernel(const OzParam
         }
     } else {
         // ---- epilogue warps (4 warpgroups): warpgroup wg owns accumulator columns 24 wg .. 24 wg + 23 = 8 column frames ----
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        if constexpr (NWG == 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
         const int quarter = warp & 3;                 // TMEM lanes 32 * quarter .. + 31
-        const int wg = (warp - 4) >> 2;               // 0..3
+        const int wg = (warp - 4) >> 2;               // 0..NWG-1
         const int wt = tid - 128 - wg * 128;          // thread index inside the warpgroup
         const int g = lane / 3, a = lane - 3 * g;
         const bool row_ok = lane < 30;
@@ -522,7 +567,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gram_i8_ts_kernel(const OzParam
         double* wg_scratch = scratch + wg * (OZ_FI * TS_WG_PITCH);
         double* my_row = wg_scratch + (quarter * 10 + g) * TS_WG_PITCH + 3 * a;
         const int last_row = min(p.row_end, p.M - 1);
-        OzWalker w;
+        TsWalker<FJ> w;
         w.init(ti_begin, ntj, blk_start, blk_count);
         int tb = 0; uint32_t tphase = 0;
         int cur_ti = -1; uint32_t afree_phase = 0;
@@ -530,16 +575,14 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gram_i8_ts_kernel(const OzParam
             if (wg == 0 && w.ti != cur_ti) {
                 // this warp's 32 A rows of the new block row: global -> registers -> TMEM
                 if (cur_ti >= 0) { mbar_wait(a_free, afree_phase); afree_phase ^= 1; tc_fence_after(); }
-                const uint4* src = reinterpret_cast<const uint4*>(p.packT + ((size_t)w.ti * OZ_M + quarter * 32 + lane) * TS_ROW_BYTES);
+                const uint4* src = reinterpret_cast<const uint4*>(p.packT + ((size_t)w.ti * OZ_M + quarter * 32 + lane) * (size_t)(OZ_SLICES * kp));
 #pragma unroll
                 for (int s = 0; s < OZ_SLICES; ++s) {
-                    uint32_t v[32];
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const uint4 x = __ldg(src + s * 8 + k);
-                        v[4 * k] = x.x; v[4 * k + 1] = x.y; v[4 * k + 2] = x.z; v[4 * k + 3] = x.w;
+                    for (int kc = 0; kc < nch; ++kc) {   // 32 atoms = 32 bytes = 8 TMEM columns
+                        const uint4 x0 = __ldg(src + (s * kp >> 4) + 2 * kc), x1 = __ldg(src + (s * kp >> 4) + 2 * kc + 1);
+                        const uint32_t v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+                        tmem_st8(tlane + (uint32_t)(ACOL + s * (kp >> 2) + kc * 8), v);
                     }
-                    tmem_st32(tlane + (uint32_t)(TS_ACOL + s * 32), v);
                 }
                 tmem_wait_st();
                 tc_fence_before();
@@ -548,7 +591,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gram_i8_ts_kernel(const OzParam
                 cur_ti = w.ti;
             }
             // G of this thread's pairs (the pass/slot mapping below): fetched now, used after the accumulate phase
-            const double gj = p.Gq[w.tj * OZ_FJ + wg * 8 + (lane & 7)];
+            const double gj = p.Gq[w.tj * FJ + wg * 8 + (lane & 7)];
             double gi[3];
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
@@ -562,12 +605,12 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gram_i8_ts_kernel(const OzParam
             for (int pr = 0; pr < OZ_NPAIR; ++pr) {
                 mbar_wait(&tfull[tb], tphase);
                 tc_fence_after();
-                const uint32_t t0 = tlane + (uint32_t)(tb * 2 * OZ_N + wg * 24);
+                const uint32_t t0 = tlane + (uint32_t)(tb * 2 * N + wg * 24);
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     uint32_t ev[8], od[8];
                     tmem_ld8(t0 + c * 8, ev);
-                    tmem_ld8(t0 + OZ_N + c * 8, od);
+                    tmem_ld8(t0 + N + c * 8, od);
                     tmem_wait_ld();
 #pragma unroll
                     for (int n = 0; n < 8; ++n)
@@ -602,7 +645,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) gram_i8_ts_kernel(const OzParam
                 const int pass = (wt >> 5) + 4 * r;
                 const int slot = 4 * pass + (lane >> 3);          // 0..39 (valid) .. 47
                 const int il = (slot / 5) + 8 * (slot % 5), jl = lane & 7;
-                const int i = w.ti * OZ_FI + il, j = w.tj * OZ_FJ + wg * 8 + jl;
+                const int i = w.ti * OZ_FI + il, j = w.tj * FJ + wg * 8 + jl;
                 pi[r] = i; pj[r] = j;
                 out_row[r] = p.out + (condensed_row_base(p.M, i) - p.idx_base - i - 1);
                 const bool live = slot < OZ_FI && i < j && j < p.M;
@@ -680,12 +723,29 @@ __global__ void quant_info_kernel(const unsigned long long* maxbits, double* qin
     qinfo[2] = __longlong_as_double((long long)*maxbits);
 }
 
+// Which tcgen05 kernel serves K kept atoms, and the operand layouts it reads.
+//   mode 4 / 2: gram_i8_ts_kernel<4> / <2> (A in TMEM; column tiles of 32 / 16 frames), whole contraction in one stage:
+//               packT [ti][128 rows][slice][kp B], packB [tj][slice][kp / 16][N / 8][8 rows][16 B]
+//   mode 0    : gram_i8_kernel (A and B through shared memory, K-blocks of 128 atoms): packA / packB as in OzParams
+struct OzPlan {
+    int mode, kp, fj, n;   // kp = padded atoms per stage row, fj = frames per column tile, n = 3 fj
+    int groups;            // 16-atom groups per row
+};
+static OzPlan oz_plan(int K) {
+    OzPlan pl;
+    const int kp = (K + 31) / 32 * 32;
+    if (kp <= TsCfg<4>::KP_MAX) pl = {4, kp, TsCfg<4>::FJ, TsCfg<4>::N, kp / 16};
+    else if (kp <= TsCfg<2>::KP_MAX) pl = {2, kp, TsCfg<2>::FJ, TsCfg<2>::N, kp / 16};
+    else pl = {0, OZ_KB, OZ_FJ, OZ_N, (K + OZ_KB - 1) / OZ_KB * 8};
+    return pl;
+}
+
 // one thread = 16 consecutive atoms of one coordinate of one frame -> one 16-byte run per slice in each layout
-__global__ void __launch_bounds__(256) quant_pack_kernel(const double* __restrict__ centred, int M, int K, int nkb,
+__global__ void __launch_bounds__(256) quant_pack_kernel(const double* __restrict__ centred, int M, int K, OzPlan pl,
                                                          const unsigned long long* __restrict__ maxbits,
                                                          uint8_t* __restrict__ packA, uint8_t* __restrict__ packB,
                                                          uint8_t* __restrict__ packT) {
-    const int groups = nkb * 8;  // 16-atom groups per row
+    const int groups = pl.groups;
     const long long total = (long long)M * 3 * groups;
     const double scale = ldexp(1.0, quant_exponent(*maxbits));
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -715,30 +775,29 @@ __global__ void __launch_bounds__(256) quant_pack_kernel(const double* __restric
             w[2][t >> 2] |= (uint32_t)(d2 & 0xff) << sh;
             w[3][t >> 2] |= (uint32_t)(d3 & 0xff) << sh;
         }
-        const int kb = g16 >> 3, kc16 = g16 & 7;
-        {
-            const int ti = fr / OZ_FI, fi = fr - ti * OZ_FI;
-            const int row = (fi / 10) * 32 + (fi % 10) * 3 + c;
-            if (packA) {
-                uint8_t* dst = packA + ((size_t)ti * nkb + kb) * OZ_A_BYTES + (size_t)kc16 * (OZ_M * 16) + (row >> 3) * 128 + (row & 7) * 16;
+        const int ti = fr / OZ_FI, fi = fr - ti * OZ_FI;
+        const int rowA = (fi / 10) * 32 + (fi % 10) * 3 + c;
+        const int tj = fr / pl.fj, fj = fr - tj * pl.fj;
+        const int rowB = fj * 3 + c;
+        if (pl.mode) {
+            // A: one contiguous [slice][kp] run per TMEM lane; B: canonical no-swizzle K-major core matrices, all of K
+            uint8_t* dt = packT + ((size_t)ti * OZ_M + rowA) * (size_t)(OZ_SLICES * pl.kp) + g16 * 16;
+            uint8_t* db = packB + (size_t)tj * (size_t)(OZ_SLICES * pl.n * pl.kp) + (size_t)g16 * (pl.n * 16) + (rowB >> 3) * 128 +
+                          (rowB & 7) * 16;
 #pragma unroll
-                for (int s = 0; s < 4; ++s)
-                    *reinterpret_cast<uint4*>(dst + s * OZ_A_SLICE) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
+            for (int s = 0; s < 4; ++s) {
+                *reinterpret_cast<uint4*>(dt + s * pl.kp) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
+                *reinterpret_cast<uint4*>(db + (size_t)s * (pl.n * pl.kp)) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
             }
-            if (packT) {  // single K-block: [ti][row][slice][128 B], one contiguous 512 B run per TMEM lane
-                uint8_t* dt = packT + ((size_t)ti * OZ_M + row) * (OZ_SLICES * OZ_KB) + kc16 * 16;
+        } else {
+            const int nkb = groups >> 3, kb = g16 >> 3, kc16 = g16 & 7;
+            uint8_t* da = packA + ((size_t)ti * nkb + kb) * OZ_A_BYTES + (size_t)kc16 * (OZ_M * 16) + (rowA >> 3) * 128 + (rowA & 7) * 16;
+            uint8_t* db = packB + ((size_t)tj * nkb + kb) * OZ_B_BYTES + (size_t)kc16 * (OZ_N * 16) + (rowB >> 3) * 128 + (rowB & 7) * 16;
 #pragma unroll
-                for (int s = 0; s < 4; ++s)
-                    *reinterpret_cast<uint4*>(dt + s * OZ_KB) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
+            for (int s = 0; s < 4; ++s) {
+                *reinterpret_cast<uint4*>(da + s * OZ_A_SLICE) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
+                *reinterpret_cast<uint4*>(db + s * OZ_B_SLICE) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
             }
-        }
-        {
-            const int tj = fr / OZ_FJ, fj = fr - tj * OZ_FJ;
-            const int row = fj * 3 + c;
-            uint8_t* dst = packB + ((size_t)tj * nkb + kb) * OZ_B_BYTES + (size_t)kc16 * (OZ_N * 16) + (row >> 3) * 128 + (row & 7) * 16;
-#pragma unroll
-            for (int s = 0; s < 4; ++s)
-                *reinterpret_cast<uint4*>(dst + s * OZ_B_SLICE) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
         }
     }
 }
@@ -760,39 +819,66 @@ __global__ void __launch_bounds__(128) quant_g_kernel(const double* __restrict__
     if (lane == 0) Gq[fr] = 0.5 * g * ldexp(1.0, -2 * f);
 }
 
-size_t oz_packA_bytes(int M, int K) { return (size_t)((M + OZ_FI - 1) / OZ_FI) * ((K + OZ_KB - 1) / OZ_KB) * OZ_A_BYTES; }
-size_t oz_packB_bytes(int M, int K) { return (size_t)((M + OZ_FJ - 1) / OZ_FJ) * ((K + OZ_KB - 1) / OZ_KB) * OZ_B_BYTES; }
-size_t oz_g_entries(int M) {
-    const size_t a = (size_t)((M + OZ_FI - 1) / OZ_FI) * OZ_FI, b = (size_t)((M + OZ_FJ - 1) / OZ_FJ) * OZ_FJ;
-    return (a > b ? a : b) + 64;
+// operand buffer sizes (packA doubles as the size of packT: both hold ceil(M / 40) row tiles of 128 rows)
+size_t oz_packA_bytes(int M, int K) {
+    const OzPlan pl = oz_plan(K);
+    const size_t tiles = (size_t)((M + OZ_FI - 1) / OZ_FI);
+    return pl.mode ? tiles * OZ_M * OZ_SLICES * pl.kp : tiles * (size_t)(pl.groups >> 3) * OZ_A_BYTES;
 }
+size_t oz_packB_bytes(int M, int K) {
+    const OzPlan pl = oz_plan(K);
+    const size_t tiles = (size_t)((M + pl.fj - 1) / pl.fj);
+    return pl.mode ? tiles * OZ_SLICES * pl.n * pl.kp : tiles * (size_t)(pl.groups >> 3) * OZ_B_BYTES;
+}
+size_t oz_g_entries(int M) { return (size_t)((M + OZ_FI - 1) / OZ_FI) * OZ_FI + 128; }
 int oz_row_align() { return OZ_FI; }
 
 cudaError_t launch_quant_pack(const double* centred, int M, int K, uint8_t* packA, uint8_t* packB, uint8_t* packT, double* Gq,
                               double* qinfo, unsigned long long* maxbits, int sm_count, cudaStream_t stream) {
-    const int nkb = (K + OZ_KB - 1) / OZ_KB;
+    const OzPlan pl = oz_plan(K);
     cudaError_t e;
     if ((e = cudaMemsetAsync(maxbits, 0, sizeof(unsigned long long), stream)) != cudaSuccess) return e;
-    if (nkb > 1) packT = nullptr;   // several K-blocks: A streams through shared memory (packA)
-    else packA = nullptr;           // one K-block: A lives in TMEM, loaded from the row-major packT
-    if (packA && (e = cudaMemsetAsync(packA, 0, oz_packA_bytes(M, K), stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(pl.mode ? packT : packA, 0, oz_packA_bytes(M, K), stream)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(packB, 0, oz_packB_bytes(M, K), stream)) != cudaSuccess) return e;
-    if (packT && (e = cudaMemsetAsync(packT, 0, oz_packA_bytes(M, K), stream)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(Gq, 0, sizeof(double) * oz_g_entries(M), stream)) != cudaSuccess) return e;
     const long long n = (long long)M * K * 3;
     long long blocks = (n + 255) / 256;
     if (blocks > (long long)sm_count * 8) blocks = (long long)sm_count * 8;
     maxabs_kernel<<<(unsigned)blocks, 256, 0, stream>>>(centred, n, maxbits);
     quant_info_kernel<<<1, 1, 0, stream>>>(maxbits, qinfo);
-    const long long total = (long long)M * 3 * nkb * 8;
+    const long long total = (long long)M * 3 * pl.groups;
     blocks = (total + 255) / 256;
     if (blocks > (long long)sm_count * 16) blocks = (long long)sm_count * 16;
-    quant_pack_kernel<<<(unsigned)blocks, 256, 0, stream>>>(centred, M, K, nkb, maxbits, packA, packB, packT);
+    quant_pack_kernel<<<(unsigned)blocks, 256, 0, stream>>>(centred, M, K, pl, maxbits, packA, packB, packT);
     quant_g_kernel<<<(M + 3) / 4, 128, 0, stream>>>(centred, M, K, maxbits, Gq);
     return cudaGetLastError();
 }
 
+template <int NWG>
+static cudaError_t launch_ts(OzParams p, int sm_count, cudaStream_t stream) {
+    using Cfg = TsCfg<NWG>;
+    const int ti_begin = p.row_begin / OZ_FI;
+    const int last_row = p.row_end < p.M - 1 ? p.row_end : p.M - 1;
+    const int ti_end = (last_row + OZ_FI - 1) / OZ_FI;
+    const long long ntj = (p.M + Cfg::FJ - 1) / Cfg::FJ;
+    long long blocks = 0;
+    for (int ti = ti_begin; ti < ti_end; ++ti) blocks += ntj - TsWalker<Cfg::FJ>::first_tj(ti);
+    if (blocks <= 0) return cudaSuccess;
+    p.total_blocks = blocks;
+    const long long grid = blocks < sm_count ? blocks : sm_count;
+    cudaError_t e = cudaFuncSetAttribute(gram_i8_ts_kernel<NWG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) return e;
+    gram_i8_ts_kernel<NWG><<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM, stream>>>(p);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_gram_i8(OzParams p, int K, int sm_count, cudaStream_t stream) {
+    const OzPlan pl = oz_plan(K);
+    if (pl.mode) {
+        p.nkb = 1;
+        p.last_chunks = pl.kp / 32;
+        return pl.mode == 4 ? launch_ts<4>(p, sm_count, stream) : launch_ts<2>(p, sm_count, stream);
+    }
     p.nkb = (K + OZ_KB - 1) / OZ_KB;
     const int tail = K - (p.nkb - 1) * OZ_KB;
     p.last_chunks = (tail + 31) / 32;
@@ -805,16 +891,12 @@ cudaError_t launch_gram_i8(OzParams p, int K, int sm_count, cudaStream_t stream)
     if (blocks <= 0) return cudaSuccess;
     p.total_blocks = blocks;
     const long long grid = blocks < sm_count ? blocks : sm_count;
-    if (p.nkb == 1 && p.packT) {
-        cudaError_t e = cudaFuncSetAttribute(gram_i8_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        gram_i8_ts_kernel<<<(unsigned)grid, TS_THREADS, TS_SMEM_BYTES, stream>>>(p);
-        return cudaGetLastError();
-    }
     cudaError_t e = cudaFuncSetAttribute(gram_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES);
     if (e != cudaSuccess) return e;
     gram_i8_kernel<<<(unsigned)grid, OZ_THREADS, OZ_SMEM_BYTES, stream>>>(p);
     return cudaGetLastError();
 }
+
+int oz_kernel_mode(int K) { return oz_plan(K).mode; }
 
 }  // namespace ct

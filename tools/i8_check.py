@@ -24,7 +24,7 @@ def engine(variant):
 
 def main():
     mode = sys.argv[1] if len(sys.argv) > 1 else "quick"
-    e_ref = engine(None)
+    e_ref = engine(-2)
     e_i8 = engine(10)
     shapes = [(96, 50, {}), (41, 7, {}), (333, 100, {}), (700, 130, {}), (260, 64, dict(solute_natoms=20)),
               (500, 300, dict(no_hydrogen=True)), (1000, 300, {})]
