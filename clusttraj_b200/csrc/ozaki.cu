@@ -14,17 +14,21 @@
 //   * the epilogue recombines the six levels in FP64 (exact int -> double conversions, weights 2^(8(6-q)-2f)),
 //     takes G from the SAME quantised coordinates, and solves the 3x3 problem as gram.cu does.
 //
-// Shape on the tensor core: one tcgen05.mma is M=128 x N=96 x K=32 (int8).  The 128 A rows are 40 frames:
-// warp-quarter w, lane 3g+a  <->  frame 10w+g, coordinate a (two zero rows per quarter), so the three rows of a
-// frame's covariance sit in three adjacent TMEM lanes of ONE epilogue warp; the 96 B rows are 32 frames x 3
-// coordinates.  A CTA owns a contiguous run of (40 x 32)-frame blocks of the upper triangle (row-major), so the A
-// operand stays in shared memory while B streams.  Operands are stored in HBM already in the canonical
-// no-swizzle K-major core-matrix order (8 rows x 16 bytes contiguous), so a pipeline stage is a handful of 1-D
-// cp.async.bulk copies and the shared-memory descriptors need no swizzle.
+// Shape on the tensor core: one tcgen05.mma is M=128 x N=96 (or 48) x K=32 (int8).  The 128 A rows are 40 frames:
+// TMEM quarter w, lane 3g+a  <->  frame 10w+g, coordinate a (two zero rows per quarter), so the three rows of a
+// frame's covariance sit in three adjacent TMEM lanes of ONE epilogue warp; the B rows are 32 (16) frames x 3
+// coordinates.  A CTA owns a contiguous run of blocks of the upper triangle (row-major).  Operands are stored in HBM
+// already in the order the hardware wants (ct_load_frames -> quant_pack_kernel), so a pipeline stage is a handful of
+// 1-D cp.async.bulk copies and the shared-memory descriptors need no swizzle.
 //
-// Roles (384 threads, one CTA per SM): warp 0 = bulk-copy producer, warp 1 = MMA issuer (one lane), warp 2 =
-// TMEM allocator, warps 4-11 = epilogue (two warpgroups, 48 accumulator columns = 16 frame pairs per lane each).
-// TMEM: two buffers of 2 levels x 96 columns; the MMA warp fills one "level pair" while the epilogue drains the other.
+// Three kernels (launch_gram_i8 picks by the padded atom count kp):
+//   gram_i8_ts_kernel<4>  kp <= 128: A tile resident in TMEM (".ts" MMA), B streams, N = 96, 16 epilogue warps;
+//   gram_i8_ts_kernel<2>  kp <= 320: the same with N = 48 (A takes 320 of the 512 TMEM columns), 8 epilogue warps;
+//   gram_i8_kernel        larger kp: A and B both through shared memory in K-blocks of 128 atoms, 8 epilogue warps
+//                         that transpose with shuffles (shared memory is full); slower (shared-memory bound MMAs).
+// Roles in every kernel: warp 0 = bulk-copy producer (one lane), warp 1 = MMA issuer (one elected lane), warp 2 =
+// TMEM allocator, warps 4.. = epilogue.  TMEM: two buffers of 2 levels x N columns; the MMA warp fills one "level pair"
+// while the epilogue drains the other.
 #include "common.cuh"
 #include "solve3x3.cuh"
 
