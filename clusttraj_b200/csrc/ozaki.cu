@@ -32,6 +32,8 @@
 #include "common.cuh"
 #include "solve3x3.cuh"
 
+#include <cstdlib>
+
 namespace ct {
 
 constexpr int OZ_FI = 40;                    // frames per A (row) tile
@@ -48,7 +50,8 @@ constexpr int OZ_STAGES = 2;
 constexpr int OZ_THREADS = 384;
 constexpr int OZ_SMEM_BYTES = OZ_STAGES * OZ_STAGE_BYTES + 128;
 constexpr int OZ_TMEM_COLS = 512;
-constexpr int OZ_NPAIR = 3;                  // level pairs (levels 0..5)
+constexpr int OZ_NPAIR = 3;                  // level pairs (levels 0..5), issued in the order (2,3), (4,5), (0,1): the pair the
+                                             // epilogue waits for last is the cheapest one (3 of the 15 products)
 
 
 // ---- tcgen05 / TMEM PTX ------------------------------------------------------------------------------------
@@ -259,7 +262,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) gram_i8_kernel(const OzParams p
                     if (leader) {
 #pragma unroll
                         for (int lv = 0; lv < 2; ++lv) {
-                            const int q = 2 * pr + lv;
+                            const int q = 2 * ((pr + 1) % OZ_NPAIR) + lv;   // level pairs in the order (2,3), (4,5), (0,1)
                             const uint32_t d = tmem_base + (uint32_t)(tb * 2 * OZ_N + lv * OZ_N);
                             const int s_lo = q > 3 ? q - 3 : 0, s_hi = q < 3 ? q : 3;
 #pragma unroll
@@ -298,7 +301,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) gram_i8_kernel(const OzParams p
         const int u1 = (a + 2) % 3, u2 = (a + 1) % 3;   // which of the three pairs this lane SENDS in shuffle 1 / 2
         const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 48);
         const double s2 = p.qinfo[0];
-        const double sc[OZ_NPAIR] = {s2 * 1099511627776.0, s2 * 16777216.0, s2 * 256.0};   // 2^40, 2^24, 2^8
+        const double sc[OZ_NPAIR] = {s2 * 16777216.0, s2 * 256.0, s2 * 1099511627776.0};   // 2^24, 2^8, 2^40 (issue order)
         const int last_row = min(p.row_end, p.M - 1);
         OzWalker w;
         w.init(ti_begin, ntj, blk_start, blk_count);
@@ -531,7 +534,7 @@ __global__ void __launch_bounds__(TsCfg<NWG>::THREADS, 1) gram_i8_ts_kernel(cons
                     if (elect_one()) {
 #pragma unroll
                         for (int lv = 0; lv < 2; ++lv) {
-                            const int q = 2 * pr + lv;
+                            const int q = 2 * ((pr + 1) % OZ_NPAIR) + lv;   // level pairs in the order (2,3), (4,5), (0,1)
                             const uint32_t d = tmem_base + (uint32_t)(tb * 2 * N + lv * N);
                             const int s_lo = q > 3 ? q - 3 : 0, s_hi = q < 3 ? q : 3;
 #pragma unroll
@@ -567,7 +570,7 @@ __global__ void __launch_bounds__(TsCfg<NWG>::THREADS, 1) gram_i8_ts_kernel(cons
         const bool row_ok = lane < 30;
         const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
         const double s2 = p.qinfo[0];
-        const double sc[OZ_NPAIR] = {s2 * 1099511627776.0, s2 * 16777216.0, s2 * 256.0};
+        const double sc[OZ_NPAIR] = {s2 * 16777216.0, s2 * 256.0, s2 * 1099511627776.0};   // 2^24, 2^8, 2^40 (issue order)
         double* wg_scratch = scratch + wg * (OZ_FI * TS_WG_PITCH);
         double* my_row = wg_scratch + (quarter * 10 + g) * TS_WG_PITCH + 3 * a;
         const int last_row = min(p.row_end, p.M - 1);
@@ -671,10 +674,10 @@ __global__ void __launch_bounds__(TsCfg<NWG>::THREADS, 1) gram_i8_ts_kernel(cons
             }
             unsigned okmask;
             if ((wt >> 5) < 2) {
-                okmask = largest_root_lean<3>(qa, qb, qd, hg, lam);
+                okmask = largest_root_f64<3>(qa, qb, qd, hg, lam);
             } else {  // passes 10 and 11 do not exist: warps 2 and 3 of the warpgroup have two passes
                 double a2[2] = {qa[0], qa[1]}, b2[2] = {qb[0], qb[1]}, d2[2] = {qd[0], qd[1]}, h2[2] = {hg[0], hg[1]}, l2[2];
-                okmask = largest_root_lean<2>(a2, b2, d2, h2, l2);
+                okmask = largest_root_f64<2>(a2, b2, d2, h2, l2);
                 lam[0] = l2[0]; lam[1] = l2[1]; lam[2] = 0.0;
             }
 #pragma unroll
@@ -682,9 +685,9 @@ __global__ void __launch_bounds__(TsCfg<NWG>::THREADS, 1) gram_i8_ts_kernel(cons
                 const int i = pi[r], j = pj[r];
                 const double eh = hg[r] - lam[r];
                 const double v = fmax(eh, 0.0) * p.inv_k2;
-                const float y = rsqrtf(fmaxf((float)v, 1e-37f));
-                double rm = v * (double)y;
-                rm = fma(fma(-rm, rm, v), (double)(0.5f * y), rm);
+                const double y = rsqrt_approx_f64(fmax(v, 1e-300));        // sqrt(v) = v / sqrt(v), one Newton step
+                double rm = v * y;
+                rm = fma(fma(-rm, rm, v), 0.5 * y, rm);
                 const bool ok = (okmask >> r) & 1u;
                 const bool mine = plive[r] && i >= p.row_begin && i < last_row;
                 if ((!ok || eh < p.flag_rel * hg[r]) && mine) {
@@ -738,8 +741,10 @@ struct OzPlan {
 static OzPlan oz_plan(int K) {
     OzPlan pl;
     const int kp = (K + 31) / 32 * 32;
-    if (kp <= TsCfg<4>::KP_MAX) pl = {4, kp, TsCfg<4>::FJ, TsCfg<4>::N, kp / 16};
-    else if (kp <= TsCfg<2>::KP_MAX) pl = {2, kp, TsCfg<2>::FJ, TsCfg<2>::N, kp / 16};
+    const char* force = getenv("CLUSTTRAJ_B200_OZ_MODE");   // development: 2 = prefer the N = 48 shape, 0 = shared-memory kernel
+    const int fm = force ? atoi(force) : 4;
+    if (kp <= TsCfg<4>::KP_MAX && fm == 4) pl = {4, kp, TsCfg<4>::FJ, TsCfg<4>::N, kp / 16};
+    else if (kp <= TsCfg<2>::KP_MAX && fm != 0) pl = {2, kp, TsCfg<2>::FJ, TsCfg<2>::N, kp / 16};
     else pl = {0, OZ_KB, OZ_FJ, OZ_N, (K + OZ_KB - 1) / OZ_KB * 8};
     return pl;
 }

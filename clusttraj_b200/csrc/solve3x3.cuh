@@ -230,6 +230,64 @@ __device__ __forceinline__ unsigned largest_root_lean(const double (&a)[NP], con
     return ok;
 }
 
+// FP64 reciprocal / reciprocal square root approximations (about 23 bits; SASS MUFU.RCP64H / MUFU.RSQ64H): ONE
+// special-function-unit operation instead of the F2F + MUFU + F2F of going through FP32, which matters where the
+// quarter-rate XU pipe is shared by many warps doing the same solve (ozaki.cu).
+__device__ __forceinline__ double rcp_approx_f64(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return r;
+}
+__device__ __forceinline__ double rsqrt_approx_f64(double x) {
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return r;
+}
+
+// All-FP64 variant of the lockstep root solve: Newton from the upper bound min((G_i+G_j)/2, sqrt(3a)) with the
+// division replaced by rcp.approx.f64 (a step only needs ~1e-7 relative accuracy: the iteration is self-correcting),
+// no FP32 phase, no conversions.  Typical trajectories start within a few per cent of the root: 4 steps.  A pair has
+// settled when its step is below 1e-7 of the root (the error left is then ~1e-14); near-double roots (mirror images,
+// collinear atoms) converge linearly, run out of iterations and are reported through ok_mask for the fix-up path.
+template <int NP>
+__device__ __forceinline__ unsigned largest_root_f64(const double (&a)[NP], const double (&b)[NP], const double (&d)[NP],
+                                                     const double (&half_g)[NP], double (&lam)[NP]) {
+    double x[NP], m8d[NP], m4b[NP], d2[NP], last[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        const double a3 = 3.0 * a[p];
+        const double s = a3 * rsqrt_approx_f64(fmax(a3, 1e-300)) * 1.000001;   // >= sqrt(3a)
+        const double x0 = fmin(half_g[p], s);
+        x[p] = x0 > 0.0 ? x0 : 0.0;   // S == 0 (zero padding): every root is 0 and the iteration stays there
+        m8d[p] = -8.0 * d[p];
+        m4b[p] = -4.0 * b[p];
+        d2[p] = 2.0 * d[p];
+        last[p] = 0.0;
+    }
+#pragma unroll 1
+    for (int it = 0; it < 32; ++it) {
+        bool settled = true;
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            const double t = fma(x[p], x[p], -a[p]);
+            const double f = fma(t, t, fma(m8d[p], x[p], m4b[p]));
+            const double fq = fma(x[p], t, -d2[p]);                      // f' / 4
+            const double step = fq > 0.0 ? f * (0.25 * rcp_approx_f64(fq)) : 0.0;
+            x[p] -= step;
+            last[p] = fabs(step);
+            settled = settled && (last[p] <= 1e-7 * x[p]);
+        }
+        if (settled) break;
+    }
+    unsigned ok = 0;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        lam[p] = x[p];
+        if (last[p] <= 1e-7 * x[p] && x[p] == x[p]) ok |= 1u << p;
+    }
+    return ok;
+}
+
 // Cyclic Jacobi on a symmetric 4x4 matrix (in registers, fully unrolled indices).  On return A holds the
 // eigenvalues on its diagonal and the columns of V the eigenvectors.
 __device__ __forceinline__ void jacobi4(double (&A)[4][4], double (&V)[4][4]) {
