@@ -178,6 +178,13 @@ __device__ __forceinline__ double level_pair(int e, int o) {
     return __hiloint2double(hi, (int)(unsigned)(v & 0xffffffffLL)) - 6755399441055744.0;
 }
 
+// The same for kp <= 128 atoms: every level sum is below 4 * 2^14 * 128 = 2^23 there, so even * 256 + odd still fits
+// 32 bits (|v| < 1.62e9) and the 64-bit multiply-add and sign extension are not needed.
+__device__ __forceinline__ double level_pair32(int e, int o) {
+    const int v = e * 256 + o;
+    return __hiloint2double(0x43300000, v ^ (int)0x80000000) - 4503601774854144.0;   // 2^52 + 2^31
+}
+
 __device__ __forceinline__ double sel3(int k, double x0, double x1, double x2) { return k == 0 ? x0 : (k == 1 ? x1 : x2); }
 
 __global__ void __launch_bounds__(OZ_THREADS, 1) gram_i8_kernel(const OzParams p) {
@@ -621,7 +628,8 @@ __global__ void __launch_bounds__(TsCfg<NWG>::THREADS, 1) gram_i8_ts_kernel(cons
                     tmem_wait_ld();
 #pragma unroll
                     for (int n = 0; n < 8; ++n)
-                        acc[c * 8 + n] = fma(level_pair((int)ev[n], (int)od[n]), sc[pr], acc[c * 8 + n]);
+                        acc[c * 8 + n] = fma(NWG == 4 ? level_pair32((int)ev[n], (int)od[n]) : level_pair((int)ev[n], (int)od[n]), sc[pr],
+                                             acc[c * 8 + n]);
                 }
                 tc_fence_before();
                 __syncwarp();
