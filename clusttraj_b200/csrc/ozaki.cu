@@ -620,16 +620,20 @@ __global__ void __launch_bounds__(TsCfg<NWG>::THREADS, 1) gram_i8_ts_kernel(cons
                 mbar_wait(&tfull[tb], tphase);
                 tc_fence_after();
                 const uint32_t t0 = tlane + (uint32_t)(tb * 2 * N + wg * 24);
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    uint32_t ev[8], od[8];
-                    tmem_ld8(t0 + c * 8, ev);
-                    tmem_ld8(t0 + N + c * 8, od);
+                {   // 16 + 8 columns: two TMEM round trips per level pair instead of three
+                    uint32_t ev[16], od[16], ev2[8], od2[8];
+                    tmem_ld16(t0, ev);
+                    tmem_ld16(t0 + N, od);
+                    tmem_ld8(t0 + 16, ev2);
+                    tmem_ld8(t0 + N + 16, od2);
                     tmem_wait_ld();
 #pragma unroll
+                    for (int n = 0; n < 16; ++n)
+                        acc[n] = fma(NWG == 4 ? level_pair32((int)ev[n], (int)od[n]) : level_pair((int)ev[n], (int)od[n]), sc[pr], acc[n]);
+#pragma unroll
                     for (int n = 0; n < 8; ++n)
-                        acc[c * 8 + n] = fma(NWG == 4 ? level_pair32((int)ev[n], (int)od[n]) : level_pair((int)ev[n], (int)od[n]), sc[pr],
-                                             acc[c * 8 + n]);
+                        acc[16 + n] = fma(NWG == 4 ? level_pair32((int)ev2[n], (int)od2[n]) : level_pair((int)ev2[n], (int)od2[n]), sc[pr],
+                                          acc[16 + n]);
                 }
                 tc_fence_before();
                 __syncwarp();
