@@ -42,7 +42,7 @@ class ct_stats(C.Structure):
 EXPORTS = [
     "ct_version", "ct_device_count", "ct_last_error", "ct_engine_create", "ct_engine_destroy", "ct_host_alloc",
     "ct_host_free", "ct_load_frames", "ct_rows_pairs", "ct_rmsd_rows", "ct_rmsd_rows_device", "ct_copy_slab",
-    "ct_rmsd_condensed", "ct_pair_values", "ct_get_stats", "ct_pack_resident",
+    "ct_rmsd_condensed", "ct_pair_values", "ct_get_stats", "ct_pack_resident", "ct_matrix_consumers",
 ]
 
 _lib = None
@@ -86,6 +86,8 @@ def load_library(build_if_missing=True):
         lib.ct_pair_values.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, P(ct_stats)]
         lib.ct_get_stats.argtypes = [C.c_void_p, P(ct_stats)]
         lib.ct_pack_resident.argtypes = [C.c_void_p, P(ct_stats)]
+        lib.ct_matrix_consumers.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p,
+                                            P(C.c_double), P(ct_stats)]
         _lib = lib
         return lib
 
@@ -201,6 +203,31 @@ class Engine:
         self._check(self._lib.ct_pair_values(self._h, pairs.ctypes.data, len(pairs), vals.ctypes.data,
                                              perms.ctypes.data if want_perms else None, C.byref(st)), "ct_pair_values")
         return (vals, perms, st.as_dict()) if want_perms else (vals, st.as_dict())
+
+    def matrix_consumers(self, n_frames, clusters=None, distmat=None):
+        """(total sum, medoid frame index per cluster, stats) of a condensed matrix: `distmat` (host array) or, with
+        distmat=None, the whole matrix the last rmsd_rows_device(0, M) left on the GPU.  `clusters` = 1-based labels."""
+        M = int(n_frames)
+        ptr = None
+        if distmat is not None:
+            distmat = np.ascontiguousarray(distmat, dtype=np.float64)
+            if distmat.shape != (M * (M - 1) // 2,):
+                raise ValueError("distmat must be the condensed vector of n_frames frames")
+            ptr = distmat.ctypes.data
+        if clusters is None:
+            labels, n_clusters, med = None, 0, None
+        else:
+            labels = np.ascontiguousarray(clusters, dtype=np.int32)
+            if labels.shape != (M,):
+                raise ValueError("clusters must hold one label per frame")
+            n_clusters = int(len(np.unique(labels)))   # classify.py:157
+            med = np.empty(n_clusters, dtype=np.int64)
+        total = C.c_double()
+        st = ct_stats()
+        self._check(self._lib.ct_matrix_consumers(self._h, ptr, M, labels.ctypes.data if labels is not None else None,
+                                                  n_clusters, med.ctypes.data if med is not None else None,
+                                                  C.byref(total), C.byref(st)), "ct_matrix_consumers")
+        return float(total.value), med, st.as_dict()
 
     def stats(self):
         st = ct_stats()

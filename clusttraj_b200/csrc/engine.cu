@@ -28,6 +28,10 @@ cudaError_t launch_quant_pack(const double* centred, int M, int K, uint8_t* pack
 cudaError_t launch_gram_i8(OzParams p, int K, int sm_count, cudaStream_t stream);
 cudaError_t launch_fixup(const double* centred, int M, int K, const FixList& fix, double* out, long long idx_base,
                          long long n_entries, unsigned long long* flagged_total, int sm_count, cudaStream_t stream);
+cudaError_t launch_consumers(const double* d, long long L, int M, const int* labels, int n_clusters, double* scratch,
+                             unsigned long long* best_bits, long long* medoid, int sm_count, cudaStream_t stream);
+int consumers_scratch_doubles(int M);
+int consumers_sum_offset(int M);
 struct PairPlan;
 struct PairPlanHost;
 int pair_plan_build(PairPlanHost** out, const int32_t* kept_z, int K, int natoms, const ct_opts* o, std::string& err);
@@ -69,6 +73,12 @@ struct ct_engine {
     ct::PairPlanHost* plan = nullptr;
     // outputs
     double* d_slab = nullptr; size_t slab_cap = 0;       // whole-slab device buffer (rows_device)
+    int64_t slab_full_M = 0;                             // > 0: d_slab holds the WHOLE matrix of that many frames
+    // consumers of the matrix (ct_matrix_consumers)
+    int* d_labels = nullptr; size_t labels_cap = 0;
+    double* d_cons = nullptr; size_t cons_cap = 0;
+    unsigned long long* d_best = nullptr; size_t best_cap = 0;
+    long long* d_medoid = nullptr; size_t medoid_cap = 0;
     double* d_chunk[2] = {nullptr, nullptr}; size_t chunk_cap = 0;  // streaming double buffer
     int2* d_fix_pairs = nullptr; unsigned int* d_fix_count = nullptr; unsigned int fix_cap = 1u << 20;
     unsigned long long* d_counters = nullptr;  // [0] flagged pairs, [1] lsap steps
@@ -174,6 +184,7 @@ void ct_engine_destroy(ct_engine* e) {
     cudaDeviceSynchronize();
     cudaFree(e->d_raw); cudaFree(e->d_keep); cudaFree(e->d_centred); cudaFree(e->d_G); cudaFree(e->d_packed);
     cudaFree(e->d_packA); cudaFree(e->d_packB); cudaFree(e->d_packT); cudaFree(e->d_Gq); cudaFree(e->d_qinfo); cudaFree(e->d_maxbits);
+    cudaFree(e->d_labels); cudaFree(e->d_cons); cudaFree(e->d_best); cudaFree(e->d_medoid);
     cudaFree(e->d_slab); cudaFree(e->d_chunk[0]); cudaFree(e->d_chunk[1]);
     cudaFree(e->d_fix_pairs); cudaFree(e->d_fix_count); cudaFree(e->d_counters);
     for (int k = 0; k < 2; ++k) { cudaEventDestroy(e->ev_chunk_done[k]); cudaEventDestroy(e->ev_copy_done[k]); }
@@ -387,6 +398,7 @@ int ct_rmsd_rows_device(ct_engine* e, int64_t row_begin, int64_t row_end, const 
     if (rc) return rc;
     CT_CUDA(e, cudaSetDevice(e->device));
     const int64_t n = ct_rows_pairs(e->M, row_begin, row_end);
+    e->slab_full_M = 0;
     if ((rc = ensure(e, e->d_slab, e->slab_cap, (size_t)std::max<int64_t>(n, 1)))) return rc;
     CT_CUDA(e, cudaMemsetAsync(e->d_counters, 0, sizeof(unsigned long long) * 4, e->s_compute));
     int64_t launches = 0;
@@ -405,6 +417,7 @@ int ct_rmsd_rows_device(ct_engine* e, int64_t row_begin, int64_t row_end, const 
     e->stats.kernel_ms = ms; e->stats.total_ms = ms; e->stats.d2h_ms = 0.0;
     e->stats.gram_ms = e->use_gram ? ms_main : 0.0; e->stats.pair_ms = e->use_gram ? ms - ms_main : ms;
     if ((rc = finish_stats(e, n, launches))) return rc;
+    if (row_begin == 0 && row_end >= e->M - 1) e->slab_full_M = e->M;
     if (out_dev) *out_dev = e->d_slab;
     if (stats) *stats = e->stats;
     return CT_OK;
@@ -528,6 +541,58 @@ int ct_pair_values(ct_engine* e, const int64_t* pairs, int64_t n_pairs, double* 
     cudaFree(d_pairs); cudaFree(d_vals); cudaFree(d_perms);
     int rc = finish_stats(e, n_pairs, 1);
     if (rc) return rc;
+    if (stats) *stats = e->stats;
+    return CT_OK;
+}
+
+int ct_matrix_consumers(ct_engine* e, const double* distmat, int64_t M, const int32_t* labels, int32_t n_clusters,
+                        int64_t* medoids, double* total, ct_stats* stats) {
+    if (!e) return fail(nullptr, CT_ERR_ARG, "engine is NULL");
+    if (M < 2 || M > (int64_t)1 << 30) return fail(e, CT_ERR_ARG, "ct_matrix_consumers: need 2 <= M <= 2^30 frames");
+    if (n_clusters < 0 || (n_clusters > 0 && (!labels || !medoids)))
+        return fail(e, CT_ERR_ARG, "ct_matrix_consumers: labels and medoids are required when n_clusters > 0");
+    if (!total) return fail(e, CT_ERR_ARG, "ct_matrix_consumers: total is NULL");
+    for (int64_t i = 0; n_clusters > 0 && i < M; ++i)
+        if (labels[i] < 1 || labels[i] > n_clusters)
+            return fail(e, CT_ERR_ARG, "ct_matrix_consumers: cluster labels must lie in 1..n_clusters");
+    CT_CUDA(e, cudaSetDevice(e->device));
+    const int64_t L = M * (M - 1) / 2;
+    int rc;
+    CT_CUDA(e, cudaEventRecord(e->ev_a, e->s_compute));
+    if (distmat) {
+        e->slab_full_M = 0;
+        if ((rc = ensure(e, e->d_slab, e->slab_cap, (size_t)L))) return rc;
+        CT_CUDA(e, cudaMemcpyAsync(e->d_slab, distmat, sizeof(double) * (size_t)L, cudaMemcpyHostToDevice, e->s_compute));
+        e->slab_full_M = M;
+    } else if (e->slab_full_M != M) {
+        return fail(e, CT_ERR_STATE, "ct_matrix_consumers: no whole matrix of M frames on the GPU "
+                                     "(pass distmat, or call ct_rmsd_rows_device(e, 0, M, ...) first)");
+    }
+    CT_CUDA(e, cudaEventRecord(e->ev_b, e->s_compute));
+    if ((rc = ensure(e, e->d_cons, e->cons_cap, (size_t)ct::consumers_scratch_doubles((int)M)))) return rc;
+    if (n_clusters > 0) {
+        if ((rc = ensure(e, e->d_labels, e->labels_cap, (size_t)M))) return rc;
+        if ((rc = ensure(e, e->d_best, e->best_cap, (size_t)n_clusters))) return rc;
+        if ((rc = ensure(e, e->d_medoid, e->medoid_cap, (size_t)n_clusters))) return rc;
+        CT_CUDA(e, cudaMemcpyAsync(e->d_labels, labels, sizeof(int) * (size_t)M, cudaMemcpyHostToDevice, e->s_compute));
+    }
+    CT_CUDA(e, ct::launch_consumers(e->d_slab, L, (int)M, e->d_labels, n_clusters, e->d_cons, e->d_best, e->d_medoid,
+                                    e->sm_count, e->s_compute));
+    CT_CUDA(e, cudaEventRecord(e->ev_c, e->s_compute));
+    CT_CUDA(e, cudaMemcpyAsync(total, e->d_cons + ct::consumers_sum_offset((int)M), sizeof(double), cudaMemcpyDeviceToHost,
+                               e->s_compute));
+    if (n_clusters > 0)
+        CT_CUDA(e, cudaMemcpyAsync(medoids, e->d_medoid, sizeof(long long) * (size_t)n_clusters, cudaMemcpyDeviceToHost,
+                                   e->s_compute));
+    CT_CUDA(e, cudaStreamSynchronize(e->s_compute));
+    for (int c = 0; c < n_clusters; ++c)
+        if (medoids[c] < 0 || medoids[c] >= M)  // the reference's np.argmin raises on an empty cluster (classify.py:163)
+            return fail(e, CT_ERR_ARG, "ct_matrix_consumers: cluster " + std::to_string(c + 1) + " has no members");
+    float ms = 0.f;
+    CT_CUDA(e, cudaEventElapsedTime(&ms, e->ev_a, e->ev_b)); e->stats.h2d_ms = ms;
+    CT_CUDA(e, cudaEventElapsedTime(&ms, e->ev_b, e->ev_c)); e->stats.kernel_ms = ms;
+    e->stats.total_ms = e->stats.h2d_ms + e->stats.kernel_ms;
+    e->stats.pairs = L; e->stats.launches = n_clusters > 0 ? 5 : 2;
     if (stats) *stats = e->stats;
     return CT_OK;
 }

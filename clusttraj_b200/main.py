@@ -5,6 +5,7 @@ import time
 
 import numpy as np
 
+from .classify import find_medoids_from_clusters, sum_distmat
 from .distmat import get_distmat
 from .io import Logger, configure_runtime
 
@@ -35,9 +36,16 @@ def main(args=None):
                        f"({n / max(t2 - t1, 1e-12):.3e} pairs/s)\n")
     _, clusters = classify(clust_opt, distmat)
     Logger.logger.info(f"A total {len(clusters)} snapshots were read and {clusters.max()} cluster(s) was(were) found.\n")
+    # the summary the reference writes (main.py:107-135): matrix sum, cluster sizes and medoids — both reductions
+    # run on the GPU (clusttraj_b200/classify.py) instead of over a host-side squareform
+    total = sum_distmat(distmat)
+    medoids = find_medoids_from_clusters(distmat, clusters)
     with open(clust_opt.summary_name, "w") as fh:
         fh.write(str(clust_opt))
-        fh.write(f"\nTotal sum of the RMSD matrix: {float(np.sum(distmat))}\n")
         fh.write(f"A total {len(clusters)} snapshots were read and {clusters.max()} cluster(s) was(were) found.\n")
+        fh.write(f"\nThe total sum of the RMSD matrix is {total}\n")
+        fh.write("\nCluster\tSize\tMedoid\n")
+        for c in range(1, int(clusters.max()) + 1):
+            fh.write(f"{c}\t{int((clusters == c).sum())}\t{int(medoids[c - 1])}\n")
     Logger.logger.info(f"Total wall time: {time.monotonic() - t0:.6f} s\n")
     return 0

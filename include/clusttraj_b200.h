@@ -109,6 +109,18 @@ int ct_rmsd_condensed(ct_engine* e, const double* coords, const int32_t* atomic_
 int ct_pair_values(ct_engine* e, const int64_t* pairs, int64_t n_pairs, double* values, int32_t* perms /* [n_pairs][K] or NULL */,
                    ct_stats* stats);
 
+/* Consumers of the condensed matrix at scale, replacing clusttraj/classify.py:146-177 without
+ * the M x M squareform the reference builds on the host:
+ *   *total      = sum_distmat(distmat)                                   (classify.py:168-177)
+ *   medoids[c]  = find_medoids_from_clusters(distmat, clusters)[c]       (classify.py:146-165): the member of cluster
+ *                 c+1 with the smallest sum of distances to the other members, lowest frame index on ties.
+ * distmat: HOST pointer to the M(M-1)/2 condensed vector (copied to the GPU), or NULL to use the whole matrix that
+ * ct_rmsd_rows_device(e, 0, M, ...) left there.  labels: [M] cluster ids 1..n_clusters (the fcluster / cut_tree+1
+ * convention of classify.py:110,136); n_clusters = 0 computes the sum alone.  A cluster without members is an error
+ * (the reference raises). */
+int ct_matrix_consumers(ct_engine* e, const double* distmat, int64_t M, const int32_t* labels, int32_t n_clusters,
+                        int64_t* medoids, double* total, ct_stats* stats);
+
 int ct_get_stats(const ct_engine* e, ct_stats* stats);
 const char* ct_version(void);
 

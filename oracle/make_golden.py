@@ -140,5 +140,53 @@ def main():
     print("max |reference-over-shims - reference golden| =", np.abs(mine - golden).max())
 
 
+
+def make_consumers_golden():
+    """tests/golden/reference_consumers.json: the UNMODIFIED clusttraj.classify.find_medoids_from_clusters /
+    sum_distmat (classify.py:146-177) on small matrices (the reference's own tests never call them)."""
+    import scipy.cluster.hierarchy as hcl
+
+    _import_reference()
+    import clusttraj.classify as ref_classify
+
+    assert ref_classify.__file__.startswith(REFERENCE), ref_classify.__file__
+    from clusttraj_b200.synth import make_trajectory
+    from oracle import distmat_restated as O
+
+    cases, matrices = {}, {}
+
+    def add(name, matrix_name, distmat, clusters):
+        distmat = np.asarray(distmat, dtype=np.float64)
+        clusters = np.asarray(clusters, dtype=int)
+        med = ref_classify.find_medoids_from_clusters(distmat, clusters)
+        tot = ref_classify.sum_distmat(distmat)
+        matrices[matrix_name] = [float(v).hex() for v in distmat]
+        cases[name] = {"matrix": matrix_name, "clusters": [int(c) for c in clusters],
+                       "medoids": [int(m) for m in med], "sum_hex": float(tot).hex(), "sum_repr": repr(float(tot))}
+
+    golden = np.load(os.path.join(GOLDEN, "ref_test_distmat.npy"))
+    add("ref_golden_3_clusters", "ref_golden", golden, [1, 2, 3])       # test/conftest.py:83-85
+    add("ref_golden_2_clusters", "ref_golden", golden, [1, 1, 2])       # test/test_classify.py:44
+    add("ref_golden_1_cluster", "ref_golden", golden, [1, 1, 1])
+    z, x = make_trajectory(60, 12, seed=31, n_modes=4)
+    d60 = O.build_distance_matrix(z, x)
+    Z = hcl.linkage(d60, "average")
+    for t in (0.5, 1.5, 3.0):
+        add(f"synth60_average_t{t}", "synth60", d60, hcl.fcluster(Z, t, criterion="distance"))
+    add("synth60_maxclust5", "synth60", d60, hcl.fcluster(hcl.linkage(d60, "ward"), 5, criterion="maxclust"))
+    rng = np.random.default_rng(77)
+    d45 = rng.uniform(0.1, 9.0, size=45 * 44 // 2)
+    lab = rng.integers(1, 6, size=45)
+    lab[:5] = (1, 2, 3, 4, 5)
+    add("random45_5_labels", "random45", d45, lab)
+    with open(os.path.join(GOLDEN, "reference_consumers.json"), "w") as fh:
+        json.dump({"matrices": matrices, "cases": cases}, fh, indent=0)
+    print("wrote", os.path.join(GOLDEN, "reference_consumers.json"), {k: v["medoids"] for k, v in cases.items()})
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "consumers":
+        make_consumers_golden()
+    else:
+        main()
+        make_consumers_golden()

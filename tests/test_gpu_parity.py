@@ -484,3 +484,114 @@ def test_int8_kernel_error_is_a_rigid_input_perturbation():
     assert np.abs(got - exact)[~far].max() <= 1e-9
     assert np.abs(got - exact).max() <= 2 * q
     e.close()
+
+
+# ---- consumers of the matrix: sum_distmat / find_medoids_from_clusters (clusttraj/classify.py:146-177) -----------------
+
+def _consumer_cases(golden_dir):
+    import json
+
+    with open(os.path.join(golden_dir, "reference_consumers.json")) as fh:
+        data = json.load(fh)
+    mats = {k: np.array([float.fromhex(h) for h in v]) for k, v in data["matrices"].items()}
+    return [(name, mats[c["matrix"]], np.array(c["clusters"]), np.array(c["medoids"]), float.fromhex(c["sum_hex"]))
+            for name, c in data["cases"].items()]
+
+
+def test_consumers_against_unmodified_reference(golden_dir):
+    """The package's classify entry points (same names and arguments as the reference's) on the vectors the unmodified
+    clusttraj/classify.py produced."""
+    from clusttraj_b200.classify import find_medoids_from_clusters, sum_distmat
+
+    for name, d, clusters, medoids, total in _consumer_cases(golden_dir):
+        got = find_medoids_from_clusters(d, clusters)
+        assert got.dtype.kind == "i" and (got == medoids).all(), (name, got, medoids)
+        assert abs(sum_distmat(d) - total) <= 1e-12 * abs(total), name
+
+
+def test_consumers_on_the_device_resident_matrix():
+    """Medoids and sum straight from the matrix ct_rmsd_rows_device left on the GPU (no host round trip), against the
+    oracle; empty clusters and bad labels are errors like in the reference."""
+    import scipy.cluster.hierarchy as hcl
+    from clusttraj_b200 import _engine
+    from clusttraj_b200.synth import make_trajectory
+    from oracle import classify_restated as C
+
+    M = 700
+    atoms, coords = make_trajectory(M, 30, seed=44, n_modes=6)
+    e = _engine_with("-2")
+    e.load_frames(coords, atoms, engine_opts())
+    _, n, _ = e.rmsd_rows_device(0, M)
+    d = e.copy_slab(0, n)
+    for method, k in (("average", 6), ("ward", 23), ("complete", 1)):
+        clusters = hcl.fcluster(hcl.linkage(d, method), k, criterion="maxclust")
+        total, med, st = e.matrix_consumers(M, clusters=clusters)        # distmat=None: the resident matrix
+        want = C.find_medoids_from_clusters(d, clusters)
+        if not (med == want).all():   # only a floating-point tie between two candidates may differ
+            S = C.member_sums(d, clusters)
+            assert np.abs(S[med] - S[want]).max() <= 1e-12 * S.max()
+        assert abs(total - C.sum_distmat(d)) <= 1e-12 * total
+        assert st["h2d_ms"] < 1.0   # nothing was uploaded
+    with pytest.raises(_engine.EngineError, match="must lie in 1..n_clusters"):
+        # 2 distinct labels but no cluster "2": the reference's np.argmin raises on the empty cluster (classify.py:164)
+        e.matrix_consumers(M, clusters=np.where(np.arange(M) < 5, 1, 3))
+    e.load_frames(coords[:50], atoms, engine_opts())
+    e.rmsd_rows_device(0, 50)
+    with pytest.raises(_engine.EngineError, match="no whole matrix"):
+        e.matrix_consumers(M, clusters=np.ones(M, int))
+    e.close()
+
+
+def test_consumers_config2_size():
+    """20k frames (2.0e8 entries, 1.6 GB): one pass over the vector on the GPU; the reference's squareform would need
+    a 3.2 GB square matrix on the host.  Checked on sampled clusters against direct sums."""
+    from clusttraj_b200 import _engine
+
+    M = 20000
+    rng = np.random.default_rng(3)
+    d = _engine.pinned_empty(M * (M - 1) // 2)
+    d[:] = rng.random(d.size)
+    clusters = rng.integers(1, 41, size=M)
+    clusters[:40] = np.arange(1, 41)
+    e = _engine_with(None)
+    total, med, st = e.matrix_consumers(M, clusters=clusters, distmat=d)
+    assert abs(total - float(np.sum(d))) <= 1e-11 * total
+    print(f"consumers on 2.0e8 entries: upload {st['h2d_ms']:.1f} ms, kernels {st['kernel_ms']:.2f} ms")
+
+    def member_sum(i):
+        js = np.where(clusters == clusters[i])[0]
+        js = js[js != i]
+        lo, hi = np.minimum(i, js), np.maximum(i, js)
+        return d[M * lo - lo * (lo + 1) // 2 + (hi - lo - 1)].sum()
+
+    for c in (1, 17, 40):
+        members = np.where(clusters == c)[0]
+        sums = np.array([member_sum(int(i)) for i in members])
+        assert clusters[med[c - 1]] == c
+        assert member_sum(int(med[c - 1])) <= sums.min() * (1 + 1e-12)
+    e.close()
+
+
+def test_cli_config1_end_to_end(golden_dir, tmp_path):
+    """BASELINE config 1: the reference's test trajectory, -rmsd 1.0, no reorder, average linkage, through the CLI:
+    matrix on the GPU -> SciPy linkage -> labels [1 2 3] -> summary with the matrix sum and medoids."""
+    import shutil
+
+    from clusttraj_b200.main import main
+
+    traj = str(tmp_path / "testtraj.xyz")
+    shutil.copy(os.path.join(golden_dir, "ref_testtraj.xyz"), traj)
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        rc = main([traj, "-rmsd", "1.0", "-m", "average", "-f"])
+    finally:
+        os.chdir(cwd)
+    assert rc == 0
+    d = np.load(tmp_path / "distmat.npy")
+    want = np.array([3.4161225575825, 4.370869363191556, 4.468489811370548])   # SURVEY.md 8c(2), plain mode
+    assert np.abs(d - want).max() <= 1e-7
+    assert (np.loadtxt(tmp_path / "clusters.dat", dtype=int) == [1, 2, 3]).all()
+    text = open(tmp_path / "clusters.out").read()
+    assert "3 cluster(s)" in text and "The total sum of the RMSD matrix is 12.2554" in text
+    assert "1\t1\t0" in text and "3\t1\t2" in text   # every frame is the medoid of its own cluster

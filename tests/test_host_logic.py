@@ -162,3 +162,20 @@ def test_classify_on_golden_vector(tmp_path, ref_golden_distmat):
     assert list(clusters) == [1, 2, 3]
     opt.update({"n_clusters": 2})
     assert list(classify(opt, ref_golden_distmat)[1]) == [1, 1, 2]
+
+
+def test_classify_consumers_check_arguments_and_fail_loudly_without_a_gpu():
+    """clusttraj_b200.classify mirrors classify.py:146-177; shape errors are raised on the host like squareform's,
+    and without a GPU the functions raise instead of falling back to a CPU path."""
+    from clusttraj_b200 import _engine
+    from clusttraj_b200.classify import find_medoids_from_clusters, sum_distmat
+
+    with pytest.raises(ValueError, match="condensed"):
+        sum_distmat(np.zeros(4))                      # 4 is not M (M - 1) / 2
+    with pytest.raises(ValueError, match="one label per frame"):
+        find_medoids_from_clusters(np.zeros(3), np.array([1, 2]))
+    if _engine.device_count() == 0:
+        with pytest.raises(_engine.EngineError):
+            sum_distmat(np.zeros(3))
+        with pytest.raises(_engine.EngineError):
+            find_medoids_from_clusters(np.zeros(3), np.array([1, 1, 2]))

@@ -72,3 +72,26 @@ def test_linkage_labels_config1(reference_vectors):
     assert list(hcl.fcluster(Z, 1.0, criterion="distance")) == [1, 2, 3]
     assert Z[0, 2] == pytest.approx(3.4161225575825, abs=1e-12)
     assert Z[1, 2] == pytest.approx(4.419679587281052, abs=1e-12)
+
+
+# ---- consumers of the matrix (clusttraj/classify.py:146-177) -------------------------------------------------------
+
+def _consumer_cases(golden_dir):
+    import json
+
+    with open(os.path.join(golden_dir, "reference_consumers.json")) as fh:
+        data = json.load(fh)
+    mats = {k: np.array([float.fromhex(h) for h in v]) for k, v in data["matrices"].items()}
+    return [(name, mats[c["matrix"]], np.array(c["clusters"]), np.array(c["medoids"]), float.fromhex(c["sum_hex"]))
+            for name, c in data["cases"].items()]
+
+
+def test_consumers_oracle_matches_unmodified_reference(golden_dir):
+    """oracle/classify_restated.py against what the unmodified classify.py produced (oracle/make_golden.py)."""
+    from oracle import classify_restated as C
+
+    cases = _consumer_cases(golden_dir)
+    assert len(cases) >= 8
+    for name, d, clusters, medoids, total in cases:
+        assert (C.find_medoids_from_clusters(d, clusters) == medoids).all(), name
+        assert C.sum_distmat(d) == total, name
