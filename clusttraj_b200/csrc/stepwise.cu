@@ -52,11 +52,12 @@ __host__ __device__ inline int pair_smem_per_warp(int nmax) {
     return (b + 15) / 16 * 16;
 }
 
-// sqrt for the Euclidean cost: FP32 rsqrt seed + two FP64 Newton steps on the residual (within 1 ulp of
-// the correctly rounded value, ~3x cheaper than the IEEE sequence and free of long dependent chains)
+// sqrt for the Euclidean cost: rsqrt.approx.f64 seed (one XU operation, ~22 bits; the FP32 rsqrt it replaces needed
+// two F2F conversions around it, and the quarter-rate XU pipe was as loaded as the FP64 pipe in the frontier scans)
+// + two FP64 Newton steps on the residual: within 1 ulp of the correctly rounded value, ~3x cheaper than the IEEE
+// sequence and free of long dependent chains
 __device__ __forceinline__ double cost_sqrt(double d2) {
-    const float y = rsqrtf(fmaxf((float)d2, 1e-30f));
-    const double yd = (double)y, h = 0.5 * yd;
+    const double yd = rsqrt_approx_f64(fmax(d2, 1e-300)), h = 0.5 * yd;
     double s = d2 * yd;
     s = fma(fma(-s, s, d2), h, s);
     s = fma(fma(-s, s, d2), h, s);
