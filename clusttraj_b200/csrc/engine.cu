@@ -292,6 +292,9 @@ int ct_load_frames(ct_engine* e, const double* coords, const int32_t* atomic_num
         double qi[4];
         CT_CUDA(e, cudaMemcpy(qi, e->d_qinfo, sizeof qi, cudaMemcpyDeviceToHost));
         e->quant_f = qi[1];
+        if (e->gram_variant == 10 && e->quant_f < 0)
+            return fail(e, CT_ERR_UNSUPPORTED, "the int8 Gram kernel was forced but the coordinates are not finite or span "
+                                               "more than 2^30 A");
         if (e->gram_variant == -1 && e->quant_f < e->min_quant_f) {
             // coordinates too far from the centroid for 31-bit fixed point at the accuracy bound: FP64 tensor path
             e->use_i8 = false;

@@ -720,7 +720,13 @@ __global__ void __launch_bounds__(TsCfg<NWG>::THREADS, 1) gram_i8_ts_kernel(cons
 __global__ void __launch_bounds__(256) maxabs_kernel(const double* __restrict__ x, long long n, unsigned long long* out) {
     double m = 0.0;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) m = fmax(m, fabs(x[k]));
+    bool bad = false;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        const double v = fabs(x[k]);
+        bad |= !(v <= 1.7976931348623157e308);   // NaN or infinity: no fixed-point image
+        m = fmax(m, v);
+    }
+    if (bad) m = __longlong_as_double(0x7ff0000000000000LL);   // +inf: quant_exponent() turns it into "do not quantise"
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(m));  // m >= 0: bit order = value order
@@ -730,6 +736,7 @@ __global__ void __launch_bounds__(256) maxabs_kernel(const double* __restrict__ 
 __device__ __forceinline__ int quant_exponent(unsigned long long maxbits) {
     const double m = __longlong_as_double((long long)maxbits);
     if (!(m > 0.0)) return 30;
+    if (!(m <= 1.7976931348623157e308)) return -1000;   // non-finite coordinates: the engine takes the FP64 kernel
     int e;
     frexp(m, &e);  // m = frac * 2^e, frac in [0.5, 1)  =>  m < 2^e
     return 30 - e;

@@ -595,3 +595,25 @@ def test_cli_config1_end_to_end(golden_dir, tmp_path):
     text = open(tmp_path / "clusters.out").read()
     assert "3 cluster(s)" in text and "The total sum of the RMSD matrix is 12.2554" in text
     assert "1\t1\t0" in text and "3\t1\t2" in text   # every frame is the medoid of its own cluster
+
+
+def test_non_finite_coordinates_take_the_fp64_kernel():
+    """A NaN coordinate has no fixed-point image: the engine must not quantise (it would turn NaN into a number) but
+    run the FP64 path, where the NaN reaches every value of that frame as it does in the reference."""
+    from clusttraj_b200 import _engine
+    from clusttraj_b200.synth import make_trajectory
+
+    atoms, coords = make_trajectory(50, 20, seed=2)
+    coords[7, 3, 1] = np.nan
+    e = _engine_with(None)
+    got, st = _full(e, atoms, coords)
+    assert st["gram_path"] == 1
+    bad = np.array([condensed_index(50, min(7, j), max(7, j)) for j in range(50) if j != 7])
+    assert np.isnan(got[bad]).all()
+    mask = np.ones(got.size, bool); mask[bad] = False
+    assert np.isfinite(got[mask]).all()
+    e.close()
+    forced = _engine_with("10")
+    with pytest.raises(_engine.EngineError, match="not finite"):
+        forced.load_frames(coords, atoms, engine_opts())
+    forced.close()
