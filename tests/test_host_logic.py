@@ -179,3 +179,51 @@ def test_classify_consumers_check_arguments_and_fail_loudly_without_a_gpu():
             sum_distmat(np.zeros(3))
         with pytest.raises(_engine.EngineError):
             find_medoids_from_clusters(np.zeros(3), np.array([1, 1, 2]))
+
+
+def test_native_readers_xyz_fast_path_pdb_gro(tmp_path, golden_dir):
+    """The bulk XYZ parse equals the line-by-line one (also on the reference's fixture); PDB (MODEL frames, element
+    column or atom-name guess) and GRO (nm -> Angstrom) give the same arrays as the XYZ of the same frames."""
+    from clusttraj_b200 import xyz
+    from clusttraj_b200.synth import make_trajectory
+
+    z, x = make_trajectory(7, 9, seed=3, n_duplicates=0, mirrored=False, decimals=3)
+    p = str(tmp_path / "t.xyz")
+    xyz.write_xyz(p, z, x, decimals=3)
+    a_fast, c_fast = xyz.read_xyz(p)
+    a_slow, c_slow = xyz._read_xyz_slow(open(p).read().split("\n"), p)
+    assert (a_fast == a_slow).all() and np.array_equal(c_fast, c_slow) and np.abs(c_fast - x).max() < 1e-12
+    ref = os.path.join(golden_dir, "ref_testtraj.xyz")
+    a1, c1 = xyz.read_xyz(ref)
+    a2, c2 = xyz._read_xyz_slow(open(ref).read().split("\n"), ref)
+    assert (a1 == a2).all() and np.array_equal(c1, c2) and c1.shape == (3, 41, 3)
+    # irregular file (blank line between frames): the fall-back takes over
+    irregular = str(tmp_path / "i.xyz")
+    text = open(p).read().split("\n")
+    open(irregular, "w").write("\n".join(text[:11]) + "\n\n" + "\n".join(text[11:]))
+    a3, c3 = xyz.read_xyz(irregular)
+    assert np.array_equal(c3, c_fast) and (a3 == a_fast).all()
+    # PDB with and without the element column, GRO
+    pdb = str(tmp_path / "t.pdb")
+    with open(pdb, "w") as fh:
+        for m in range(7):
+            fh.write(f"MODEL     {m + 1:4d}\n")
+            for k in range(9):
+                sym = xyz.SYMBOLS[int(z[k])]
+                el = f"{sym:>2s}" if m % 2 == 0 else "  "
+                fh.write(f"ATOM  {k + 1:5d} {sym + str(k):<4s} MOL A   1    {x[m, k, 0]:8.3f}{x[m, k, 1]:8.3f}{x[m, k, 2]:8.3f}"
+                         f"  1.00  0.00          {el}\n")
+            fh.write("ENDMDL\n")
+        fh.write("END\n")
+    ap, cp = xyz.read_trajectory(pdb)
+    assert (ap == a_fast).all() and np.abs(cp - x).max() < 1e-9
+    gro = str(tmp_path / "t.gro")
+    with open(gro, "w") as fh:
+        for m in range(7):
+            fh.write(f"frame {m}\n{9:5d}\n")
+            for k in range(9):
+                fh.write(f"{1:5d}{'MOL':<5s}{xyz.SYMBOLS[int(z[k])] + str(k):>5s}{k + 1:5d}"
+                         f"{x[m, k, 0] / 10:8.4f}{x[m, k, 1] / 10:8.4f}{x[m, k, 2] / 10:8.4f}\n")
+            fh.write("   5.00000   5.00000   5.00000\n")
+    ag, cg = xyz.read_trajectory(gro)
+    assert (ag == a_fast).all() and np.abs(cg - x).max() < 1e-3 + 1e-9   # .gro keeps 3-4 decimals of nm
