@@ -117,16 +117,6 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
                  : "r"(taddr)
                  : "memory");
 }
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
-        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
-        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
-        "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
-        "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
-        : "memory");
-}
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
                  "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
@@ -379,16 +369,16 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) gram_i8_kernel(const OzParams p
                 quartic_invariants(s9, qa[m], qb[m], qd[m]);
                 hg[m] = live ? gi + p.Gq[j] : 3.0;  // half sums: G_i = G_j = 3 for the identity stand-in
             }
-            const unsigned okmask = largest_root_lockstep<6>(qa, qb, qd, hg, lam);
+            const unsigned okmask = largest_root_f64<6>(qa, qb, qd, hg, lam);
 #pragma unroll
             for (int m = 0; m < 6; ++m) {
                 const int jj = 3 * m + a;
                 const int j = j0 + jj;
                 const double eh = hg[m] - lam[m];
                 const double v = fmax(eh, 0.0) * p.inv_k2;
-                const float y = rsqrtf(fmaxf((float)v, 1e-37f));
-                double r = v * (double)y;
-                r = fma(fma(-r, r, v), (double)(0.5f * y), r);
+                const double y = rsqrt_approx_f64(fmax(v, 1e-300));        // sqrt(v) = v / sqrt(v), one Newton step
+                double r = v * y;
+                r = fma(fma(-r, r, v), 0.5 * y, r);
                 const bool ok = (okmask >> m) & 1u;
                 const bool mine = row_mine && jj < 16 && i < j && j < p.M;
                 if ((!ok || eh < p.flag_rel * hg[m]) && mine) {

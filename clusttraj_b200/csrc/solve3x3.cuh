@@ -159,77 +159,6 @@ __device__ __forceinline__ unsigned largest_root_lockstep(const double (&a)[NP],
     return ok;
 }
 
-// Lean variant of largest_root_lockstep for epilogues that are bound by instruction issue (the tcgen05 path,
-// ozaki.cu): the FP32 phase has no per-pair bookkeeping — every pair takes every step (a converged pair barely
-// moves), the thread leaves the loop when all its steps are below 2e-5 of the root — and f' <= 0 (noise next to a
-// double root) simply freezes the pair, which the FP64 acceptance test then reports through ok_mask.
-template <int NP>
-__device__ __forceinline__ unsigned largest_root_lean(const double (&a)[NP], const double (&b)[NP], const double (&d)[NP],
-                                                      const double (&half_g)[NP], double (&lam)[NP]) {
-    float l0[NP], af[NP], df2[NP], m4d[NP], bf4[NP], x[NP];
-#pragma unroll
-    for (int p = 0; p < NP; ++p) {
-        const float af0 = (float)a[p];
-        float l = fminf((float)half_g[p], sqrtf(3.0f * af0)) * 1.000001f;
-        if (!(l > 0.0f)) l = 1.0f;
-        l0[p] = l;
-        const float sc = __frcp_rn(l);
-        const float sc2 = sc * sc;
-        af[p] = af0 * sc2;
-        df2[p] = 2.0f * ((float)d[p] * sc2 * sc);
-        m4d[p] = -4.0f * df2[p];
-        bf4[p] = 4.0f * ((float)b[p] * sc2 * sc2);
-        x[p] = 1.0f;
-    }
-#pragma unroll 1
-    for (int it = 0; it < 16; ++it) {
-        bool settled = true;
-#pragma unroll
-        for (int p = 0; p < NP; ++p) {
-            const float t = fmaf(x[p], x[p], -af[p]);
-            const float f = fmaf(t, t, fmaf(m4d[p], x[p], -bf4[p]));
-            const float fq = fmaf(x[p], t, -df2[p]);
-            const float step = fq > 1e-30f ? f * (0.25f * __frcp_rn(fq)) : 0.0f;
-            x[p] -= step;
-            settled = settled && (fabsf(step) <= 2e-5f * x[p]);
-        }
-        if (settled) break;
-    }
-    unsigned ok = 0;
-    double d2[NP], d8[NP], b4[NP];
-#pragma unroll
-    for (int p = 0; p < NP; ++p) {
-        d2[p] = 2.0 * d[p];
-        d8[p] = 8.0 * d[p];
-        b4[p] = 4.0 * b[p];
-        double l = (double)(x[p] * l0[p]);
-        const double t = fma(l, l, -a[p]);
-        const double f = fma(t, t, -fma(d8[p], l, b4[p]));
-        const double fq = fma(l, t, -d2[p]);
-        const double step = f * (double)(0.25f * __frcp_rn((float)fq));
-        l -= step;
-        lam[p] = l;
-        if (fabs(step) <= 1e-6 * l) ok |= 1u << p;
-    }
-    if (ok != (1u << NP) - 1u) {
-#pragma unroll
-        for (int p = 0; p < NP; ++p) {
-            if ((ok >> p) & 1u) continue;
-            if (a[p] == 0.0) { lam[p] = 0.0; ok |= 1u << p; continue; }
-#pragma unroll 1
-            for (int it = 0; it < 24; ++it) {
-                const double t = fma(lam[p], lam[p], -a[p]);
-                const double f = fma(t, t, -fma(d8[p], lam[p], b4[p]));
-                const double fq = fma(lam[p], t, -d2[p]);
-                const double st = f * (double)(0.25f * __frcp_rn((float)fq));
-                lam[p] -= st;
-                if (fabs(st) <= 1e-13 * lam[p]) { ok |= 1u << p; break; }
-            }
-        }
-    }
-    return ok;
-}
-
 // FP64 reciprocal / reciprocal square root approximations (about 23 bits; SASS MUFU.RCP64H / MUFU.RSQ64H): ONE
 // special-function-unit operation instead of the F2F + MUFU + F2F of going through FP32, which matters where the
 // quarter-rate XU pipe is shared by many warps doing the same solve (ozaki.cu).
