@@ -73,7 +73,7 @@ struct BlockWalker {
 };
 
 // Fused epilogue: each lane owns the 3x3 covariance of NP = 2*MA*MB frame pairs (acc[ma][mb][ca][cb][e]);
-// all of them are solved in lockstep (largest_root_lockstep) and stored into the condensed vector.
+// all of them are solved in lockstep (largest_root_f64) and stored into the condensed vector.
 template <class Cfg>
 __device__ __forceinline__ void epilogue_store(const double (&acc)[Cfg::MA][Cfg::MB][3][3][2], const GramParams& p, int i0,
                                                int j0, int wi, int wj, int lane, int last_row) {
@@ -98,7 +98,7 @@ __device__ __forceinline__ void epilogue_store(const double (&acc)[Cfg::MA][Cfg:
             }
         }
     }
-    const unsigned okmask = largest_root_lockstep<NP>(qa, qb, qd, hg, lam);
+    const unsigned okmask = largest_root_f64<NP>(qa, qb, qd, hg, lam);
 #pragma unroll
     for (int ma = 0; ma < MA; ++ma) {
         const int i = i0 + (wi * MA + ma) * 8 + (lane >> 2);

@@ -174,14 +174,22 @@ __device__ __forceinline__ double rsqrt_approx_f64(double x) {
 }
 
 // All-FP64 variant of the lockstep root solve: Newton from the upper bound min((G_i+G_j)/2, sqrt(3a)) with the
-// division replaced by rcp.approx.f64 (a step only needs ~1e-7 relative accuracy: the iteration is self-correcting),
-// no FP32 phase, no conversions.  Typical trajectories start within a few per cent of the root: 4 steps.  A pair has
-// settled when its step is below 1e-7 of the root (the error left is then ~1e-14); near-double roots (mirror images,
-// collinear atoms) converge linearly, run out of iterations and are reported through ok_mask for the fix-up path.
+// division replaced by rcp.approx.f64 (a step only needs ~1e-6 relative accuracy: the iteration is self-correcting),
+// no FP32 phase, no conversions.  Typical trajectories start within a few per cent of the root: 4 steps.
+// Acceptance must tell quadratic from linear convergence: at a (near-)double root — planar or collinear structures
+// (sigma_3 = 0 makes sigma_1+sigma_2+-sigma_3 coincide), mirror images — the steps only halve, a step of 1e-7 then
+// means an ERROR of 1e-7, and once the halving reaches the sqrt(eps) noise floor of a double root single steps
+// collapse at random.  A pair settles when its step is below 1e-7 of the root AND quadratically smaller than the step
+// before (step * x <= 16 * previous^2; on the very first step: below 1e-13 outright).  Pairs that never get there
+// within 20 steps are reported through ok_mask and re-done by the explicit-rotation fix-up path.
 template <int NP>
 __device__ __forceinline__ unsigned largest_root_f64(const double (&a)[NP], const double (&b)[NP], const double (&d)[NP],
                                                      const double (&half_g)[NP], double (&lam)[NP]) {
-    double x[NP], m8d[NP], m4b[NP], d2[NP], last[NP];
+    double x[NP], m8d[NP], m4b[NP], d2[NP];
+    int e_last[NP];                   // biased exponent of the previous step (the tests below are integer-only: the
+                                      // FP64 pipe is the busiest one in these epilogues)
+    unsigned ok = 0;
+    constexpr unsigned ALL = (1u << NP) - 1u;
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
         const double a3 = 3.0 * a[p];
@@ -191,28 +199,30 @@ __device__ __forceinline__ unsigned largest_root_f64(const double (&a)[NP], cons
         m8d[p] = -8.0 * d[p];
         m4b[p] = -4.0 * b[p];
         d2[p] = 2.0 * d[p];
-        last[p] = 0.0;
+        // "previous step" of the first step: 2^-22 x, so that only a first step below ~1e-12 x settles
+        e_last[p] = ((__double2hiint(x[p]) >> 20) & 0x7ff) - 22;
+        if (a[p] == 0.0) ok |= 1u << p;   // (a NaN covariance settles nowhere and goes to the fix-up path, which propagates it)
     }
 #pragma unroll 1
-    for (int it = 0; it < 32; ++it) {
-        bool settled = true;
+    for (int it = 0; it < 20 && ok != ALL; ++it) {
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
             const double t = fma(x[p], x[p], -a[p]);
             const double f = fma(t, t, fma(m8d[p], x[p], m4b[p]));
             const double fq = fma(x[p], t, -d2[p]);                      // f' / 4
-            const double step = fq > 0.0 ? f * (0.25 * rcp_approx_f64(fq)) : 0.0;
-            x[p] -= step;
-            last[p] = fabs(step);
-            settled = settled && (last[p] <= 1e-7 * x[p]);
+            const bool up = fq > 0.0;
+            const double step = up ? f * (0.25 * rcp_approx_f64(fq)) : 0.0;
+            x[p] -= step;                                                // a settled pair barely moves
+            // |step| <= 2^-23 x  and  |step| x <= 16 previous^2, on the exponents (each within a factor 2)
+            const int e_as = (__double2hiint(step) >> 20) & 0x7ff, e_x = (__double2hiint(x[p]) >> 20) & 0x7ff;
+            if (up && e_as + 23 <= e_x && e_as + e_x <= 2 * e_last[p] + 4) ok |= 1u << p;
+            e_last[p] = e_as;
         }
-        if (settled) break;
     }
-    unsigned ok = 0;
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
         lam[p] = x[p];
-        if (last[p] <= 1e-7 * x[p] && x[p] == x[p]) ok |= 1u << p;
+        if (!(x[p] == x[p])) ok &= ~(1u << p);
     }
     return ok;
 }

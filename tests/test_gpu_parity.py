@@ -617,3 +617,40 @@ def test_non_finite_coordinates_take_the_fp64_kernel():
     with pytest.raises(_engine.EngineError, match="not finite"):
         forced.load_frames(coords, atoms, engine_opts())
     forced.close()
+
+
+@pytest.mark.parametrize("kind", ["collinear", "planar", "two_atoms", "one_atom", "random_large_rmsd", "tiny_scale", "huge_scale"])
+def test_degenerate_geometries_on_both_gram_kernels(kind):
+    """Rank-deficient covariances (collinear / planar / 1-2 atoms: double roots of the quartic), structures with nothing in
+    common (start of the Newton iteration far above the root) and extreme length scales, on both Gram kernels."""
+    rng = np.random.default_rng(abs(hash(kind)) % 1000)
+    M = 57
+    if kind == "collinear":
+        t = rng.normal(size=(M, 23, 1))
+        frames = t * rng.normal(size=(M, 1, 3)) + rng.normal(size=(M, 1, 3))
+    elif kind == "planar":
+        uv = rng.normal(size=(M, 31, 2))
+        basis = rng.normal(size=(M, 2, 3))
+        frames = np.einsum("mnk,mkj->mnj", uv, basis) * 4.0
+    elif kind == "two_atoms":
+        frames = rng.normal(size=(M, 2, 3)) * 3.0
+    elif kind == "one_atom":
+        frames = rng.normal(size=(M, 1, 3)) * 3.0
+    elif kind == "random_large_rmsd":
+        frames = rng.normal(size=(M, 140, 3)) * 8.0
+    elif kind == "tiny_scale":
+        frames = rng.normal(size=(M, 40, 3)) * 1e-4
+    else:
+        frames = rng.normal(size=(M, 40, 3)) * 60.0
+    frames = np.ascontiguousarray(frames)
+    atoms = np.full(frames.shape[1], 6, np.int32)
+    want = oracle_rows(atoms, frames, range(M))
+    scale = max(float(np.abs(want).max()), 1e-300)
+    for variant, path in ((None, 2), ("-2", 1)):
+        e = _engine_with(variant)
+        got, st = _full(e, atoms, frames)
+        assert st["gram_path"] == path
+        assert np.isfinite(got).all() and (got >= 0).all()
+        tol = max(1e-9 * max(scale, 1.0), 2.0 * st["quant_step"]) if kind != "tiny_scale" else 1e-12
+        assert np.abs(got - want).max() <= tol, (kind, variant, np.abs(got - want).max(), tol, st["flagged"])
+        e.close()
