@@ -43,6 +43,7 @@ EXPORTS = [
     "ct_version", "ct_device_count", "ct_last_error", "ct_engine_create", "ct_engine_destroy", "ct_host_alloc",
     "ct_host_free", "ct_load_frames", "ct_rows_pairs", "ct_rmsd_rows", "ct_rmsd_rows_device", "ct_copy_slab",
     "ct_rmsd_condensed", "ct_pair_values", "ct_get_stats", "ct_pack_resident", "ct_matrix_consumers",
+    "ct_pair_transforms",
 ]
 
 _lib = None
@@ -86,6 +87,7 @@ def load_library(build_if_missing=True):
         lib.ct_pair_values.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, P(ct_stats)]
         lib.ct_get_stats.argtypes = [C.c_void_p, P(ct_stats)]
         lib.ct_pack_resident.argtypes = [C.c_void_p, P(ct_stats)]
+        lib.ct_pair_transforms.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, P(ct_stats)]
         lib.ct_matrix_consumers.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p,
                                             P(C.c_double), P(ct_stats)]
         _lib = lib
@@ -203,6 +205,17 @@ class Engine:
         self._check(self._lib.ct_pair_values(self._h, pairs.ctypes.data, len(pairs), vals.ctypes.data,
                                              perms.ctypes.data if want_perms else None, C.byref(st)), "ct_pair_values")
         return (vals, perms, st.as_dict()) if want_perms else (vals, st.as_dict())
+
+    def pair_transforms(self, pairs):
+        """(values, R [n,3,3], T [n,3]) for (reference frame, moving frame) pairs: aligned = (raw - centre) @ R + T is
+        what clusttraj/io.py:align_mol writes for the moving frame (all atoms)."""
+        pairs = np.ascontiguousarray(pairs, dtype=np.int64).reshape(-1, 2)
+        vals = np.empty(len(pairs), dtype=np.float64)
+        xf = np.empty((len(pairs), 12), dtype=np.float64)
+        st = ct_stats()
+        self._check(self._lib.ct_pair_transforms(self._h, pairs.ctypes.data, len(pairs), vals.ctypes.data, xf.ctypes.data,
+                                                 C.byref(st)), "ct_pair_transforms")
+        return vals, xf[:, :9].reshape(-1, 3, 3).copy(), xf[:, 9:].copy()
 
     def matrix_consumers(self, n_frames, clusters=None, distmat=None):
         """(total sum, medoid frame index per cluster, stats) of a condensed matrix: `distmat` (host array) or, with

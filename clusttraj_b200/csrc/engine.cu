@@ -41,7 +41,7 @@ cudaError_t launch_pairs_rows(const PairPlanHost* plan, const double* centred, i
                               cudaStream_t stream);
 cudaError_t launch_pairs_list(const PairPlanHost* plan, const double* centred, int M, int K, const long long* pairs_dev,
                               long long n_pairs, double* values_dev, int* perms_dev, unsigned long long* counters,
-                              int sm_count, cudaStream_t stream);
+                              int sm_count, cudaStream_t stream, double* xf_dev);
 }  // namespace ct
 
 struct ct_engine {
@@ -516,24 +516,28 @@ int ct_rmsd_condensed(ct_engine* e, const double* coords, const int32_t* atomic_
     return ct_rmsd_rows(e, 0, M, out, stats);
 }
 
-int ct_pair_values(ct_engine* e, const int64_t* pairs, int64_t n_pairs, double* values, int32_t* perms, ct_stats* stats) {
+static int pair_values_impl(ct_engine* e, const int64_t* pairs, int64_t n_pairs, double* values, int32_t* perms,
+                            double* transforms, bool ordered, ct_stats* stats, const char* who) {
     if (!e) return fail(nullptr, CT_ERR_ARG, "engine is NULL");
     if (!e->loaded) return fail(e, CT_ERR_STATE, "no frames loaded (call ct_load_frames first)");
-    if (n_pairs < 0 || (n_pairs > 0 && (!pairs || !values))) return fail(e, CT_ERR_ARG, "ct_pair_values: NULL argument");
-    for (int64_t t = 0; t < n_pairs; ++t)
-        if (pairs[2 * t] < 0 || pairs[2 * t + 1] >= e->M || pairs[2 * t] >= pairs[2 * t + 1])
-            return fail(e, CT_ERR_ARG, "ct_pair_values: need 0 <= i < j < M");
+    if (n_pairs < 0 || (n_pairs > 0 && (!pairs || !values))) return fail(e, CT_ERR_ARG, std::string(who) + ": NULL argument");
+    for (int64_t t = 0; t < n_pairs; ++t) {
+        const int64_t i = pairs[2 * t], j = pairs[2 * t + 1];
+        if (i < 0 || j < 0 || i >= e->M || j >= e->M || i == j || (ordered && i > j))
+            return fail(e, CT_ERR_ARG, std::string(who) + (ordered ? ": need 0 <= i < j < M" : ": need two different frames in 0..M-1"));
+    }
     if (n_pairs == 0) return CT_OK;
     CT_CUDA(e, cudaSetDevice(e->device));
-    long long* d_pairs = nullptr; double* d_vals = nullptr; int* d_perms = nullptr;
+    long long* d_pairs = nullptr; double* d_vals = nullptr; int* d_perms = nullptr; double* d_xf = nullptr;
     CT_CUDA(e, cudaMalloc(&d_pairs, sizeof(long long) * 2 * (size_t)n_pairs));
     CT_CUDA(e, cudaMalloc(&d_vals, sizeof(double) * (size_t)n_pairs));
     if (perms) CT_CUDA(e, cudaMalloc(&d_perms, sizeof(int) * (size_t)n_pairs * e->K));
+    if (transforms) CT_CUDA(e, cudaMalloc(&d_xf, sizeof(double) * 12 * (size_t)n_pairs));
     CT_CUDA(e, cudaMemcpy(d_pairs, pairs, sizeof(long long) * 2 * (size_t)n_pairs, cudaMemcpyHostToDevice));
     CT_CUDA(e, cudaMemsetAsync(e->d_counters, 0, sizeof(unsigned long long) * 4, e->s_compute));
     CT_CUDA(e, cudaEventRecord(e->ev_a, e->s_compute));
     CT_CUDA(e, ct::launch_pairs_list(e->plan, e->d_centred, (int)e->M, e->K, d_pairs, n_pairs, d_vals, d_perms,
-                                     e->d_counters, e->sm_count, e->s_compute));
+                                     e->d_counters, e->sm_count, e->s_compute, d_xf));
     CT_CUDA(e, cudaEventRecord(e->ev_b, e->s_compute));
     CT_CUDA(e, cudaStreamSynchronize(e->s_compute));
     float ms = 0.f;
@@ -541,11 +545,22 @@ int ct_pair_values(ct_engine* e, const int64_t* pairs, int64_t n_pairs, double* 
     e->stats.kernel_ms = ms; e->stats.pair_ms = ms; e->stats.gram_ms = 0.0; e->stats.total_ms = ms; e->stats.d2h_ms = 0.0;
     CT_CUDA(e, cudaMemcpy(values, d_vals, sizeof(double) * (size_t)n_pairs, cudaMemcpyDeviceToHost));
     if (perms) CT_CUDA(e, cudaMemcpy(perms, d_perms, sizeof(int) * (size_t)n_pairs * e->K, cudaMemcpyDeviceToHost));
-    cudaFree(d_pairs); cudaFree(d_vals); cudaFree(d_perms);
+    if (transforms) CT_CUDA(e, cudaMemcpy(transforms, d_xf, sizeof(double) * 12 * (size_t)n_pairs, cudaMemcpyDeviceToHost));
+    cudaFree(d_pairs); cudaFree(d_vals); cudaFree(d_perms); cudaFree(d_xf);
     int rc = finish_stats(e, n_pairs, 1);
     if (rc) return rc;
     if (stats) *stats = e->stats;
     return CT_OK;
+}
+
+int ct_pair_values(ct_engine* e, const int64_t* pairs, int64_t n_pairs, double* values, int32_t* perms, ct_stats* stats) {
+    return pair_values_impl(e, pairs, n_pairs, values, perms, nullptr, true, stats, "ct_pair_values");
+}
+
+int ct_pair_transforms(ct_engine* e, const int64_t* pairs, int64_t n_pairs, double* values, double* transforms,
+                       ct_stats* stats) {
+    if (n_pairs > 0 && !transforms) return fail(e, CT_ERR_ARG, "ct_pair_transforms: transforms is NULL");
+    return pair_values_impl(e, pairs, n_pairs, values, nullptr, transforms, false, stats, "ct_pair_transforms");
 }
 
 int ct_matrix_consumers(ct_engine* e, const double* distmat, int64_t M, const int32_t* labels, int32_t n_clusters,

@@ -25,7 +25,7 @@ namespace ct {
 struct PairPlan {
     int K;            // kept atoms
     int natoms;       // kept solute atoms (0 without -ns)
-    int has_ns, do_reorder, solute_phase, final_direct, weighted;
+    int has_ns, do_reorder, solute_phase, final_direct, weighted, final_kabsch;
     double w_solute, w_solvent;  // per-atom weights (distmat.py:259-262)
     // element blocks: phase 0 = solute reorder (distmat.py:184-223), phase 1 = main reorder (:231-256)
     int nblocks[2];
@@ -253,6 +253,17 @@ __device__ __forceinline__ void warp_cov(const double* P, const double* Q, int k
     for (int t = 0; t < 9; ++t) s[t] = warp_sum(s[t]);
 }
 
+// R <- R * U (row-major 3x3, both act on row vectors from the right)
+__device__ __forceinline__ void mat3_rmul(double* R, const double* U) {
+    double T[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) T[3 * r + c] = fma(R[3 * r], U[c], fma(R[3 * r + 1], U[3 + c], R[3 * r + 2] * U[6 + c]));
+#pragma unroll
+    for (int t = 0; t < 9; ++t) R[t] = T[t];
+}
+
 __device__ int reorder_phase(const PairPlan& pl, int phase, double* W, int* perm, const double* Q, unsigned char* sm,
                              int lane) {
     const int nmax = pl.nmax;
@@ -302,10 +313,16 @@ __device__ int reorder_phase(const PairPlan& pl, int phase, double* W, int* perm
     return steps;
 }
 
+// XF: also return the rigid transform clusttraj/io.py:align_mol (582-756) applies to ALL atoms of the moving frame
+// (hydrogens and excluded atoms included) when it writes superposed structures: xf[0..8] = R (row-major, acts on row
+// vectors: out = (x - centre) R + T), xf[9..11] = T.  It is the product of the rotations of the value pipeline, except
+// for the last one, which align_mol only applies for -ns -e --final-kabsch and for -ws --final-kabsch (io.py:733-746).
+template <bool XF>
 __device__ double pair_value_warp(const PairPlan& pl, const double* __restrict__ Pg, const double* __restrict__ Qg,
-                                  double* W, int* perm, unsigned char* sm, int lane, int& steps) {
+                                  double* W, int* perm, unsigned char* sm, int lane, int& steps, double* xf) {
     const int K = pl.K, ns = pl.natoms;
     double s[9], U[9];
+    double Rt[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, Tt[3] = {0, 0, 0};
     steps = 0;
     // working copy of the moving frame; with -ns the reference subtracts centroid(Q[:natoms]) from P
     // once more (distmat.py:174) although Q is already centred on it
@@ -323,11 +340,13 @@ __device__ double pair_value_warp(const PairPlan& pl, const double* __restrict__
     warp_cov(W, Qg, pl.has_ns ? ns : K, lane, s);
     kabsch_rotation(s, U);
     warp_rotate(W, K, U, lane);
+    if (XF) mat3_rmul(Rt, U);
     if (pl.solute_phase) {
         steps += reorder_phase(pl, 0, W, perm, Qg, sm, lane);
         warp_cov(W, Qg, ns, lane, s);
         kabsch_rotation(s, U);
         warp_rotate(W, K, U, lane);
+        if (XF) mat3_rmul(Rt, U);
     }
     if (pl.do_reorder) steps += reorder_phase(pl, 1, W, perm, Qg, sm, lane);
 
@@ -340,12 +359,25 @@ __device__ double pair_value_warp(const PairPlan& pl, const double* __restrict__
             res += pl.weighted ? d2 * (k < ns ? pl.w_solute : pl.w_solvent) : d2;
         }
         res = warp_sum(res);
+        if (XF && lane == 0) {
+#pragma unroll
+            for (int t = 0; t < 9; ++t) xf[t] = Rt[t];
+            xf[9] = 0.0; xf[10] = 0.0; xf[11] = 0.0;
+        }
         return pl.weighted ? sqrt(res) : sqrt(res / (double)K);
     }
     if (!pl.weighted) {
         // rmsd.kabsch_rmsd: rotate again (no re-centring) and measure directly
         warp_cov(W, Qg, K, lane, s);
         kabsch_rotation(s, U);
+        if (XF) {
+            if (pl.has_ns && pl.do_reorder && pl.final_kabsch) mat3_rmul(Rt, U);   // io.py:743-746
+            if (lane == 0) {
+#pragma unroll
+                for (int t = 0; t < 9; ++t) xf[t] = Rt[t];
+                xf[9] = 0.0; xf[10] = 0.0; xf[11] = 0.0;
+            }
+        }
         double res = 0.0;
         for (int k = lane; k < K; k += 32) {
             const double x = W[3 * k], y = W[3 * k + 1], z = W[3 * k + 2];
@@ -391,16 +423,32 @@ __device__ double pair_value_warp(const PairPlan& pl, const double* __restrict__
         for (int b = 0; b < 3; ++b) s[a * 3 + b] = (s[a * 3 + b] - cp[a] * cq[b] * iw) * iw;
     const double lam = kabsch_rotation(s, U);
     const double msd = pqs * iw - 2.0 * lam;
+    if (XF) {
+        // rmsd.kabsch_weighted(Q, Pr, W) as used at io.py:733-741: x_ref ~ x_mov U + (c_ref - c_mov U), weighted centres
+        if (pl.final_kabsch) {
+            mat3_rmul(Rt, U);
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                Tt[c] = (cq[c] - fma(cp[0], U[c], fma(cp[1], U[3 + c], cp[2] * U[6 + c]))) * iw;
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int t = 0; t < 9; ++t) xf[t] = Rt[t];
+            xf[9] = Tt[0]; xf[10] = Tt[1]; xf[11] = Tt[2];
+        }
+    }
     return sqrt(fmax(msd, 0.0));
 }
 
 // pairs given by the condensed slab of rows [row_begin,row_end) (pairs_list == nullptr) or explicitly
+template <bool XF>
 __global__ void __launch_bounds__(PAIR_WARPS * 32) pair_kernel(const PairPlan pl, const double* __restrict__ centred, int M,
                                                                long long idx_base, long long n_entries,
                                                                const long long* __restrict__ pairs_list,
                                                                double* __restrict__ out, int* __restrict__ perms_out,
                                                                double* __restrict__ work, int* __restrict__ perm_work,
-                                                               int smem_per_warp, unsigned long long* counters) {
+                                                               int smem_per_warp, unsigned long long* counters,
+                                                               double* __restrict__ xf_out) {
     extern __shared__ __align__(16) unsigned char pair_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long gw = (long long)blockIdx.x * PAIR_WARPS + warp;
@@ -423,8 +471,8 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) pair_kernel(const PairPlan pl
             j = (int)(idx - condensed_row_base(M, r) + r + 1);
         }
         int steps;
-        const double val = pair_value_warp(pl, centred + (size_t)j * pl.K * 3, centred + (size_t)i * pl.K * 3, W, perm, sm,
-                                           lane, steps);
+        const double val = pair_value_warp<XF>(pl, centred + (size_t)j * pl.K * 3, centred + (size_t)i * pl.K * 3, W, perm, sm,
+                                               lane, steps, XF ? xf_out + (size_t)e * 12 : nullptr);
         my_steps += (unsigned long long)steps;
         if (lane == 0) out[e] = val;
         if (perms_out) {
@@ -465,6 +513,7 @@ int pair_plan_build(PairPlanHost** out, const int32_t* kept_z, int K, int natoms
     p.solute_phase = p.has_ns && p.do_reorder && !o->reorder_solvent_only;
     p.final_direct = p.has_ns && p.do_reorder && !o->final_kabsch;
     p.weighted = o->weight_solute != 0.0;
+    p.final_kabsch = o->final_kabsch != 0;
     if (p.weighted) {
         if (!p.has_ns || K == natoms) { delete h; err = "weight_solute needs solute_natoms and at least one solvent atom"; return CT_ERR_UNSUPPORTED; }
         p.w_solute = o->weight_solute / natoms;
@@ -522,13 +571,14 @@ void pair_plan_free(PairPlanHost* p) {
 
 static cudaError_t launch_pairs(PairPlanHost* h, const double* centred, int M, long long idx_base, long long n_entries,
                                 const long long* pairs_list, double* out, int* perms_out, unsigned long long* counters,
-                                int sm_count, cudaStream_t stream) {
+                                int sm_count, cudaStream_t stream, double* xf_out = nullptr) {
     if (n_entries <= 0) return cudaSuccess;
     const int smem = h->smem_per_warp * PAIR_WARPS;
-    cudaError_t e = cudaFuncSetAttribute(pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    auto kernel = xf_out ? pair_kernel<true> : pair_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pair_kernel, PAIR_WARPS * 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, PAIR_WARPS * 32, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     long long grid = (long long)sm_count * per_sm;
@@ -542,9 +592,9 @@ static cudaError_t launch_pairs(PairPlanHost* h, const double* centred, int M, l
         if ((e = cudaMalloc(&h->d_perm, sizeof(int) * warps * h->plan.K)) != cudaSuccess) return e;
         h->work_warps = warps;
     }
-    pair_kernel<<<(unsigned)grid, PAIR_WARPS * 32, smem, stream>>>(h->plan, centred, M, idx_base, n_entries, pairs_list, out,
-                                                                   perms_out, h->d_work, h->d_perm, h->smem_per_warp,
-                                                                   counters);
+    kernel<<<(unsigned)grid, PAIR_WARPS * 32, smem, stream>>>(h->plan, centred, M, idx_base, n_entries, pairs_list, out,
+                                                              perms_out, h->d_work, h->d_perm, h->smem_per_warp, counters,
+                                                              xf_out);
     return cudaGetLastError();
 }
 
@@ -560,10 +610,10 @@ cudaError_t launch_pairs_rows(const PairPlanHost* plan, const double* centred, i
 
 cudaError_t launch_pairs_list(const PairPlanHost* plan, const double* centred, int M, int K, const long long* pairs_dev,
                               long long n_pairs, double* values_dev, int* perms_dev, unsigned long long* counters,
-                              int sm_count, cudaStream_t stream) {
+                              int sm_count, cudaStream_t stream, double* xf_dev) {
     (void)K;
     return launch_pairs(const_cast<PairPlanHost*>(plan), centred, M, 0, n_pairs, pairs_dev, values_dev, perms_dev, counters,
-                        sm_count, stream);
+                        sm_count, stream, xf_dev);
 }
 
 }  // namespace ct

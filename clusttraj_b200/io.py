@@ -248,3 +248,113 @@ def parse_args(args: argparse.Namespace) -> ClustOptions:
         out_medoids_fmt=args.medoids_configurations or None, summary_name=base + ".out",
         solute_natoms=args.natoms_solute, weight_solute=args.weight_solute,
         reorder_excl=np.asarray([x - 1 for x in excl], np.int32), verbose=args.verbose)
+
+
+# ---- structure output (reference: clusttraj/io.py:582-1015) -------------------------------------
+# align_mol's arithmetic (centre, Kabsch rotations, Hungarian reorders, the optional final rotation) runs on the GPU
+# through ct_pair_transforms, which returns the rigid transform of every (medoid, member) pair; the host applies it
+# to ALL atoms of the member (hydrogens included, original atom order: what align_mol prints) and writes the files.
+
+def _frame_centres(atoms, coords, noh, nsatoms):
+    """Centre align_mol subtracts from every atom of a frame (io.py:624-647): centroid of the kept atoms, or of the
+    kept solute atoms with -ns."""
+    keep = atoms != 1 if noh else np.ones(len(atoms), bool)
+    if nsatoms:
+        keep = keep & (np.arange(len(atoms)) < nsatoms)
+    return coords[:, keep, :].mean(axis=1)
+
+
+def superposed_frames(trajfile, reference, members, noh, reorder, reorder_solvent_only, nsatoms, weight_solute,
+                      reorderexcl, final_kabsch):
+    """(atomic numbers [N], reference frame [N,3] centred as io.py:823-858 writes it, members [len(members), N, 3]
+    superposed on it as io.py:align_mol returns them)."""
+    from . import _engine
+    from .distmat import _engine_for, _load_trajectory, _opts_from, visible_devices
+
+    atoms, coords = _load_trajectory(trajfile)
+    opts = _opts_from(noh, reorder, reorder_solvent_only, nsatoms, weight_solute, reorderexcl, final_kabsch)
+    centres = _frame_centres(atoms, coords, bool(noh), nsatoms)
+    ref = coords[reference] - centres[reference]
+    members = [int(m) for m in members]
+    if not members:
+        return atoms, ref, np.empty((0,) + ref.shape)
+    eng = _engine_for(visible_devices()[0])
+    eng.load_frames(coords, atoms, opts)
+    _, R, T = eng.pair_transforms([(reference, m) for m in members])
+    moved = np.einsum("mnk,mkj->mnj", coords[members] - centres[members][:, None, :], R) + T[:, None, :]
+    return atoms, ref, moved
+
+
+def _xyz_titles(trajfile):
+    titles = []
+    with open(trajfile) as fh:
+        lines = fh.read().split("\n")
+    pos = 0
+    while pos < len(lines):
+        if not lines[pos].strip():
+            pos += 1
+            continue
+        n = int(lines[pos].split()[0])
+        titles.append(lines[pos + 1].rstrip() if pos + 1 < len(lines) else "")
+        pos += n + 2
+    return titles
+
+
+class _XyzWriter:
+    """Minimal stand-in for pybel.Outputfile("xyz", ...): refuses to overwrite unless asked (like OpenBabel's)."""
+
+    def __init__(self, path, overwrite):
+        if os.path.exists(path) and not overwrite:
+            raise IOError(f"{path} already exists. Use 'overwrite=True' to overwrite it.")
+        self.fh = open(path, "w")
+
+    def write(self, atoms, coords, title):
+        from .xyz import SYMBOLS
+
+        self.fh.write(f"{len(atoms)}\n{title}\n")
+        for z, (x, y, w) in zip(atoms, coords):
+            self.fh.write(f"{SYMBOLS[int(z)]:<3s}{x:15.5f}{y:15.5f}{w:15.5f}\n")
+
+    def close(self):
+        self.fh.close()
+
+
+def _writer(outfmt, path, overwrite):
+    if outfmt != "xyz":
+        raise NotImplementedError(f"structure output in .{outfmt} needs OpenBabel; clusttraj_b200 writes .xyz natively")
+    return _XyzWriter(path, overwrite)
+
+
+def save_clusters_config(trajfile, clusters, distmat, noh, reorder, reorder_solvent_only, nsatoms, weight_solute,
+                         outbasename, outfmt, reorderexcl, final_kabsch, overwrite):
+    """Save the superposed configurations of every cluster, medoid first (io.py:758-899): one file
+    ``<outbasename>_<cluster>.<outfmt>`` per cluster."""
+    from .classify import find_medoids_from_clusters
+
+    clusters = np.asarray(clusters)
+    medoids = find_medoids_from_clusters(distmat, clusters)      # io.py:810-816 recomputes them from a squareform
+    titles = _xyz_titles(trajfile) if trajfile.lower().endswith(".xyz") else None
+    for cnum in range(1, int(clusters.max()) + 1):
+        medoid = int(medoids[cnum - 1])
+        members = [int(i) for i in np.where(clusters == cnum)[0] if i != medoid]
+        atoms, ref, moved = superposed_frames(trajfile, medoid, members, noh, reorder, reorder_solvent_only, nsatoms,
+                                              weight_solute, reorderexcl, final_kabsch)
+        out = _writer(outfmt, f"{outbasename}_{cnum}.{outfmt}", overwrite)
+        out.write(atoms, ref, titles[medoid] if titles else "")
+        for m, xyz in zip(members, moved):
+            out.write(atoms, xyz, titles[m] if titles else "")
+        out.close()
+
+
+def save_medoids_config(trajfile, medoids, noh, reorder, reorder_solvent_only, nsatoms, weight_solute, outbasename,
+                        outfmt, reorderexcl, final_kabsch, overwrite):
+    """Save the medoids superposed on the first one to a single file (io.py:902-1015)."""
+    medoids = [int(m) for m in np.asarray(medoids)]
+    titles = _xyz_titles(trajfile) if trajfile.lower().endswith(".xyz") else None
+    atoms, ref, moved = superposed_frames(trajfile, medoids[0], medoids[1:], noh, reorder, reorder_solvent_only, nsatoms,
+                                          weight_solute, reorderexcl, final_kabsch)
+    out = _writer(outfmt, f"{outbasename}.{outfmt}", overwrite)
+    out.write(atoms, ref, titles[medoids[0]] if titles else "")
+    for m, xyz in zip(medoids[1:], moved):
+        out.write(atoms, xyz, titles[m] if titles else "")
+    out.close()

@@ -7,7 +7,7 @@ import numpy as np
 
 from .classify import find_medoids_from_clusters, sum_distmat
 from .distmat import get_distmat
-from .io import Logger, configure_runtime
+from .io import Logger, configure_runtime, save_clusters_config, save_medoids_config
 
 
 def classify(clust_opt, distmat):
@@ -36,6 +36,12 @@ def main(args=None):
                        f"({n / max(t2 - t1, 1e-12):.3e} pairs/s)\n")
     _, clusters = classify(clust_opt, distmat)
     Logger.logger.info(f"A total {len(clusters)} snapshots were read and {clusters.max()} cluster(s) was(were) found.\n")
+    # superposed structures per cluster / medoids (main.py:67-92,116-137): transforms from the GPU, .xyz written natively
+    if clust_opt.save_confs:
+        save_clusters_config(clust_opt.trajfile, clusters, distmat, clust_opt.no_hydrogen, clust_opt.reorder_alg,
+                             clust_opt.reorder_solvent_only, clust_opt.solute_natoms, clust_opt.weight_solute,
+                             clust_opt.out_conf_name, clust_opt.out_conf_fmt, clust_opt.reorder_excl, clust_opt.final_kabsch,
+                             clust_opt.overwrite)
     # the summary the reference writes (main.py:107-135): matrix sum, cluster sizes and medoids — both reductions
     # run on the GPU (clusttraj_b200/classify.py) instead of over a host-side squareform
     total = sum_distmat(distmat)
@@ -47,5 +53,10 @@ def main(args=None):
         fh.write("\nCluster\tSize\tMedoid\n")
         for c in range(1, int(clusters.max()) + 1):
             fh.write(f"{c}\t{int((clusters == c).sum())}\t{int(medoids[c - 1])}\n")
+    if clust_opt.save_medoids:
+        save_medoids_config(clust_opt.trajfile, medoids, clust_opt.no_hydrogen, clust_opt.reorder_alg,
+                            clust_opt.reorder_solvent_only, clust_opt.solute_natoms, clust_opt.weight_solute,
+                            clust_opt.out_medoids_name, clust_opt.out_medoids_fmt, clust_opt.reorder_excl,
+                            clust_opt.final_kabsch, clust_opt.overwrite)
     Logger.logger.info(f"Total wall time: {time.monotonic() - t0:.6f} s\n")
     return 0

@@ -109,6 +109,19 @@ int ct_rmsd_condensed(ct_engine* e, const double* coords, const int32_t* atomic_
 int ct_pair_values(ct_engine* e, const int64_t* pairs, int64_t n_pairs, double* values, int32_t* perms /* [n_pairs][K] or NULL */,
                    ct_stats* stats);
 
+/* Superposition transforms for structure output: what clusttraj/io.py:align_mol (582-756) applies to
+ * ALL atoms of a frame when save_clusters_config / save_medoids_config (io.py:758-1015) write the members of a cluster
+ * superposed on its medoid.  pairs = [n_pairs][2] (reference frame, moving frame), in either order of index; for each:
+ * values[t] = the pair's RMSD as the matrix holds it, transforms[t] = 12 doubles R (3x3 row-major) and T such that
+ *   aligned = (raw_moving - centre_moving) R + T        (row vectors; centre = the centroid ct_load_frames subtracts:
+ *                                                        all kept atoms, or the kept solute atoms with -ns)
+ * R is the product of the rotations of the per-pair pipeline (solute / whole-system Kabsch, second solute Kabsch after the
+ * solute reorder) and of the final rotation where align_mol applies one (-ns -e --final-kabsch: io.py:743-746;
+ * -ws --final-kabsch: the weighted Kabsch with its translation, io.py:733-741).  Runs the per-pair kernel whatever the
+ * mode (the frames must have been loaded with the same options as the matrix). */
+int ct_pair_transforms(ct_engine* e, const int64_t* pairs, int64_t n_pairs, double* values, double* transforms /* [n_pairs][12] */,
+                       ct_stats* stats);
+
 /* Consumers of the condensed matrix at scale, replacing clusttraj/classify.py:146-177 without
  * the M x M squareform the reference builds on the host:
  *   *total      = sum_distmat(distmat)                                   (classify.py:168-177)

@@ -184,9 +184,51 @@ def make_consumers_golden():
     print("wrote", os.path.join(GOLDEN, "reference_consumers.json"), {k: v["medoids"] for k, v in cases.items()})
 
 
+
+
+# name -> (noh, reorder?, reorder_solvent_only, nsatoms, weight_solute, excl(0-based), final_kabsch) for align_mol
+ALIGN_MODES_TESTTRAJ = {k: MODES_TESTTRAJ[k] for k in ("plain", "noh", "ns17", "noh_ns17", "e", "ns17_e", "ns17_e_rs", "ns17_e_noh",
+                                                       "ns17_e_fk", "ns17_e_ws08_fk", "ns17_e_ws08", "ns17_e_excl1920")}
+ALIGN_MODES_SOLV = {k: MODES_SOLV[k] for k in ("plain", "ns12_e", "ns12_e_rs", "ns12_e_noh", "ns12_e_fk", "ns12_e_excl")}
+
+
+def make_align_golden():
+    """tests/golden/reference_align.json: the UNMODIFIED clusttraj.io.align_mol (io.py:582-756) superposing every
+    later frame of the fixtures on frame 0 prepared as save_clusters_config prepares a medoid (io.py:823-856)."""
+    _, shim_rmsd = _import_reference()
+    import clusttraj.io as ref_io
+    from openbabel import pybel
+    from oracle import io_restated as IO
+
+    assert ref_io.__file__.startswith(REFERENCE), ref_io.__file__
+    out = {}
+    for ds, fname, modes in (("testtraj", "ref_testtraj.xyz", ALIGN_MODES_TESTTRAJ), ("synth_solv", "synth_solv_6x36.xyz", ALIGN_MODES_SOLV)):
+        traj = os.path.join(GOLDEN, fname)
+        mols = list(pybel.readfile("xyz", traj))
+        out[ds] = {"trajfile": fname, "modes": {}}
+        for name, mode in modes.items():
+            noh, do_reorder, rs, ns, ws, excl, fk = mode
+            reorder = shim_rmsd.reorder_hungarian if do_reorder else None
+            q_atoms = np.array([a.atomicnum for a in mols[0]])
+            q_all = np.array([a.coords for a in mols[0]])
+            Q, Qa, _ = IO.reference_frame(q_atoms, q_all, noh, ns)   # verbatim io.py:823-856 (no function of its own in the reference)
+            frames = []
+            for mol in mols[1:]:
+                text = ref_io.align_mol(mol, Q, Qa, noh, reorder, rs, ns, ws, np.asarray(excl, np.int32), fk)
+                rows = text.strip().split("\n")[2:]
+                frames.append([[float(v).hex() for v in r.split("\t")[1:4]] for r in rows])
+            out[ds]["modes"][name] = {"args": mode, "aligned_hex": frames}
+    with open(os.path.join(GOLDEN, "reference_align.json"), "w") as fh:
+        json.dump(out, fh, indent=0)
+    print("wrote", os.path.join(GOLDEN, "reference_align.json"))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "consumers":
         make_consumers_golden()
+    elif len(sys.argv) > 1 and sys.argv[1] == "align":
+        make_align_golden()
     else:
         main()
         make_consumers_golden()
+        make_align_golden()

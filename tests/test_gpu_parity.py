@@ -654,3 +654,71 @@ def test_degenerate_geometries_on_both_gram_kernels(kind):
         tol = max(1e-9 * max(scale, 1.0), 2.0 * st["quant_step"]) if kind != "tiny_scale" else 1e-12
         assert np.abs(got - want).max() <= tol, (kind, variant, np.abs(got - want).max(), tol, st["flagged"])
         e.close()
+
+
+# ---- structure output (clusttraj/io.py:582-1015): transforms from the per-pair kernel --------------------------------
+
+def _align_cases(golden_dir):
+    import json
+
+    with open(os.path.join(golden_dir, "reference_align.json")) as fh:
+        data = json.load(fh)
+    for ds in data.values():
+        for mode in ds["modes"].values():
+            mode["aligned"] = np.array([[[float.fromhex(h) for h in row] for row in fr] for fr in mode["aligned_hex"]])
+    return data
+
+
+def test_superposed_frames_against_unmodified_align_mol(golden_dir):
+    """Every later frame of the fixtures superposed on frame 0, in every mode align_mol distinguishes, against what the
+    unmodified clusttraj.io.align_mol printed (tests/golden/reference_align.json)."""
+    from clusttraj_b200.io import superposed_frames
+    from clusttraj_b200.reorder import reorder_hungarian
+
+    worst = 0.0
+    for ds in _align_cases(golden_dir).values():
+        traj = os.path.join(golden_dir, ds["trajfile"])
+        for name, mode in ds["modes"].items():
+            noh, do_reorder, rs, ns, ws, excl, fk = mode["args"]
+            n = len(mode["aligned"])
+            atoms, ref, moved = superposed_frames(traj, 0, range(1, n + 1), noh, reorder_hungarian if do_reorder else None,
+                                                  rs, ns, ws, np.asarray(excl, np.int32), fk)
+            err = np.abs(moved - mode["aligned"]).max()
+            worst = max(worst, err)
+            assert err <= 1e-9, (name, err)
+    print(f"superposed structures: worst |dx| = {worst:.2e} A")
+
+
+def test_save_clusters_and_medoids_config(golden_dir, tmp_path):
+    """The two writers on a clustered synthetic trajectory: medoid first, members in trajectory order, every member
+    closer to its medoid after superposition than the matrix says (same RMSD for the plain mode), no overwrite."""
+    from clusttraj_b200 import xyz
+    from clusttraj_b200.classify import find_medoids_from_clusters
+    from clusttraj_b200.io import save_clusters_config, save_medoids_config
+    from clusttraj_b200.synth import make_trajectory
+    import scipy.cluster.hierarchy as hcl
+
+    atoms, coords = make_trajectory(40, 18, seed=12, n_modes=3, n_duplicates=0, mirrored=False)
+    traj = str(tmp_path / "t.xyz")
+    xyz.write_xyz(traj, atoms, coords)
+    e = _engine_with(None)
+    d, _ = _full(e, atoms, xyz.read_xyz(traj)[1])
+    e.close()
+    clusters = hcl.fcluster(hcl.linkage(d, "average"), 3, criterion="maxclust")
+    base = str(tmp_path / "confs")
+    save_clusters_config(traj, clusters, d, False, None, False, None, None, base, "xyz", np.asarray([], np.int32), False, False)
+    medoids = find_medoids_from_clusters(d, clusters)
+    for c in range(1, 4):
+        a, x = xyz.read_xyz(f"{base}_{c}.xyz")
+        members = [int(i) for i in np.where(clusters == c)[0] if i != medoids[c - 1]]
+        assert len(x) == 1 + len(members) and (a == atoms).all()
+        assert np.abs(x[0].mean(axis=0)).max() < 1e-5          # the medoid is written centred
+        for k, m in enumerate(members):
+            i, j = sorted((int(medoids[c - 1]), m))
+            direct = np.sqrt(((x[1 + k] - x[0]) ** 2).sum() / len(atoms))
+            assert abs(direct - d[condensed_index(40, i, j)]) < 2e-5   # 5 decimals in the file
+    with pytest.raises(IOError):
+        save_clusters_config(traj, clusters, d, False, None, False, None, None, base, "xyz", np.asarray([], np.int32), False, False)
+    save_medoids_config(traj, medoids, False, None, False, None, None, str(tmp_path / "med"), "xyz", np.asarray([], np.int32), False, True)
+    a, x = xyz.read_xyz(str(tmp_path / "med.xyz"))
+    assert len(x) == 3

@@ -227,3 +227,30 @@ def test_native_readers_xyz_fast_path_pdb_gro(tmp_path, golden_dir):
             fh.write("   5.00000   5.00000   5.00000\n")
     ag, cg = xyz.read_trajectory(gro)
     assert (ag == a_fast).all() and np.abs(cg - x).max() < 1e-3 + 1e-9   # .gro keeps 3-4 decimals of nm
+
+
+def test_structure_output_host_side(tmp_path, golden_dir):
+    """Host pieces of the structure writers (io.py:582-1015 mirror): the per-frame centre equals the one the oracle's
+    restatement of io.py:823-856 subtracts, the .xyz writer refuses to overwrite, other formats are refused loudly."""
+    from clusttraj_b200 import io as bio
+    from clusttraj_b200.xyz import read_xyz
+    from oracle import io_restated as IO
+
+    atoms, coords = read_xyz(os.path.join(golden_dir, "ref_testtraj.xyz"))
+    for noh, ns in ((False, None), (True, None), (False, 17), (True, 17)):
+        c = bio._frame_centres(atoms[0], coords, noh, ns)
+        for k in range(len(coords)):
+            _, _, centred = IO.reference_frame(atoms[k], coords[k], noh, ns)
+            assert np.abs((coords[k] - c[k]) - centred).max() < 1e-12
+    path = str(tmp_path / "o.xyz")
+    w = bio._XyzWriter(path, overwrite=False)
+    w.write(atoms[0], coords[0], "frame 0")
+    w.close()
+    a, x = read_xyz(path)
+    assert (a == atoms[0]).all() and np.abs(x[0] - coords[0]).max() < 1e-5
+    with pytest.raises(IOError):
+        bio._XyzWriter(path, overwrite=False)
+    bio._XyzWriter(path, overwrite=True).close()
+    with pytest.raises(NotImplementedError):
+        bio._writer("pdb", str(tmp_path / "o.pdb"), True)
+    assert bio._xyz_titles(os.path.join(golden_dir, "ref_testtraj.xyz")).__len__() == 3

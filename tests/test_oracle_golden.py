@@ -95,3 +95,34 @@ def test_consumers_oracle_matches_unmodified_reference(golden_dir):
     for name, d, clusters, medoids, total in cases:
         assert (C.find_medoids_from_clusters(d, clusters) == medoids).all(), name
         assert C.sum_distmat(d) == total, name
+
+
+# ---- structure output: align_mol (clusttraj/io.py:582-756) --------------------------------------------------------------
+
+def _align_cases(golden_dir):
+    import json
+
+    with open(os.path.join(golden_dir, "reference_align.json")) as fh:
+        data = json.load(fh)
+    for ds in data.values():
+        for mode in ds["modes"].values():
+            mode["aligned"] = np.array([[[float.fromhex(h) for h in row] for row in fr] for fr in mode["aligned_hex"]])
+    return data
+
+
+def test_align_oracle_matches_unmodified_reference(golden_dir):
+    """oracle/io_restated.align_coords against the coordinates the unmodified align_mol printed (oracle/make_golden.py)."""
+    from oracle import io_restated as IO
+
+    n = 0
+    for ds in _align_cases(golden_dir).values():
+        atoms, coords = read_xyz(os.path.join(golden_dir, ds["trajfile"]))
+        for name, mode in ds["modes"].items():
+            noh, do_reorder, rs, ns, ws, excl, fk = mode["args"]
+            reorder = R.reorder_hungarian if do_reorder else None
+            Q, Qa, _ = IO.reference_frame(atoms[0], coords[0], noh, ns)
+            for k in range(1, len(coords)):
+                got = IO.align_coords(atoms[k], coords[k], Q, Qa, noh, reorder, rs, ns, ws, np.asarray(excl, np.int32), fk)
+                assert np.abs(got - mode["aligned"][k - 1]).max() <= 1e-12, (name, k)
+                n += 1
+    assert n >= 40
