@@ -307,16 +307,17 @@ def run_b200_arm(args, rank, world, local_rank):
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
                 os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"bf16_tflops": 1590.0}
             chunks = (K + 31) // 32
-            fj = 32 if (chunks <= 4 or chunks > 10) else 16   # column-tile frames of the kernel variant (csrc/ozaki.cu)
+            fj = 32 if chunks <= 4 else (16 if chunks <= 10 else 26)   # column-tile frames of the kernel variant (csrc/ozaki.cu)
+            n_mma = 80 if chunks > 10 else 3 * fj
             ntj = (M + fj - 1) // fj
             last = min(r1, M - 1)
             blocks = sum(ntj - (40 * ti + 1) // fj for ti in range(r0 // 40, (last + 39) // 40))
-            i8_ops = blocks * 15 * chunks * 2.0 * 128 * (3 * fj) * 32
+            i8_ops = blocks * 15 * chunks * 2.0 * 128 * n_mma * 32
             i8_tops = i8_ops / (mean_gram_ms * 1e-3) / 1e12
             i8_peak = 2.0 * float(peaks["bf16_tflops"])
             roofline.update(
                 kernel="gram_i8_ts_kernel<4>" if chunks <= 4 else ("gram_i8_ts_kernel<2>" if chunks <= 10 else "gram_i8_kernel"),
-                tensor_pipe={"kind": f"int8 tcgen05.mma (SASS UTCIMMA), M128 N{3 * fj} K32", "issued_tops": i8_tops,
+                tensor_pipe={"kind": f"int8 tcgen05.mma (SASS UTCIMMA), M128 N{n_mma} K32", "issued_tops": i8_tops,
                              "peak_tops": i8_peak, "frac": i8_tops / i8_peak,
                              "peak_source": "2 x the measured dense bf16 rate of MEASURED_PEAKS.json (int8 runs at twice "
                                             "the bf16 rate; no int8 figure is measured on this pool)"},

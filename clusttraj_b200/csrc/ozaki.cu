@@ -24,11 +24,13 @@
 // Three kernels (launch_gram_i8 picks by the padded atom count kp):
 //   gram_i8_ts_kernel<4>  kp <= 128: A tile resident in TMEM (".ts" MMA), B streams, N = 96, 16 epilogue warps;
 //   gram_i8_ts_kernel<2>  kp <= 320: the same with N = 48 (A takes 320 of the 512 TMEM columns), 8 epilogue warps;
-//   gram_i8_kernel        larger kp: A and B both through shared memory in K-blocks of 128 atoms, 8 epilogue warps
-//                         that transpose with shuffles (shared memory is full); slower (shared-memory bound MMAs).
+//   gram_i8_kernel        larger kp: A and B both stream through shared memory in K-blocks of 128 atoms; N = 80 so that ALL
+//                         six level accumulators (480 TMEM columns) stay resident over the K-blocks of a block and are
+//                         converted once; 8 epilogue warps that transpose with shuffles (shared memory is full).  Bound
+//                         by the L2 -> shared-memory operand traffic (104 KB per K-block and SM).
 // Roles in every kernel: warp 0 = bulk-copy producer (one lane), warp 1 = MMA issuer (one elected lane), warp 2 =
-// TMEM allocator, warps 4.. = epilogue.  TMEM: two buffers of 2 levels x N columns; the MMA warp fills one "level pair"
-// while the epilogue drains the other.
+// TMEM allocator, warps 4.. = epilogue.  TMEM (ts kernels): two buffers of 2 levels x N columns; the MMA warp fills one
+// "level pair" while the epilogue drains the other.
 #include "common.cuh"
 #include "solve3x3.cuh"
 
@@ -37,8 +39,8 @@
 namespace ct {
 
 constexpr int OZ_FI = 40;                    // frames per A (row) tile
-constexpr int OZ_FJ = 32;                    // frames per B (column) tile
-constexpr int OZ_M = 128, OZ_N = 96;         // MMA tile
+constexpr int OZ_FJ = 26;                    // frames per B (column) tile of gram_i8_kernel: 78 rows + 2 zero rows
+constexpr int OZ_M = 128, OZ_N = 80;         // MMA tile of gram_i8_kernel (six levels x 80 columns = 480 TMEM columns)
 constexpr int OZ_KB = 128;                   // atoms per K-block (= bytes per operand row per slice per stage)
 constexpr int OZ_SLICES = 4;
 constexpr int OZ_A_SLICE = OZ_M * OZ_KB;     // 16 KiB
@@ -182,9 +184,9 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) gram_i8_kernel(const OzParams p
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OZ_STAGES * OZ_STAGE_BYTES);
     uint64_t* full = bars;            // [2] stage loaded (tx bytes)
     uint64_t* empty = bars + 2;       // [2] stage consumed (tcgen05.commit)
-    uint64_t* tfull = bars + 4;       // [2] TMEM level pair complete (tcgen05.commit)
-    uint64_t* tempty = bars + 6;      // [2] TMEM level pair drained (8 epilogue warps)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t* tfull = bars + 4;       // [3] level pair complete over ALL K-blocks of the block (tcgen05.commit)
+    uint64_t* tempty = bars + 7;      // [3] level pair drained (8 epilogue warps)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int ti_begin = p.row_begin / OZ_FI;
@@ -194,10 +196,9 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) gram_i8_kernel(const OzParams p
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&full[s], 1); mbar_init(&empty[s], 1);
-            mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8);
-        }
+        for (int s = 0; s < 2; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+#pragma unroll
+        for (int s = 0; s < OZ_NPAIR; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, OZ_TMEM_COLS);
@@ -237,129 +238,127 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) gram_i8_kernel(const OzParams p
             }
         } else if (warp == 1) {
             // ---- MMA issuer ------------------------------------------------------------------------------------
+            // All six level accumulators of a block stay in TMEM while its K-blocks stream through shared memory: the
+            // int32 sums run over the whole contraction (|.| < 4 * 2^14 * K, no overflow below 32k atoms) and the
+            // epilogue converts each level pair ONCE per block instead of once per K-block.
             int stage = 0; uint32_t phase = 0;
-            int tb = 0; uint32_t tphase = 0;
-            const long long n_stage = blk_count * p.nkb;
-            for (long long it = 0; it < n_stage; ++it) {
-                const int kb = (int)(it % p.nkb);
-                const int nch = (kb == p.nkb - 1) ? p.last_chunks : 4;
-                mbar_wait(&full[stage], phase);
-                tc_fence_after();
-                const uint32_t aBase = smem_u32(smem + stage * OZ_STAGE_BYTES);
-                const uint32_t bBase = aBase + OZ_A_BYTES;
-                // descriptor words: only the 14-bit address field changes from one MMA to the next
-                constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);                 // SBO = 128 B, version 1
-                const uint32_t a_lo = ((uint32_t)(OZ_M * 16 >> 4) << 16) | (aBase >> 4);  // LBO = one K half of all rows
-                const uint32_t b_lo = ((uint32_t)(OZ_N * 16 >> 4) << 16) | (bBase >> 4);
-#pragma unroll
-                for (int pr = 0; pr < OZ_NPAIR; ++pr) {
-                    mbar_wait(&tempty[tb], tphase ^ 1);
+            constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);                 // SBO = 128 B, version 1
+            for (long long blk = 0; blk < blk_count; ++blk) {
+                for (int kb = 0; kb < p.nkb; ++kb) {
+                    const int nch = (kb == p.nkb - 1) ? p.last_chunks : 4;
+                    mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const bool leader = elect_one();
-                    if (leader) {
+                    const uint32_t aBase = smem_u32(smem + stage * OZ_STAGE_BYTES);
+                    const uint32_t bBase = aBase + OZ_A_BYTES;
+                    // descriptor words: only the 14-bit address field changes from one MMA to the next
+                    const uint32_t a_lo = ((uint32_t)(OZ_M * 16 >> 4) << 16) | (aBase >> 4);  // LBO = one K half of all rows
+                    const uint32_t b_lo = ((uint32_t)(OZ_N * 16 >> 4) << 16) | (bBase >> 4);
 #pragma unroll
-                        for (int lv = 0; lv < 2; ++lv) {
-                            const int q = 2 * ((pr + 1) % OZ_NPAIR) + lv;   // level pairs in the order (2,3), (4,5), (0,1)
-                            const uint32_t d = tmem_base + (uint32_t)(tb * 2 * OZ_N + lv * OZ_N);
-                            const int s_lo = q > 3 ? q - 3 : 0, s_hi = q < 3 ? q : 3;
+                    for (int pr = 0; pr < OZ_NPAIR; ++pr) {
+                        if (kb == 0) {   // the epilogue must have drained this pair of the previous block
+                            mbar_wait(&tempty[pr], (uint32_t)(blk & 1) ^ 1u);
+                            tc_fence_after();
+                        }
+                        const bool leader = elect_one();
+                        if (leader) {
 #pragma unroll
-                            for (int s = s_lo; s <= s_hi; ++s) {
+                            for (int lv = 0; lv < 2; ++lv) {
+                                const int q = 2 * ((pr + 1) % OZ_NPAIR) + lv;   // level pairs in the order (2,3), (4,5), (0,1)
+                                const uint32_t d = tmem_base + (uint32_t)(pr * 2 * OZ_N + lv * OZ_N);
+                                const int s_lo = q > 3 ? q - 3 : 0, s_hi = q < 3 ? q : 3;
 #pragma unroll
-                                for (int kc = 0; kc < 4; ++kc) {
-                                    if (kc < nch) {
-                                        // one MMA = 32 atoms = two 16-byte K halves of (rows / 8) core matrices each
-                                        const uint64_t ad = ((uint64_t)DESC_HI << 32) |
-                                                            (a_lo + (uint32_t)((s * OZ_A_SLICE + kc * 2 * OZ_M * 16) >> 4));
-                                        const uint64_t bd = ((uint64_t)DESC_HI << 32) |
-                                                            (b_lo + (uint32_t)(((q - s) * OZ_B_SLICE + kc * 2 * OZ_N * 16) >> 4));
-                                        umma_i8(d, ad, bd, OZ_IDESC, (s > s_lo || kc > 0) ? 1u : 0u);
+                                for (int s = s_lo; s <= s_hi; ++s) {
+#pragma unroll
+                                    for (int kc = 0; kc < 4; ++kc) {
+                                        if (kc < nch) {
+                                            // one MMA = 32 atoms = two 16-byte K halves of (rows / 8) core matrices each
+                                            const uint64_t ad = ((uint64_t)DESC_HI << 32) |
+                                                                (a_lo + (uint32_t)((s * OZ_A_SLICE + kc * 2 * OZ_M * 16) >> 4));
+                                            const uint64_t bd = ((uint64_t)DESC_HI << 32) |
+                                                                (b_lo + (uint32_t)(((q - s) * OZ_B_SLICE + kc * 2 * OZ_N * 16) >> 4));
+                                            umma_i8(d, ad, bd, OZ_IDESC, (kb > 0 || s > s_lo || kc > 0) ? 1u : 0u);
+                                        }
                                     }
                                 }
                             }
+                            if (kb == p.nkb - 1) umma_commit(&tfull[pr]);
                         }
+                        __syncwarp();
                     }
-                    if (leader) umma_commit(&tfull[tb]);
+                    if (elect_one()) umma_commit(&empty[stage]);
                     __syncwarp();
-                    tb ^= 1; if (tb == 0) tphase ^= 1;
+                    stage ^= 1; if (stage == 0) phase ^= 1;
                 }
-                if (elect_one()) umma_commit(&empty[stage]);
-                __syncwarp();
-                stage ^= 1; if (stage == 0) phase ^= 1;
             }
         }
     } else {
         // ---- epilogue warps ------------------------------------------------------------------------------------
         asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
         const int quarter = warp & 3;            // TMEM lanes 32 * quarter .. + 31
-        const int half = (warp - 4) >> 2;        // accumulator columns 48 * half .. + 47 = frames 16 * half .. + 15
+        const int half = (warp - 4) >> 2;        // accumulator columns 39 * half .. + 38 = column frames 13 * half .. + 12
         const int g = lane / 3, a = lane - 3 * g;
         const bool row_ok = lane < 30;
         const int src1 = (lane - a + (a + 1) % 3) & 31, src2 = (lane - a + (a + 2) % 3) & 31;
         const int u1 = (a + 2) % 3, u2 = (a + 1) % 3;   // which of the three pairs this lane SENDS in shuffle 1 / 2
-        const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 48);
+        const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 39);
         const double s2 = p.qinfo[0];
         const double sc[OZ_NPAIR] = {s2 * 16777216.0, s2 * 256.0, s2 * 1099511627776.0};   // 2^24, 2^8, 2^40 (issue order)
         const int last_row = min(p.row_end, p.M - 1);
         OzWalker w;
         w.init(ti_begin, ntj, blk_start, blk_count);
-        int tb = 0; uint32_t tphase = 0;
+        uint32_t tphase = 0;
         for (; w.valid(); w.next()) {
-            double acc[48];
+            double acc[39];
 #pragma unroll
-            for (int n = 0; n < 48; ++n) acc[n] = 0.0;
-            for (int kb = 0; kb < p.nkb; ++kb) {
+            for (int pr = 0; pr < OZ_NPAIR; ++pr) {
+                mbar_wait(&tfull[pr], tphase);
+                tc_fence_after();
+                const uint32_t t0 = tlane + (uint32_t)(pr * 2 * OZ_N);
+                // 39 columns of this half as 16 + 16 + 8 (the 40th belongs to the neighbour half / the padding)
+                uint32_t e0[16], e1[16], e2[8], o0[16], o1[16], o2[8];
+                tmem_ld16(t0, e0); tmem_ld16(t0 + 16, e1); tmem_ld8(t0 + 32, e2);
+                tmem_ld16(t0 + OZ_N, o0); tmem_ld16(t0 + OZ_N + 16, o1); tmem_ld8(t0 + OZ_N + 32, o2);
+                tmem_wait_ld();
 #pragma unroll
-                for (int pr = 0; pr < OZ_NPAIR; ++pr) {
-                    mbar_wait(&tfull[tb], tphase);
-                    tc_fence_after();
-                    const uint32_t t0 = tlane + (uint32_t)(tb * 2 * OZ_N);
-                    {
-                        uint32_t ev[2][16], od[2][16];
-                        tmem_ld16(t0, ev[0]);
-                        tmem_ld16(t0 + OZ_N, od[0]);
-                        tmem_wait_ld();
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            if (c + 1 < 3) {  // the next 16 columns travel while these are converted
-                                tmem_ld16(t0 + (c + 1) * 16, ev[(c + 1) & 1]);
-                                tmem_ld16(t0 + OZ_N + (c + 1) * 16, od[(c + 1) & 1]);
-                            }
-#pragma unroll
-                            for (int n = 0; n < 16; ++n)
-                                acc[c * 16 + n] = fma(level_pair((int)ev[c & 1][n], (int)od[c & 1][n]), sc[pr], acc[c * 16 + n]);
-                            if (c + 1 < 3) tmem_wait_ld();
-                        }
-                    }
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty[tb]);
-                    tb ^= 1; if (tb == 0) tphase ^= 1;
+                for (int n = 0; n < 16; ++n) {
+                    const double v0 = level_pair((int)e0[n], (int)o0[n]) * sc[pr], v1 = level_pair((int)e1[n], (int)o1[n]) * sc[pr];
+                    acc[n] = pr == 0 ? v0 : acc[n] + v0;
+                    acc[16 + n] = pr == 0 ? v1 : acc[16 + n] + v1;
                 }
+#pragma unroll
+                for (int n = 0; n < 7; ++n) {
+                    const double v2 = level_pair((int)e2[n], (int)o2[n]) * sc[pr];
+                    acc[32 + n] = pr == 0 ? v2 : acc[32 + n] + v2;
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[pr]);
             }
-            // ---- 3x3 solve: lanes 3g, 3g+1, 3g+2 hold the three rows of the covariances of frame i with 16 frames j;
+            tphase ^= 1;
+            // ---- 3x3 solve: lanes 3g, 3g+1, 3g+2 hold the three rows of the covariances of frame i with 13 frames j;
             // lane a takes the pairs jj = 3m + a and collects the two other rows with shuffles.  The rows arrive in
             // cyclic order (a, a+1, a+2), which leaves |S|^2, |cof S|^2 and det S unchanged.
             const int i = w.ti * OZ_FI + quarter * 10 + g;
-            const int j0 = w.tj * OZ_FJ + half * 16;
+            const int j0 = w.tj * OZ_FJ + half * 13;
             const double gi = p.Gq[i];
             const bool row_mine = row_ok && i >= p.row_begin && i < last_row;
             const long long row_off = condensed_row_base(p.M, i) - p.idx_base - i - 1;
-            double qa[6], qb[6], qd[6], hg[6], lam[6];
+            double qa[5], qb[5], qd[5], hg[5], lam[5];
 #pragma unroll
-            for (int m = 0; m < 6; ++m) {
+            for (int m = 0; m < 5; ++m) {
                 double s9[9];
 #pragma unroll
                 for (int b = 0; b < 3; ++b) {
                     const double r0 = acc[9 * m + b];
-                    const double r1 = (9 * m + 3 + b < 48) ? acc[(9 * m + 3 + b) % 48] : 0.0;
-                    const double r2 = (9 * m + 6 + b < 48) ? acc[(9 * m + 6 + b) % 48] : 0.0;
+                    const double r1 = (9 * m + 3 + b < 39) ? acc[(9 * m + 3 + b) % 39] : 0.0;
+                    const double r2 = (9 * m + 6 + b < 39) ? acc[(9 * m + 6 + b) % 39] : 0.0;
                     s9[b] = sel3(a, r0, r1, r2);
                     s9[3 + b] = __shfl_sync(0xffffffffu, sel3(u1, r0, r1, r2), src1);
                     s9[6 + b] = __shfl_sync(0xffffffffu, sel3(u2, r0, r1, r2), src2);
                 }
                 const int jj = 3 * m + a;
                 const int j = j0 + jj;
-                const bool live = row_ok && jj < 16 && j < p.M;
+                const bool live = row_ok && jj < 13 && j < p.M;
                 if (!live) {
                     // idle lanes / padding: a well-conditioned stand-in (identity) so that no lane drags its warp
                     // through the solver's slow path; the result is never stored
@@ -369,9 +368,9 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) gram_i8_kernel(const OzParams p
                 quartic_invariants(s9, qa[m], qb[m], qd[m]);
                 hg[m] = live ? gi + p.Gq[j] : 3.0;  // half sums: G_i = G_j = 3 for the identity stand-in
             }
-            const unsigned okmask = largest_root_f64<6>(qa, qb, qd, hg, lam);
+            const unsigned okmask = largest_root_f64<5>(qa, qb, qd, hg, lam);
 #pragma unroll
-            for (int m = 0; m < 6; ++m) {
+            for (int m = 0; m < 5; ++m) {
                 const int jj = 3 * m + a;
                 const int j = j0 + jj;
                 const double eh = hg[m] - lam[m];
@@ -380,7 +379,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) gram_i8_kernel(const OzParams p
                 double r = v * y;
                 r = fma(fma(-r, r, v), 0.5 * y, r);
                 const bool ok = (okmask >> m) & 1u;
-                const bool mine = row_mine && jj < 16 && i < j && j < p.M;
+                const bool mine = row_mine && jj < 13 && i < j && j < p.M;
                 if ((!ok || eh < p.flag_rel * hg[m]) && mine) {
                     const unsigned int t = atomicAdd(p.fix.count, 1u);
                     if (t < p.fix.capacity) p.fix.pairs[t] = make_int2(i, j);
@@ -811,6 +810,7 @@ __global__ void __launch_bounds__(256) quant_pack_kernel(const double* __restric
             const int nkb = groups >> 3, kb = g16 >> 3, kc16 = g16 & 7;
             uint8_t* da = packA + ((size_t)ti * nkb + kb) * OZ_A_BYTES + (size_t)kc16 * (OZ_M * 16) + (rowA >> 3) * 128 + (rowA & 7) * 16;
             uint8_t* db = packB + ((size_t)tj * nkb + kb) * OZ_B_BYTES + (size_t)kc16 * (OZ_N * 16) + (rowB >> 3) * 128 + (rowB & 7) * 16;
+            static_assert(3 * OZ_FJ <= OZ_N && OZ_N % 16 == 0, "column tile: 3 rows per frame, MMA N a multiple of 16");
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
                 *reinterpret_cast<uint4*>(da + s * OZ_A_SLICE) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
