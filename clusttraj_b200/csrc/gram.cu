@@ -122,7 +122,7 @@ __device__ __forceinline__ void epilogue_store(const double (&acc)[Cfg::MA][Cfg:
                     if (t < p.fix.capacity) p.fix.pairs[t] = make_int2(i, j);
                     else r = -1.0;  // list full: mark the entry, the fix-up kernel scans for it
                 }
-                if (mine) p.out[condensed_row_base(p.M, i) - p.idx_base + (j - i - 1)] = r;
+                if (mine) __stcs(p.out + (condensed_row_base(p.M, i) - p.idx_base + (j - i - 1)), r);   // streaming store
             }
         }
     }

@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) gram_i8_kernel(const OzParams p
                     if (t < p.fix.capacity) p.fix.pairs[t] = make_int2(i, j);
                     else r = -1.0;
                 }
-                if (mine) p.out[row_off + j] = r;
+                if (mine) __stcs(p.out + row_off + j, r);   // streaming store: the 8 B/pair output must not evict the operand tiles from L2
             }
         }
     }
@@ -696,7 +696,7 @@ __global__ void __launch_bounds__(TsCfg<NWG>::THREADS, 1) gram_i8_ts_kernel(cons
                     if (t < p.fix.capacity) p.fix.pairs[t] = make_int2(i, j);
                     else rm = -1.0;
                 }
-                if (mine) out_row[r][j] = rm;
+                if (mine) __stcs(out_row[r] + j, rm);   // streaming store: the output must not evict the operand tiles from L2
             }
         }
     }
