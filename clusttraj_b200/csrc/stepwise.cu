@@ -64,16 +64,55 @@ __device__ __forceinline__ double cost_sqrt(double d2) {
     return s;
 }
 
+// squared distance in one fixed operation order: the nearest-column pass and the frontier scans must see the same bits
+__device__ __forceinline__ double dist2(double dx, double dy, double dz) { return fma(dx, dx, fma(dy, dy, dz * dz)); }
+
 // ---- warp-parallel shortest augmenting path, column state in registers --------------------------------
 // For blocks of up to 32*C atoms.  Lane l owns columns l, l+32, ...: their coordinates, dual v and
 // tentative path cost stay in registers for the whole solve, so a frontier scan is C independent
 // distance evaluations per lane (ILP) + one warp argmin.  Row duals, predecessors and the matching live
 // in shared memory (touched once per scan / per augmentation).
+//
+// Nearest-column pass.  Column duals only ever decrease from 0 and a row's dual is 0 until the row is inserted, so
+// the first frontier scan of row i returns min_j (c_ij - v_j) >= min_j c_ij = m_i, with equality at the nearest
+// column a_i whenever v[a_i] is still 0.  When a_i is also unmatched that scan ends the augmentation at once:
+// row i takes a_i, u_i = m_i, no other dual moves.  So all m_i, a_i are computed up front, lanes owning ROWS, over
+// SQUARED distances (7 FP64 operations per entry instead of the ~18 of a scan entry, no cross-lane reduction, one
+// square root per row), and the sequential insertion loop runs the Dijkstra scans only for the rows whose nearest
+// column is taken or has a moved dual (~10 % of the rows on solvent-shell data).  The result is the one the plain
+// insertion order produces, step for step.
 template <int C>
 __device__ int lsap_warp_reg(int n, const double* Qe, const double* Pe, double* u, int* pred, int* r4c, int* c4r,
-                             int lane) {
-    double px[C], py[C], pz[C], v[C], sh[C];
+                             double* m_row, int* a_row, unsigned char* moved, int lane) {
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    {
+        double qx[C], qy[C], qz[C], bd[C];
+        int bj[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int i = lane + 32 * c;
+            const bool in = i < n;
+            qx[c] = in ? Qe[3 * i] : 0.0; qy[c] = in ? Qe[3 * i + 1] : 0.0; qz[c] = in ? Qe[3 * i + 2] : 0.0;
+            bd[c] = INF; bj[c] = -1;
+        }
+#pragma unroll 2
+        for (int j = 0; j < n; ++j) {
+            const double x = Pe[3 * j], y = Pe[3 * j + 1], z = Pe[3 * j + 2];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const double d2 = dist2(qx[c] - x, qy[c] - y, qz[c] - z);
+                const bool lt = d2 < bd[c];
+                bd[c] = lt ? d2 : bd[c];
+                bj[c] = lt ? j : bj[c];
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int i = lane + 32 * c;
+            if (i < n) { m_row[i] = cost_sqrt(bd[c]); a_row[i] = bj[c]; moved[i] = 0; }
+        }
+    }
+    double px[C], py[C], pz[C], v[C], sh[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) {
         const int j = lane + 32 * c;
@@ -86,8 +125,30 @@ __device__ int lsap_warp_reg(int n, const double* Qe, const double* Pe, double* 
     unsigned valid = 0;
 #pragma unroll
     for (int c = 0; c < C; ++c) if (lane + 32 * c < n) valid |= 1u << c;
-    int steps = 0;
-    for (int cur = 0; cur < n; ++cur) {
+    int steps = 0;   // frontier scans + direct assignments (each stands for the first scan of its row)
+    int cur = 0;
+    while (cur < n) {
+        // direct assignments, 32 consecutive rows at a time: a row takes its nearest column when that column is
+        // unmatched, its dual has not moved and no earlier row of the batch wants it too; the rows before the first
+        // failing one are committed together, the failing one goes through the scans below
+        {
+            const int row = cur + lane;
+            int a = -1;
+            bool ok = false;
+            if (row < n) {
+                a = a_row[row];
+                ok = a >= 0 && r4c[a] < 0 && !moved[a];
+            }
+            const unsigned same = __match_any_sync(0xffffffffu, a);
+            ok = ok && (__ffs(same) - 1 == lane);
+            const unsigned fail = ~__ballot_sync(0xffffffffu, ok);
+            const int run = fail ? __ffs(fail) - 1 : 32;
+            if (lane < run) { r4c[a] = row; c4r[row] = a; u[row] = m_row[row]; }
+            __syncwarp();
+            steps += run;
+            cur += run;
+            if (run == 32 || cur >= n) continue;
+        }
 #pragma unroll
         for (int c = 0; c < C; ++c) sh[c] = INF;
         unsigned open = valid;  // owned columns not yet scanned
@@ -100,8 +161,7 @@ __device__ int lsap_warp_reg(int n, const double* Qe, const double* Pe, double* 
             int bestj = 0x7fffffff;
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                const double dx = qx - px[c], dy = qy - py[c], dz = qz - pz[c];
-                const double r = cost_sqrt(dx * dx + dy * dy + dz * dz) + mu - v[c];
+                const double r = cost_sqrt(dist2(qx - px[c], qy - py[c], qz - pz[c])) + mu - v[c];
                 const bool live = (open >> c) & 1u;
                 const bool upd = live && r < sh[c];
                 sh[c] = upd ? r : sh[c];
@@ -133,9 +193,12 @@ __device__ int lsap_warp_reg(int n, const double* Qe, const double* Pe, double* 
         for (int c = 0; c < C; ++c) {
             if (((valid & ~open) >> c) & 1u) {
                 const double delta = minVal - sh[c];
-                v[c] -= delta;
-                const int r = r4c[lane + 32 * c];
-                if (r >= 0) u[r] += delta;
+                if (delta != 0.0) {
+                    v[c] -= delta;
+                    moved[lane + 32 * c] = 1;
+                    const int r = r4c[lane + 32 * c];
+                    if (r >= 0) u[r] += delta;
+                }
             }
         }
         __syncwarp();
@@ -152,6 +215,7 @@ __device__ int lsap_warp_reg(int n, const double* Qe, const double* Pe, double* 
             }
         }
         __syncwarp();
+        ++cur;
     }
     return steps;
 }
@@ -291,12 +355,12 @@ __device__ int reorder_phase(const PairPlan& pl, int phase, double* W, int* perm
         __syncwarp();
         int st;
         switch ((n + 31) >> 5) {
-            case 1: st = lsap_warp_reg<1>(n, Qe, Pe, u, pred, r4c, c4r, lane); break;
-            case 2: st = lsap_warp_reg<2>(n, Qe, Pe, u, pred, r4c, c4r, lane); break;
-            case 3: st = lsap_warp_reg<3>(n, Qe, Pe, u, pred, r4c, c4r, lane); break;
-            case 4: st = lsap_warp_reg<4>(n, Qe, Pe, u, pred, r4c, c4r, lane); break;
-            case 5: case 6: st = lsap_warp_reg<6>(n, Qe, Pe, u, pred, r4c, c4r, lane); break;
-            case 7: case 8: st = lsap_warp_reg<8>(n, Qe, Pe, u, pred, r4c, c4r, lane); break;
+            case 1: st = lsap_warp_reg<1>(n, Qe, Pe, u, pred, r4c, c4r, v, reinterpret_cast<int*>(sh), scanned, lane); break;
+            case 2: st = lsap_warp_reg<2>(n, Qe, Pe, u, pred, r4c, c4r, v, reinterpret_cast<int*>(sh), scanned, lane); break;
+            case 3: st = lsap_warp_reg<3>(n, Qe, Pe, u, pred, r4c, c4r, v, reinterpret_cast<int*>(sh), scanned, lane); break;
+            case 4: st = lsap_warp_reg<4>(n, Qe, Pe, u, pred, r4c, c4r, v, reinterpret_cast<int*>(sh), scanned, lane); break;
+            case 5: case 6: st = lsap_warp_reg<6>(n, Qe, Pe, u, pred, r4c, c4r, v, reinterpret_cast<int*>(sh), scanned, lane); break;
+            case 7: case 8: st = lsap_warp_reg<8>(n, Qe, Pe, u, pred, r4c, c4r, v, reinterpret_cast<int*>(sh), scanned, lane); break;
             default: st = lsap_warp(n, Qe, Pe, u, v, sh, pred, r4c, c4r, scanned, lane); break;
         }
         steps += st < 0 ? -st : st;

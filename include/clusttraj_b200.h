@@ -55,7 +55,7 @@ typedef struct ct_stats {
     int64_t flagged;     /* pairs re-done by the explicit-rotation path (near-duplicates, degenerate 3x3) */
     int64_t launches;    /* kernel launches issued by the engine in this call */
     int64_t kept_atoms;  /* K: atoms entering the contraction after the mask */
-    int64_t lsap_steps;  /* total shortest-augmenting-path scan steps (Hungarian modes) */
+    int64_t lsap_steps;  /* shortest-augmenting-path frontier scans + rows assigned directly to their nearest column (Hungarian modes) */
     int64_t gram_path;   /* kernel behind the pure-Kabsch modes: 0 = none (per-pair kernel), 1 = FP64 DMMA Gram kernel,
                             2 = int8 tcgen05 Gram kernel (exact digit split of 31-bit fixed-point coordinates) */
     double quant_step;   /* path 2: the fixed-point quantum 2^-f in Angstrom (RMSD moves by at most ~1.8 quanta) */
