@@ -43,7 +43,7 @@ EXPORTS = [
     "ct_version", "ct_device_count", "ct_last_error", "ct_engine_create", "ct_engine_destroy", "ct_host_alloc",
     "ct_host_free", "ct_load_frames", "ct_rows_pairs", "ct_rmsd_rows", "ct_rmsd_rows_device", "ct_copy_slab",
     "ct_rmsd_condensed", "ct_pair_values", "ct_get_stats", "ct_pack_resident", "ct_matrix_consumers",
-    "ct_pair_transforms",
+    "ct_pair_transforms", "ct_linkage",
 ]
 
 _lib = None
@@ -88,6 +88,7 @@ def load_library(build_if_missing=True):
         lib.ct_get_stats.argtypes = [C.c_void_p, P(ct_stats)]
         lib.ct_pack_resident.argtypes = [C.c_void_p, P(ct_stats)]
         lib.ct_pair_transforms.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, P(ct_stats)]
+        lib.ct_linkage.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, P(ct_stats)]
         lib.ct_matrix_consumers.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p,
                                             P(C.c_double), P(ct_stats)]
         _lib = lib
@@ -241,6 +242,26 @@ class Engine:
                                                   n_clusters, med.ctypes.data if med is not None else None,
                                                   C.byref(total), C.byref(st)), "ct_matrix_consumers")
         return float(total.value), med, st.as_dict()
+
+    LINKAGE_METHODS = {"single": 0, "complete": 1, "average": 2, "ward": 5, "weighted": 6}   # SciPy's codes
+
+    def linkage(self, n_frames, method="average", distmat=None):
+        """(Z float64[M-1, 4], stats): scipy.cluster.hierarchy.linkage(distmat, method) on the GPU, for `distmat` (host
+        array) or, with distmat=None, the whole matrix the last rmsd_rows_device(0, M) left there."""
+        M = int(n_frames)
+        if method not in self.LINKAGE_METHODS:
+            raise ValueError(f"linkage method {method!r} does not run on the GPU (single, complete, average, weighted, ward do)")
+        ptr = None
+        if distmat is not None:
+            distmat = np.ascontiguousarray(distmat, dtype=np.float64)
+            if distmat.shape != (M * (M - 1) // 2,):
+                raise ValueError("distmat must be the condensed vector of n_frames frames")
+            ptr = distmat.ctypes.data
+        Z = np.empty((max(M - 1, 0), 4), dtype=np.float64)
+        st = ct_stats()
+        self._check(self._lib.ct_linkage(self._h, ptr, M, self.LINKAGE_METHODS[method], Z.ctypes.data, C.byref(st)),
+                    "ct_linkage")
+        return Z, st.as_dict()
 
     def stats(self):
         st = ct_stats()

@@ -1,7 +1,10 @@
-"""Drop-in for the two consumers of the RMSD matrix that clusttraj runs right after the clustering
-(clusttraj/classify.py:146-177), on the GPU and without the M x M ``squareform`` the reference builds on the
-host (3.2 GB at 20k frames, 80 GB at 100k):
+"""Drop-in for the clustering step and the two consumers of the RMSD matrix that clusttraj runs right after it
+(clusttraj/classify.py), on the GPU and without the M x M ``squareform`` the reference builds on the host (3.2 GB at
+20k frames, 80 GB at 100k):
 
+  linkage(distmat, method, optimal_ordering)     the hcl.linkage call at classify.py:30,99,127
+  classify_structures(clust_opt, distmat)        classify.py:84-110
+  classify_structures_nclusters(clust_opt, ...)  classify.py:113-143
   find_medoids_from_clusters(distmat, clusters)  classify.py:146-165
   sum_distmat(distmat)                           classify.py:168-177
 
@@ -21,6 +24,49 @@ def _n_frames(distmat):
     if M * (M - 1) // 2 != L:
         raise ValueError("distmat is not a condensed distance vector")   # what squareform raises in the reference
     return M
+
+
+GPU_LINKAGE_METHODS = ("single", "complete", "average", "weighted", "ward")
+
+
+def linkage(distmat, method="average", optimal_ordering=False):
+    """scipy.cluster.hierarchy.linkage(distmat, method, optimal_ordering=...) with the clustering itself on the GPU:
+    the linkage matrix is the one SciPy returns, bit for bit (same nearest-neighbour-chain / minimum-spanning-tree
+    step order and tie rules).  `centroid` and `median` — SciPy's generic priority-queue algorithm — are
+    passed to SciPy unchanged, as is the optional leaf reordering of the finished tree."""
+    import scipy.cluster.hierarchy as hcl
+
+    if method not in GPU_LINKAGE_METHODS:
+        return hcl.linkage(distmat, method, optimal_ordering=bool(optimal_ordering))
+    M = _n_frames(distmat)
+    eng = _engine_for(visible_devices()[0])
+    Z, _ = eng.linkage(M, method, distmat=distmat)
+    if optimal_ordering:
+        Z = hcl.optimal_leaf_ordering(Z, distmat)
+    return Z
+
+
+def classify_structures(clust_opt, distmat):
+    """Linkage + flat clusters at the RMSD threshold, written to clust_opt.out_clust_name (classify.py:84-110)."""
+    import scipy.cluster.hierarchy as hcl
+
+    Z = linkage(distmat, clust_opt.method, optimal_ordering=clust_opt.opt_order)
+    clusters = hcl.fcluster(Z, clust_opt.min_rmsd, criterion="distance")
+    np.savetxt(clust_opt.out_clust_name, clusters, fmt="%d")
+    return Z, clusters
+
+
+def classify_structures_nclusters(clust_opt, distmat):
+    """Linkage + the cut that gives clust_opt.n_clusters clusters (classify.py:113-143)."""
+    import scipy.cluster.hierarchy as hcl
+
+    Z = linkage(distmat, clust_opt.method, optimal_ordering=clust_opt.opt_order)
+    n_snapshots = Z.shape[0] + 1
+    if clust_opt.n_clusters > n_snapshots:
+        raise ValueError(f"Cannot request {clust_opt.n_clusters} clusters from {n_snapshots} snapshots")
+    clusters = hcl.cut_tree(Z, n_clusters=[clust_opt.n_clusters]).ravel() + 1
+    np.savetxt(clust_opt.out_clust_name, clusters, fmt="%d")
+    return Z, clusters
 
 
 def find_medoids_from_clusters(distmat, clusters):

@@ -32,6 +32,10 @@ cudaError_t launch_consumers(const double* d, long long L, int M, const int* lab
                              unsigned long long* best_bits, long long* medoid, int sm_count, cudaStream_t stream);
 int consumers_scratch_doubles(int M);
 int consumers_sum_offset(int M);
+size_t linkage_scratch_bytes(int M, int sm_count);
+cudaError_t run_linkage(double* D, int M, int method, unsigned char* scratch, int sm_count, double* zraw_host, int* done_flag,
+                        long long* steps_out, cudaStream_t stream);
+void linkage_finish(const double* zraw, int M, double* Z);
 struct PairPlan;
 struct PairPlanHost;
 int pair_plan_build(PairPlanHost** out, const int32_t* kept_z, int K, int natoms, const ct_opts* o, std::string& err);
@@ -79,6 +83,10 @@ struct ct_engine {
     double* d_cons = nullptr; size_t cons_cap = 0;
     unsigned long long* d_best = nullptr; size_t best_cap = 0;
     long long* d_medoid = nullptr; size_t medoid_cap = 0;
+    // hierarchical clustering (ct_linkage)
+    double* d_link = nullptr; size_t link_cap = 0;           // working copy of the matrix the NN-chain methods update
+    unsigned char* d_link_scratch = nullptr; size_t link_scratch_cap = 0;
+    int* h_link_flag = nullptr;                              // pinned
     double* d_chunk[2] = {nullptr, nullptr}; size_t chunk_cap = 0;  // streaming double buffer
     int2* d_fix_pairs = nullptr; unsigned int* d_fix_count = nullptr; unsigned int fix_cap = 1u << 20;
     unsigned long long* d_counters = nullptr;  // [0] flagged pairs, [1] lsap steps
@@ -185,6 +193,8 @@ void ct_engine_destroy(ct_engine* e) {
     cudaFree(e->d_raw); cudaFree(e->d_keep); cudaFree(e->d_centred); cudaFree(e->d_G); cudaFree(e->d_packed);
     cudaFree(e->d_packA); cudaFree(e->d_packB); cudaFree(e->d_packT); cudaFree(e->d_Gq); cudaFree(e->d_qinfo); cudaFree(e->d_maxbits);
     cudaFree(e->d_labels); cudaFree(e->d_cons); cudaFree(e->d_best); cudaFree(e->d_medoid);
+    cudaFree(e->d_link); cudaFree(e->d_link_scratch);
+    if (e->h_link_flag) cudaFreeHost(e->h_link_flag);
     cudaFree(e->d_slab); cudaFree(e->d_chunk[0]); cudaFree(e->d_chunk[1]);
     cudaFree(e->d_fix_pairs); cudaFree(e->d_fix_count); cudaFree(e->d_counters);
     for (int k = 0; k < 2; ++k) { cudaEventDestroy(e->ev_chunk_done[k]); cudaEventDestroy(e->ev_copy_done[k]); }
@@ -611,6 +621,51 @@ int ct_matrix_consumers(ct_engine* e, const double* distmat, int64_t M, const in
     CT_CUDA(e, cudaEventElapsedTime(&ms, e->ev_b, e->ev_c)); e->stats.kernel_ms = ms;
     e->stats.total_ms = e->stats.h2d_ms + e->stats.kernel_ms;
     e->stats.pairs = L; e->stats.launches = n_clusters > 0 ? 5 : 2;
+    if (stats) *stats = e->stats;
+    return CT_OK;
+}
+
+int ct_linkage(ct_engine* e, const double* distmat, int64_t M, int32_t method, double* Z, ct_stats* stats) {
+    if (!e) return fail(nullptr, CT_ERR_ARG, "engine is NULL");
+    if (M < 2 || M > (int64_t)1 << 30) return fail(e, CT_ERR_ARG, "ct_linkage: need 2 <= M <= 2^30 observations");
+    if (!Z) return fail(e, CT_ERR_ARG, "ct_linkage: Z is NULL");
+    if (method != 0 && method != 1 && method != 2 && method != 5 && method != 6)
+        return fail(e, CT_ERR_UNSUPPORTED, "ct_linkage: methods single (0), complete (1), average (2), ward (5) and weighted (6) "
+                                           "run on the GPU; centroid / median stay with SciPy");
+    CT_CUDA(e, cudaSetDevice(e->device));
+    const int64_t L = M * (M - 1) / 2;
+    int rc;
+    CT_CUDA(e, cudaEventRecord(e->ev_a, e->s_compute));
+    if (distmat) {
+        e->slab_full_M = 0;
+        if ((rc = ensure(e, e->d_slab, e->slab_cap, (size_t)L))) return rc;
+        CT_CUDA(e, cudaMemcpyAsync(e->d_slab, distmat, sizeof(double) * (size_t)L, cudaMemcpyHostToDevice, e->s_compute));
+        e->slab_full_M = M;
+    } else if (e->slab_full_M != M) {
+        return fail(e, CT_ERR_STATE, "ct_linkage: no whole matrix of M observations on the GPU "
+                                     "(pass distmat, or call ct_rmsd_rows_device(e, 0, M, ...) first)");
+    }
+    CT_CUDA(e, cudaEventRecord(e->ev_b, e->s_compute));
+    double* D = e->d_slab;
+    if (method != 0) {  // the chain methods update the matrix: work on a copy, like SciPy (the matrix stays usable)
+        if ((rc = ensure(e, e->d_link, e->link_cap, (size_t)L))) return rc;
+        CT_CUDA(e, cudaMemcpyAsync(e->d_link, e->d_slab, sizeof(double) * (size_t)L, cudaMemcpyDeviceToDevice, e->s_compute));
+        D = e->d_link;
+    }
+    if ((rc = ensure(e, e->d_link_scratch, e->link_scratch_cap, ct::linkage_scratch_bytes((int)M, e->sm_count)))) return rc;
+    if (!e->h_link_flag) CT_CUDA(e, cudaHostAlloc((void**)&e->h_link_flag, sizeof(int), cudaHostAllocDefault));
+    std::vector<double> zraw(4 * (size_t)(M - 1));
+    long long steps = 0;
+    CT_CUDA(e, ct::run_linkage(D, (int)M, method, e->d_link_scratch, e->sm_count, zraw.data(), e->h_link_flag, &steps,
+                               e->s_compute));
+    CT_CUDA(e, cudaEventRecord(e->ev_c, e->s_compute));
+    CT_CUDA(e, cudaEventSynchronize(e->ev_c));
+    ct::linkage_finish(zraw.data(), (int)M, Z);
+    float ms = 0.f;
+    CT_CUDA(e, cudaEventElapsedTime(&ms, e->ev_a, e->ev_b)); e->stats.h2d_ms = ms;
+    CT_CUDA(e, cudaEventElapsedTime(&ms, e->ev_b, e->ev_c)); e->stats.kernel_ms = ms;
+    e->stats.total_ms = e->stats.h2d_ms + e->stats.kernel_ms;
+    e->stats.pairs = L; e->stats.launches = steps + 1;
     if (stats) *stats = e->stats;
     return CT_OK;
 }

@@ -1,0 +1,300 @@
+// K6 — hierarchical clustering of the condensed RMSD matrix in HBM ("linkage on GPU"):
+// scipy.cluster.hierarchy.linkage(distmat, method) as clusttraj calls it at clusttraj/classify.py:30,99,127, for the
+// methods SciPy serves with its nearest-neighbour-chain algorithm (complete, average, weighted, ward) and with Prim's
+// minimum spanning tree (single).  SciPy is a third-party dependency of the reference (requirements.txt), importable on
+// the GPU box: the parity tests compare the linkage matrix Z bit for bit with the live module; the CPU restatement this
+// file follows step for step is oracle/linkage_restated.py (pinned against the same module, ties and duplicates
+// included).  centroid / median (SciPy's generic priority-queue algorithm) stay on the host.
+//
+// The algorithm is a chain of dependent steps, each a pass over ONE row of the matrix (M entries): "nearest live cluster
+// of the chain tip" (<= 3 M of them), "Lance-Williams update of the merged cluster's row" (M - 1 of them), or one Prim
+// step.  A step is one launch of linkage_step_kernel over the whole GPU (the row is spread over up to 148 CTAs so that
+// its column part, one 32-byte sector per entry in the condensed layout, is fetched in one round of memory latency); the
+// last CTA to finish (ticket counter) folds the per-CTA partial results and advances the state machine in device
+// memory, so the host never reads anything back between steps: it replays a CUDA graph of identical step launches until
+// the state says "done" (steps after that are no-ops).  Kernel boundaries are the only grid-wide synchronisation.
+//
+// Exactness: the step order, the tie rules (previous chain element first, then the lowest index; the merged cluster
+// lives in the higher slot) and the floating-point operation order of the update formulas are SciPy's; the formulas
+// use explicitly rounded operations (__dmul_rn ...) so that the compiler cannot contract them into FMAs.
+#include "common.cuh"
+
+#include <algorithm>
+#include <numeric>
+#include <vector>
+
+namespace ct {
+
+enum { LK_SINGLE = 0, LK_COMPLETE = 1, LK_AVERAGE = 2, LK_WARD = 5, LK_WEIGHTED = 6 };  // SciPy's method codes
+enum { ACT_SCAN = 0, ACT_UPDATE = 1, ACT_DONE = 2, ACT_PRIM = 3 };
+constexpr int LK_THREADS = 256;
+constexpr int LK_NONE = 0x7fffffff;
+
+struct LinkState {
+    int action;
+    int x, y;        // scan: x = chain tip, y = SciPy's loop variable y (persists); update: x dropped, y kept
+    int prev;        // chain element under the tip, or -1
+    int clen, k;     // chain length, merges recorded
+    int nx, ny;
+    double dxy;      // distance of the merge being applied
+    double dprev;    // D[x, prev] picked up during the scan
+    unsigned int ticket;
+    int steps;       // step launches that did work
+};
+
+__device__ __forceinline__ long long cidx(long long n, long long i, long long j) {  // i != j
+    const long long a = i < j ? i : j, b = i < j ? j : i;
+    return condensed_row_base(n, a) + (b - a - 1);
+}
+
+__device__ __forceinline__ double lw_update(int method, double dxi, double dyi, double dxy, int nx, int ny, int ni) {
+    switch (method) {
+        case LK_COMPLETE: return dxi > dyi ? dxi : dyi;
+        case LK_AVERAGE:
+            return __ddiv_rn(__dadd_rn(__dmul_rn((double)nx, dxi), __dmul_rn((double)ny, dyi)), (double)(nx + ny));
+        case LK_WEIGHTED: return __dmul_rn(0.5, __dadd_rn(dxi, dyi));
+        default: {  // ward
+            const double t = __ddiv_rn(1.0, (double)(nx + ny + ni));
+            const double a = __dmul_rn(__dmul_rn(__dmul_rn((double)(ni + nx), t), dxi), dxi);
+            const double b = __dmul_rn(__dmul_rn(__dmul_rn((double)(ni + ny), t), dyi), dyi);
+            const double c = __dmul_rn(__dmul_rn(__dmul_rn((double)ni, t), dxy), dxy);
+            return __dsqrt_rn(__dsub_rn(__dadd_rn(a, b), c));
+        }
+    }
+}
+
+// lexicographic minimum of (value, index) over the block; the result is valid in thread 0
+__device__ __forceinline__ void block_min_pair(double& d, int& i, double* sd, int* si) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, d, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+        if (od < d || (od == d && oi < i)) { d = od; i = oi; }
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { sd[w] = d; si[w] = i; }
+    __syncthreads();
+    if (w == 0) {
+        d = l < LK_THREADS / 32 ? sd[l] : __longlong_as_double(0x7ff0000000000000LL);
+        i = l < LK_THREADS / 32 ? si[l] : LK_NONE;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            const double od = __shfl_xor_sync(0xffffffffu, d, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+            if (od < d || (od == d && oi < i)) { d = od; i = oi; }
+        }
+    }
+    __syncthreads();
+}
+
+// D: working copy of the condensed matrix (NN-chain methods: updated in place; single: read only)
+__global__ void __launch_bounds__(LK_THREADS) linkage_step_kernel(LinkState* __restrict__ st, double* __restrict__ D,
+                                                                  int* __restrict__ size, int* __restrict__ chain,
+                                                                  double* __restrict__ Zraw, double* __restrict__ dmin,
+                                                                  double* __restrict__ part_d, int* __restrict__ part_i,
+                                                                  int M, int method) {
+    __shared__ LinkState s;
+    __shared__ double sd[LK_THREADS / 32];
+    __shared__ int si[LK_THREADS / 32];
+    __shared__ bool last;
+    if (threadIdx.x == 0) s = *st;
+    __syncthreads();
+    const int action = s.action;
+    if (action == ACT_DONE) return;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    const int gtid = blockIdx.x * LK_THREADS + threadIdx.x, gthreads = gridDim.x * LK_THREADS;
+    const int x = s.x;
+    double bd = INF;
+    int bi = LK_NONE;
+    if (action == ACT_SCAN) {
+        const int prev = s.prev;
+        for (int i = gtid; i < M; i += gthreads) {
+            const int sz = size[i];
+            const double d = i != x ? D[cidx(M, x, i)] : INF;
+            if (i == prev) { st->dprev = d; __threadfence(); }
+            if (sz != 0 && d < bd) { bd = d; bi = i; }
+        }
+    } else if (action == ACT_PRIM) {
+        for (int i = gtid; i < M; i += gthreads) {
+            if (size[i] == 0) continue;  // already in the tree
+            const double d = D[cidx(M, x, i)];
+            double dm = dmin[i];
+            if (dm > d) { dm = d; dmin[i] = d; }
+            if (dm < bd) { bd = dm; bi = i; }
+        }
+    } else {  // ACT_UPDATE: row of the merged cluster (slot y); bi collects the lowest live slot for an emptied chain
+        const int y = s.y, nx = s.nx, ny = s.ny;
+        const double dxy = s.dxy;
+        for (int i = gtid; i < M; i += gthreads) {
+            const int ni = size[i];
+            if (ni == 0) continue;
+            if (bi == LK_NONE) bi = i;
+            if (i == y) continue;
+            const long long iy = cidx(M, i, y);
+            D[iy] = lw_update(method, D[cidx(M, i, x)], D[iy], dxy, nx, ny, ni);
+        }
+        bd = 0.0;  // all partials compare equal: the index decides
+    }
+    block_min_pair(bd, bi, sd, si);
+    if (threadIdx.x == 0) {
+        part_d[blockIdx.x] = bd;
+        part_i[blockIdx.x] = bi;
+        __threadfence();
+        last = atomicAdd(&st->ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    bd = INF; bi = LK_NONE;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += LK_THREADS) {
+        const double od = __ldcg(part_d + b);
+        const int oi = __ldcg(part_i + b);
+        if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+    }
+    block_min_pair(bd, bi, sd, si);
+    if (threadIdx.x != 0) return;
+    // ---- state machine, one thread ----
+    LinkState n = s;
+    n.ticket = 0;
+    n.steps = s.steps + 1;
+    if (action == ACT_SCAN) {
+        int y = s.y;
+        double cur = INF;
+        if (s.clen > 1) { y = s.prev; cur = __ldcg(&st->dprev); }
+        if (bi != LK_NONE && bd < cur) { cur = bd; y = bi; }
+        n.y = y;
+        if (s.clen > 1 && y == s.prev) {
+            // reciprocal nearest neighbours: merge, the new cluster lives in the higher slot
+            const int a = x < y ? x : y, b = x < y ? y : x;
+            const int na = size[a], nb = size[b];
+            double* z = Zraw + 4 * (size_t)s.k;
+            z[0] = (double)a; z[1] = (double)b; z[2] = cur; z[3] = (double)(na + nb);
+            size[a] = 0; size[b] = na + nb;
+            n.clen = s.clen - 2;
+            n.action = ACT_UPDATE; n.x = a; n.y = b; n.nx = na; n.ny = nb; n.dxy = cur;
+        } else {
+            chain[s.clen] = y;
+            n.clen = s.clen + 1;
+            n.prev = x; n.x = y;
+        }
+    } else if (action == ACT_UPDATE) {
+        n.k = s.k + 1;
+        if (n.k == M - 1) n.action = ACT_DONE;
+        else {
+            n.action = ACT_SCAN;
+            n.y = s.y;
+            if (s.clen == 0) { chain[0] = bi; n.clen = 1; n.x = bi; n.prev = -1; }
+            else { n.x = chain[s.clen - 1]; n.prev = s.clen > 1 ? chain[s.clen - 2] : -1; }
+        }
+    } else {  // ACT_PRIM
+        const int y = bi != LK_NONE ? bi : s.y;
+        double* z = Zraw + 4 * (size_t)s.k;
+        z[0] = (double)x; z[1] = (double)y; z[2] = bd; z[3] = 0.0;
+        size[y] = 0;
+        n.x = y; n.y = y; n.k = s.k + 1;
+        if (n.k == M - 1) n.action = ACT_DONE;
+    }
+    *st = n;
+}
+
+__global__ void linkage_init_kernel(LinkState* st, int* size, double* dmin, int M, int method) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < M) {
+        size[i] = (method == LK_SINGLE && i == 0) ? 0 : 1;
+        dmin[i] = __longlong_as_double(0x7ff0000000000000LL);
+    }
+    if (i == 0) {
+        LinkState n{};
+        n.action = M < 2 ? ACT_DONE : (method == LK_SINGLE ? ACT_PRIM : ACT_SCAN);
+        n.x = 0; n.y = 0; n.prev = -1; n.clen = 1; n.k = 0;
+        *st = n;
+    }
+}
+
+// scratch layout (bytes): state | size[M] | chain[M] | dmin[M] | part_d[grid] | part_i[grid] | Zraw[4 (M - 1)]
+size_t linkage_scratch_bytes(int M, int sm_count) {
+    return 256 + sizeof(int) * 2 * (size_t)M + sizeof(double) * (size_t)M + 12 * (size_t)sm_count + 64 +
+           sizeof(double) * 4 * (size_t)M;
+}
+
+// Runs the clustering on `D` (NN-chain methods overwrite it) and leaves the raw merges in `zraw_host` (pinned or
+// pageable, 4 (M - 1) doubles).  `done_flag` is a pinned int the state's action is copied to between graph replays.
+cudaError_t run_linkage(double* D, int M, int method, unsigned char* scratch, int sm_count, double* zraw_host,
+                        int* done_flag, long long* steps_out, cudaStream_t stream) {
+    LinkState* st = reinterpret_cast<LinkState*>(scratch);
+    int* size = reinterpret_cast<int*>(scratch + 256);
+    int* chain = size + M;
+    double* dmin = reinterpret_cast<double*>(scratch + 256 + sizeof(int) * 2 * (size_t)M);
+    double* part_d = dmin + M;
+    int* part_i = reinterpret_cast<int*>(part_d + sm_count);
+    double* Zraw = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(part_i) + ((sizeof(int) * sm_count + 7) / 8) * 8);
+    int grid = (M + LK_THREADS - 1) / LK_THREADS;
+    if (grid > sm_count) grid = sm_count;
+    if (grid < 1) grid = 1;
+    linkage_init_kernel<<<(M + 255) / 256, 256, 0, stream>>>(st, size, dmin, M, method);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    // a graph of identical step launches, replayed until the state machine reports "done"
+    const long long max_steps = 4LL * M + 8;
+    const int batch = (int)std::min<long long>(max_steps, 2048);
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    if ((e = cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal)) != cudaSuccess) return e;
+    for (int b = 0; b < batch; ++b)
+        linkage_step_kernel<<<grid, LK_THREADS, 0, stream>>>(st, D, size, chain, Zraw, dmin, part_d, part_i, M, method);
+    e = cudaStreamEndCapture(stream, &graph);
+    if (e != cudaSuccess) return e;
+    if ((e = cudaGraphInstantiate(&exec, graph, 0)) != cudaSuccess) { cudaGraphDestroy(graph); return e; }
+    cudaError_t rc = cudaSuccess;
+    bool done = false;
+    for (long long launched = 0; launched < max_steps + batch && !done; launched += batch) {
+        if ((rc = cudaGraphLaunch(exec, stream)) != cudaSuccess) break;
+        if ((rc = cudaMemcpyAsync(done_flag, &st->action, sizeof(int), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) break;
+        if ((rc = cudaStreamSynchronize(stream)) != cudaSuccess) break;
+        done = *done_flag == ACT_DONE;
+    }
+    cudaGraphExecDestroy(exec);
+    cudaGraphDestroy(graph);
+    if (rc != cudaSuccess) return rc;
+    if (!done) return cudaErrorUnknown;  // cannot happen: the chain algorithm needs at most 4 M steps
+    int steps = 0;
+    if ((rc = cudaMemcpyAsync(&steps, &st->steps, sizeof(int), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return rc;
+    if (M > 1 && (rc = cudaMemcpyAsync(zraw_host, Zraw, sizeof(double) * 4 * (size_t)(M - 1), cudaMemcpyDeviceToHost, stream)) != cudaSuccess)
+        return rc;
+    if ((rc = cudaStreamSynchronize(stream)) != cudaSuccess) return rc;
+    *steps_out = steps;
+    return cudaSuccess;
+}
+
+// what SciPy does after either algorithm: stable sort of the merges by distance, then union-find relabelling
+// (new clusters numbered M, M + 1, ... in sorted order; the two members of a merge in ascending order)
+void linkage_finish(const double* zraw, int M, double* Z) {
+    const int n = M - 1;
+    std::vector<int> order(n);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [zraw](int a, int b) { return zraw[4 * (size_t)a + 2] < zraw[4 * (size_t)b + 2]; });
+    std::vector<int> parent(2 * (size_t)M - 1), csize(2 * (size_t)M - 1, 0);
+    std::iota(parent.begin(), parent.end(), 0);
+    std::fill(csize.begin(), csize.begin() + M, 1);
+    auto find = [&parent](int v) {
+        int r = v;
+        while (parent[r] != r) r = parent[r];
+        while (parent[v] != r) { const int nx = parent[v]; parent[v] = r; v = nx; }
+        return r;
+    };
+    int next = M;
+    for (int k = 0; k < n; ++k) {
+        const double* z = zraw + 4 * (size_t)order[k];
+        const int xr = find((int)z[0]), yr = find((int)z[1]);
+        double* o = Z + 4 * (size_t)k;
+        o[0] = (double)(xr < yr ? xr : yr);
+        o[1] = (double)(xr < yr ? yr : xr);
+        o[2] = z[2];
+        parent[xr] = next; parent[yr] = next;
+        csize[next] = csize[xr] + csize[yr];
+        o[3] = (double)csize[next];
+        ++next;
+    }
+}
+
+}  // namespace ct

@@ -1,26 +1,22 @@
 """CLI entry (reference: clusttraj/main.py:24-174): options -> RMSD matrix on the GPU -> the unchanged
-SciPy linkage / fcluster -> clusters file and summary."""
+linkage on the GPU (SciPy's algorithm, identical Z) / fcluster -> clusters file and summary."""
 import sys
 import time
 
 import numpy as np
 
-from .classify import find_medoids_from_clusters, sum_distmat
+from .classify import (classify_structures, classify_structures_nclusters, find_medoids_from_clusters,
+                       sum_distmat)
 from .distmat import get_distmat
 from .io import Logger, configure_runtime, save_clusters_config, save_medoids_config
 
 
 def classify(clust_opt, distmat):
-    """SciPy hierarchical clustering exactly as the reference calls it (classify.py:84-143)."""
-    import scipy.cluster.hierarchy as hcl
-
-    Z = hcl.linkage(distmat, clust_opt.method, optimal_ordering=bool(clust_opt.opt_order))
+    """The clustering step as the reference's main dispatches it (main.py:47-57): -nc -> classify_structures_nclusters,
+    else classify_structures; the linkage runs on the GPU (clusttraj_b200/classify.py)."""
     if clust_opt.n_clusters is not None:
-        clusters = hcl.fcluster(Z, clust_opt.n_clusters, criterion="maxclust")
-    else:
-        clusters = hcl.fcluster(Z, clust_opt.min_rmsd, criterion="distance")
-    np.savetxt(clust_opt.out_clust_name, clusters, fmt="%d")
-    return Z, clusters
+        return classify_structures_nclusters(clust_opt, distmat)
+    return classify_structures(clust_opt, distmat)
 
 
 def main(args=None):

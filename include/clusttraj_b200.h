@@ -134,6 +134,16 @@ int ct_pair_transforms(ct_engine* e, const int64_t* pairs, int64_t n_pairs, doub
 int ct_matrix_consumers(ct_engine* e, const double* distmat, int64_t M, const int32_t* labels, int32_t n_clusters,
                         int64_t* medoids, double* total, ct_stats* stats);
 
+/* Hierarchical clustering of the condensed matrix on the GPU: scipy.cluster.hierarchy.linkage(distmat,
+ * method) as clusttraj calls it at clusttraj/classify.py:30,99,127.  method uses SciPy's codes: 0 single, 1 complete,
+ * 2 average, 5 ward, 6 weighted (centroid and median are not offered: CT_ERR_UNSUPPORTED, use SciPy).  Z: [M-1][4]
+ * float64, the linkage matrix exactly as SciPy returns it (same merges, same order, same tie rules, bit-identical
+ * heights).  distmat: HOST pointer to the condensed vector, or NULL to cluster the whole matrix that
+ * ct_rmsd_rows_device(e, 0, M, ...) left on the GPU; the matrix on the GPU is left unchanged (the chain methods work on
+ * a copy), so ct_matrix_consumers(e, NULL, ...) can follow.  stats: kernel_ms (clustering), h2d_ms (upload),
+ * launches (step kernels). */
+int ct_linkage(ct_engine* e, const double* distmat, int64_t M, int32_t method, double* Z, ct_stats* stats);
+
 int ct_get_stats(const ct_engine* e, ct_stats* stats);
 const char* ct_version(void);
 

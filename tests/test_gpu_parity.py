@@ -722,3 +722,125 @@ def test_save_clusters_and_medoids_config(golden_dir, tmp_path):
     save_medoids_config(traj, medoids, False, None, False, None, None, str(tmp_path / "med"), "xyz", np.asarray([], np.int32), False, True)
     a, x = xyz.read_xyz(str(tmp_path / "med.xyz"))
     assert len(x) == 3
+
+
+# ---- hierarchical clustering on the GPU (the hcl.linkage call at clusttraj/classify.py:30,99,127) -------------------
+
+LINKAGE_METHODS = ["single", "complete", "average", "weighted", "ward"]
+
+
+def _linkage_inputs():
+    from scipy.spatial.distance import pdist
+
+    rng = np.random.default_rng(77)
+    cases = {}
+    for M in (2, 3, 7, 64, 257, 1000):
+        cases[f"random_{M}"] = rng.random(M * (M - 1) // 2) * 5.0
+    cases["ties_120"] = np.round(rng.random(120 * 119 // 2) * 3.0, 1)              # many equal distances
+    x = rng.normal(size=(90, 3))
+    x[45:] = x[:45]                                                               # exact duplicates: zero distances
+    cases["duplicates_90"] = pdist(x)
+    cases["euclid_500"] = pdist(rng.normal(size=(500, 6)))
+    cases["all_equal_33"] = np.full(33 * 32 // 2, 1.25)
+    return cases
+
+
+@pytest.mark.parametrize("method", LINKAGE_METHODS)
+def test_linkage_is_scipys_linkage_bit_for_bit(method):
+    """Z from the GPU == scipy.cluster.hierarchy.linkage(distmat, method): same merges in the same order, identical
+    heights to the last bit, on random, tie-laden, duplicate-laden and constant matrices."""
+    import scipy.cluster.hierarchy as hcl
+    from clusttraj_b200.classify import linkage
+
+    for name, d in _linkage_inputs().items():
+        want = hcl.linkage(d, method)
+        got = linkage(d, method)
+        assert got.shape == want.shape and got.dtype == np.float64
+        assert got.tobytes() == want.tobytes(), (method, name, np.abs(got - want).max(), np.argwhere(got != want)[:3])
+        assert hcl.is_valid_linkage(got)
+
+
+def test_linkage_on_the_device_resident_matrix_and_downstream():
+    """RMSD matrix -> linkage -> medoids without the matrix leaving the GPU; the matrix is left intact (the chain methods
+    work on a copy); optimal ordering, centroid/median (SciPy) and the classify_* entry points behave as the reference's."""
+    import types
+
+    import scipy.cluster.hierarchy as hcl
+    from clusttraj_b200 import _engine
+    from clusttraj_b200.classify import classify_structures, classify_structures_nclusters, linkage
+    from clusttraj_b200.synth import make_trajectory
+
+    M = 900
+    atoms, coords = make_trajectory(M, 40, seed=45, n_modes=7)
+    e = _engine_with(None)
+    e.load_frames(coords, atoms, engine_opts())
+    _, n, _ = e.rmsd_rows_device(0, M)
+    d = e.copy_slab(0, n)
+    for method in LINKAGE_METHODS:
+        Z, st = e.linkage(M, method)                       # distmat=None: the resident matrix
+        assert Z.tobytes() == hcl.linkage(d, method).tobytes(), method
+        assert st["h2d_ms"] < 1.0 and st["launches"] >= M - 1
+    assert e.copy_slab(0, n).tobytes() == d.tobytes()      # untouched
+    total, med, _ = e.matrix_consumers(M, clusters=hcl.fcluster(Z, 7, criterion="maxclust"))
+    assert abs(total - d.sum()) <= 1e-12 * total and len(med) == 7
+    with pytest.raises(ValueError, match="does not run on the GPU"):
+        e.linkage(M, "centroid")
+    e.load_frames(coords[:50], atoms, engine_opts())
+    e.rmsd_rows_device(0, 50)
+    with pytest.raises(_engine.EngineError, match="no whole matrix"):
+        e.linkage(M, "average")
+    e.close()
+    # host entry points
+    small = d[: 200 * 199 // 2]
+    assert linkage(small, "average", optimal_ordering=True).tobytes() == hcl.linkage(small, "average", optimal_ordering=True).tobytes()
+    assert linkage(small, "centroid").tobytes() == hcl.linkage(small, "centroid").tobytes()
+    with pytest.raises(ValueError):
+        linkage(d[:-1], "average")
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        opt = types.SimpleNamespace(method="ward", opt_order=False, min_rmsd=2.0, n_clusters=5,
+                                    out_clust_name=os.path.join(tmp, "clusters.dat"))
+        Zw = hcl.linkage(d, "ward")
+        Z1, c1 = classify_structures(opt, d)
+        assert Z1.tobytes() == Zw.tobytes() and (c1 == hcl.fcluster(Zw, 2.0, criterion="distance")).all()
+        assert (np.loadtxt(opt.out_clust_name, dtype=int) == c1).all()
+        Z2, c2 = classify_structures_nclusters(opt, d)
+        assert (c2 == hcl.cut_tree(Zw, n_clusters=[5]).ravel() + 1).all() and c2.max() == 5
+        opt.n_clusters = M + 1
+        with pytest.raises(ValueError, match="Cannot request"):
+            classify_structures_nclusters(opt, d)
+
+
+def test_linkage_config2_size():
+    """20000 observations (the cfg2 matrix size): Z identical to SciPy's for average linkage, and much faster."""
+    import time
+
+    import scipy.cluster.hierarchy as hcl
+    from clusttraj_b200.synth import make_trajectory
+
+    M = 20000
+    atoms, coords = make_trajectory(M, 30, seed=46, n_modes=12)
+    e = _engine_with(None)
+    e.load_frames(coords, atoms, engine_opts())
+    _, n, _ = e.rmsd_rows_device(0, M)
+    Z, st = e.linkage(M, "average")
+    d = e.copy_slab(0, n)
+    e.close()
+    t0 = time.perf_counter()
+    want = hcl.linkage(d, "average")
+    cpu_s = time.perf_counter() - t0
+    assert Z.tobytes() == want.tobytes()
+    assert st["kernel_ms"] * 1e-3 < cpu_s, (st["kernel_ms"], cpu_s)
+
+
+def test_classify_on_golden_vector(tmp_path, ref_golden_distmat):
+    """Reference test_classify.py:30-52: ward linkage of the golden matrix, labels at -rmsd 1.0 and for -nc 2."""
+    from clusttraj_b200.io import ClustOptions
+    from clusttraj_b200.main import classify
+
+    opt = ClustOptions(method="ward", min_rmsd=1.0, opt_order=False, out_clust_name=str(tmp_path / "c.dat"))
+    Z, clusters = classify(opt, ref_golden_distmat)
+    assert np.allclose(Z, [[0.0, 1.0, 2.94126393, 2.0], [2.0, 3.0, 4.6348889, 3.0]])
+    assert list(clusters) == [1, 2, 3]
+    opt.update({"n_clusters": 2})
+    assert list(classify(opt, ref_golden_distmat)[1]) == [1, 1, 2]

@@ -151,17 +151,24 @@ def test_reorder_handles():
         reorder.reorder_hungarian(None, None, None, None)
 
 
-def test_classify_on_golden_vector(tmp_path, ref_golden_distmat):
-    """Reference test_classify.py:30-52: ward linkage of the golden matrix."""
+def test_classify_fails_loudly_without_a_gpu(tmp_path, ref_golden_distmat):
+    """The clustering step runs its linkage on the GPU (clusttraj_b200/classify.py): without one it raises instead of
+    quietly calling SciPy.  (With a GPU, the reference's test_classify.py:30-52 case is test_gpu_parity.py's
+    test_classify_on_golden_vector.)  centroid / median are documented SciPy pass-throughs."""
+    import scipy.cluster.hierarchy as hcl
+
+    from clusttraj_b200 import _engine
+    from clusttraj_b200.classify import linkage
     from clusttraj_b200.io import ClustOptions
     from clusttraj_b200.main import classify
 
     opt = ClustOptions(method="ward", min_rmsd=1.0, opt_order=False, out_clust_name=str(tmp_path / "c.dat"))
-    Z, clusters = classify(opt, ref_golden_distmat)
-    assert np.allclose(Z, [[0.0, 1.0, 2.94126393, 2.0], [2.0, 3.0, 4.6348889, 3.0]])
-    assert list(clusters) == [1, 2, 3]
-    opt.update({"n_clusters": 2})
-    assert list(classify(opt, ref_golden_distmat)[1]) == [1, 1, 2]
+    if _engine.device_count() == 0:
+        with pytest.raises(_engine.EngineError):
+            classify(opt, ref_golden_distmat)
+    assert linkage(ref_golden_distmat, "median").tobytes() == hcl.linkage(ref_golden_distmat, "median").tobytes()
+    with pytest.raises(ValueError, match="condensed"):
+        linkage(np.zeros(4), "average")
 
 
 def test_classify_consumers_check_arguments_and_fail_loudly_without_a_gpu():
