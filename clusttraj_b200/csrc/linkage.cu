@@ -7,8 +7,8 @@
 // included).  centroid / median (SciPy's generic priority-queue algorithm) stay on the host.
 //
 // The algorithm is a chain of dependent steps, each a pass over ONE row of the matrix (M entries): "nearest live cluster
-// of the chain tip" (<= 3 M of them), "Lance-Williams update of the merged cluster's row" (M - 1 of them), or one Prim
-// step.  A step is one launch of linkage_step_kernel over the whole GPU (the row is spread over up to 148 CTAs so that
+// of the chain tip" (<= 3 M of them; the Lance-Williams update of the row of a cluster merged in the step before rides
+// in the same pass, the one entry the two share being handed over in registers), or one Prim step.  A step is one launch of linkage_step_kernel over the whole GPU (the row is spread over up to 148 CTAs so that
 // its column part, one 32-byte sector per entry in the condensed layout, is fetched in one round of memory latency); the
 // last CTA to finish (ticket counter) folds the per-CTA partial results and advances the state machine in device
 // memory, so the host never reads anything back between steps: it replays a CUDA graph of identical step launches until
@@ -26,17 +26,19 @@
 namespace ct {
 
 enum { LK_SINGLE = 0, LK_COMPLETE = 1, LK_AVERAGE = 2, LK_WARD = 5, LK_WEIGHTED = 6 };  // SciPy's method codes
-enum { ACT_SCAN = 0, ACT_UPDATE = 1, ACT_DONE = 2, ACT_PRIM = 3 };
+enum { ACT_SCAN = 0, ACT_DONE = 2, ACT_PRIM = 3 };
 constexpr int LK_THREADS = 256;
 constexpr int LK_NONE = 0x7fffffff;
 
 struct LinkState {
     int action;
-    int x, y;        // scan: x = chain tip, y = SciPy's loop variable y (persists); update: x dropped, y kept
+    int x, y;        // x = chain tip to scan from, y = SciPy's loop variable y (persists)
     int prev;        // chain element under the tip, or -1
     int clen, k;     // chain length, merges recorded
-    int nx, ny;
-    double dxy;      // distance of the merge being applied
+    int upd;         // 1: the merge (a, b) decided in the step before still has to be applied to column b
+    int a, b, na, nb;
+    int first_live;  // lowest live slot (where SciPy restarts an emptied chain)
+    double dxy;      // distance of that merge
     double dprev;    // D[x, prev] picked up during the scan
     unsigned int ticket;
     int steps;       // step launches that did work
@@ -97,43 +99,54 @@ __global__ void __launch_bounds__(LK_THREADS) linkage_step_kernel(LinkState* __r
     __shared__ double sd[LK_THREADS / 32];
     __shared__ int si[LK_THREADS / 32];
     __shared__ bool last;
+    const int gtid = blockIdx.x * LK_THREADS + threadIdx.x, gthreads = gridDim.x * LK_THREADS;
+    int sz = gtid < M ? size[gtid] : 0;   // does not depend on the state: in flight while the state arrives
     if (threadIdx.x == 0) s = *st;
     __syncthreads();
     const int action = s.action;
     if (action == ACT_DONE) return;
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
-    const int gtid = blockIdx.x * LK_THREADS + threadIdx.x, gthreads = gridDim.x * LK_THREADS;
     const int x = s.x;
     double bd = INF;
     int bi = LK_NONE;
     if (action == ACT_SCAN) {
-        const int prev = s.prev;
+        const int prev = s.prev, upd = s.upd, a = s.a, b = s.b, na = s.na, nb = s.nb;
+        const double dxy = s.dxy;
         for (int i = gtid; i < M; i += gthreads) {
-            const int sz = size[i];
-            const double d = i != x ? D[cidx(M, x, i)] : INF;
-            if (i == prev) { st->dprev = d; __threadfence(); }
-            if (sz != 0 && d < bd) { bd = d; bi = i; }
+            if (i != gtid) sz = size[i];
+            const bool live = sz != 0;
+            double cd = INF;
+            int ci = i;
+            bool has = false;
+            if (upd) {
+                if (live && i != b) {
+                    // Lance-Williams update of D[i, b]; when the tip is b itself these ARE the scanned values, and the
+                    // tip's own entry is the candidate "b" of its scan
+                    const long long ib = cidx(M, i, b);
+                    const double dn = lw_update(method, D[cidx(M, i, a)], D[ib], dxy, na, nb, sz);
+                    D[ib] = dn;
+                    if (x == b) { cd = dn; has = true; }
+                    else if (i == x) { cd = dn; ci = b; has = true; }
+                }
+                if (x != b && live && i != x && i != b) { cd = D[cidx(M, x, i)]; has = true; }
+            } else if (live && i != x) {
+                cd = D[cidx(M, x, i)];
+                has = true;
+            }
+            if (has) {
+                if (ci == prev) { st->dprev = cd; __threadfence(); }
+                if (cd < bd || (cd == bd && ci < bi)) { bd = cd; bi = ci; }
+            }
         }
-    } else if (action == ACT_PRIM) {
+    } else {  // ACT_PRIM
         for (int i = gtid; i < M; i += gthreads) {
-            if (size[i] == 0) continue;  // already in the tree
+            if (i != gtid) sz = size[i];
+            if (sz == 0) continue;  // already in the tree
             const double d = D[cidx(M, x, i)];
             double dm = dmin[i];
             if (dm > d) { dm = d; dmin[i] = d; }
             if (dm < bd) { bd = dm; bi = i; }
         }
-    } else {  // ACT_UPDATE: row of the merged cluster (slot y); bi collects the lowest live slot for an emptied chain
-        const int y = s.y, nx = s.nx, ny = s.ny;
-        const double dxy = s.dxy;
-        for (int i = gtid; i < M; i += gthreads) {
-            const int ni = size[i];
-            if (ni == 0) continue;
-            if (bi == LK_NONE) bi = i;
-            if (i == y) continue;
-            const long long iy = cidx(M, i, y);
-            D[iy] = lw_update(method, D[cidx(M, i, x)], D[iy], dxy, nx, ny, ni);
-        }
-        bd = 0.0;  // all partials compare equal: the index decides
     }
     block_min_pair(bd, bi, sd, si);
     if (threadIdx.x == 0) {
@@ -157,6 +170,7 @@ __global__ void __launch_bounds__(LK_THREADS) linkage_step_kernel(LinkState* __r
     LinkState n = s;
     n.ticket = 0;
     n.steps = s.steps + 1;
+    n.upd = 0;
     if (action == ACT_SCAN) {
         int y = s.y;
         double cur = INF;
@@ -164,27 +178,28 @@ __global__ void __launch_bounds__(LK_THREADS) linkage_step_kernel(LinkState* __r
         if (bi != LK_NONE && bd < cur) { cur = bd; y = bi; }
         n.y = y;
         if (s.clen > 1 && y == s.prev) {
-            // reciprocal nearest neighbours: merge, the new cluster lives in the higher slot
+            // reciprocal nearest neighbours: merge, the new cluster lives in the higher slot; its row is updated by the
+            // next step, which also scans from the new chain tip
             const int a = x < y ? x : y, b = x < y ? y : x;
             const int na = size[a], nb = size[b];
             double* z = Zraw + 4 * (size_t)s.k;
             z[0] = (double)a; z[1] = (double)b; z[2] = cur; z[3] = (double)(na + nb);
             size[a] = 0; size[b] = na + nb;
-            n.clen = s.clen - 2;
-            n.action = ACT_UPDATE; n.x = a; n.y = b; n.nx = na; n.ny = nb; n.dxy = cur;
+            n.k = s.k + 1;
+            if (n.k == M - 1) n.action = ACT_DONE;
+            else {
+                n.upd = 1; n.a = a; n.b = b; n.na = na; n.nb = nb; n.dxy = cur;
+                int f = s.first_live;
+                if (a == f) { do ++f; while (size[f] == 0); }
+                n.first_live = f;
+                n.clen = s.clen - 2;
+                if (n.clen == 0) { chain[0] = f; n.clen = 1; n.x = f; n.prev = -1; }
+                else { n.x = chain[n.clen - 1]; n.prev = n.clen > 1 ? chain[n.clen - 2] : -1; }
+            }
         } else {
             chain[s.clen] = y;
             n.clen = s.clen + 1;
             n.prev = x; n.x = y;
-        }
-    } else if (action == ACT_UPDATE) {
-        n.k = s.k + 1;
-        if (n.k == M - 1) n.action = ACT_DONE;
-        else {
-            n.action = ACT_SCAN;
-            n.y = s.y;
-            if (s.clen == 0) { chain[0] = bi; n.clen = 1; n.x = bi; n.prev = -1; }
-            else { n.x = chain[s.clen - 1]; n.prev = s.clen > 1 ? chain[s.clen - 2] : -1; }
         }
     } else {  // ACT_PRIM
         const int y = bi != LK_NONE ? bi : s.y;
@@ -197,7 +212,7 @@ __global__ void __launch_bounds__(LK_THREADS) linkage_step_kernel(LinkState* __r
     *st = n;
 }
 
-__global__ void linkage_init_kernel(LinkState* st, int* size, double* dmin, int M, int method) {
+__global__ void linkage_init_kernel(LinkState* st, int* size, int* chain, double* dmin, int M, int method) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < M) {
         size[i] = (method == LK_SINGLE && i == 0) ? 0 : 1;
@@ -206,7 +221,8 @@ __global__ void linkage_init_kernel(LinkState* st, int* size, double* dmin, int 
     if (i == 0) {
         LinkState n{};
         n.action = M < 2 ? ACT_DONE : (method == LK_SINGLE ? ACT_PRIM : ACT_SCAN);
-        n.x = 0; n.y = 0; n.prev = -1; n.clen = 1; n.k = 0;
+        n.x = 0; n.y = 0; n.prev = -1; n.clen = 1; n.k = 0; n.first_live = 0;
+        chain[0] = 0;
         *st = n;
     }
 }
@@ -231,11 +247,11 @@ cudaError_t run_linkage(double* D, int M, int method, unsigned char* scratch, in
     int grid = (M + LK_THREADS - 1) / LK_THREADS;
     if (grid > sm_count) grid = sm_count;
     if (grid < 1) grid = 1;
-    linkage_init_kernel<<<(M + 255) / 256, 256, 0, stream>>>(st, size, dmin, M, method);
+    linkage_init_kernel<<<(M + 255) / 256, 256, 0, stream>>>(st, size, chain, dmin, M, method);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     // a graph of identical step launches, replayed until the state machine reports "done"
-    const long long max_steps = 4LL * M + 8;
+    const long long max_steps = 3LL * M + 8;
     const int batch = (int)std::min<long long>(max_steps, 2048);
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
@@ -256,7 +272,7 @@ cudaError_t run_linkage(double* D, int M, int method, unsigned char* scratch, in
     cudaGraphExecDestroy(exec);
     cudaGraphDestroy(graph);
     if (rc != cudaSuccess) return rc;
-    if (!done) return cudaErrorUnknown;  // cannot happen: the chain algorithm needs at most 4 M steps
+    if (!done) return cudaErrorUnknown;  // cannot happen: the chain algorithm needs at most 3 M scans
     int steps = 0;
     if ((rc = cudaMemcpyAsync(&steps, &st->steps, sizeof(int), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return rc;
     if (M > 1 && (rc = cudaMemcpyAsync(zraw_host, Zraw, sizeof(double) * 4 * (size_t)(M - 1), cudaMemcpyDeviceToHost, stream)) != cudaSuccess)
