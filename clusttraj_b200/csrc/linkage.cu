@@ -39,7 +39,6 @@ struct LinkState {
     int a, b, na, nb;
     int first_live;  // lowest live slot (where SciPy restarts an emptied chain)
     double dxy;      // distance of that merge
-    double dprev;    // D[x, prev] picked up during the scan
     unsigned int ticket;
     int steps;       // step launches that did work
 };
@@ -107,10 +106,20 @@ __global__ void __launch_bounds__(LK_THREADS) linkage_step_kernel(LinkState* __r
     if (action == ACT_DONE) return;
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     const int x = s.x;
+    // what the state machine will need if this scan ends in a merge (the partner can only be the previous chain
+    // element): fetched now, alongside the row, instead of as dependent loads after the reduction
+    double t_dprev = INF;
+    int t_sx = 0, t_sp = 0, t_c3 = -1, t_c4 = -1;
+    if (threadIdx.x == 0 && action == ACT_SCAN && s.clen > 1) {
+        t_dprev = D[cidx(M, x, s.prev)];   // never in the column an update of this step rewrites
+        t_sx = size[x]; t_sp = size[s.prev];
+        if (s.clen >= 3) t_c3 = chain[s.clen - 3];
+        if (s.clen >= 4) t_c4 = chain[s.clen - 4];
+    }
     double bd = INF;
     int bi = LK_NONE;
     if (action == ACT_SCAN) {
-        const int prev = s.prev, upd = s.upd, a = s.a, b = s.b, na = s.na, nb = s.nb;
+        const int upd = s.upd, a = s.a, b = s.b, na = s.na, nb = s.nb;
         const double dxy = s.dxy;
         for (int i = gtid; i < M; i += gthreads) {
             if (i != gtid) sz = size[i];
@@ -133,10 +142,7 @@ __global__ void __launch_bounds__(LK_THREADS) linkage_step_kernel(LinkState* __r
                 cd = D[cidx(M, x, i)];
                 has = true;
             }
-            if (has) {
-                if (ci == prev) { st->dprev = cd; __threadfence(); }
-                if (cd < bd || (cd == bd && ci < bi)) { bd = cd; bi = ci; }
-            }
+            if (has && (cd < bd || (cd == bd && ci < bi))) { bd = cd; bi = ci; }
         }
     } else {  // ACT_PRIM
         for (int i = gtid; i < M; i += gthreads) {
@@ -174,14 +180,14 @@ __global__ void __launch_bounds__(LK_THREADS) linkage_step_kernel(LinkState* __r
     if (action == ACT_SCAN) {
         int y = s.y;
         double cur = INF;
-        if (s.clen > 1) { y = s.prev; cur = __ldcg(&st->dprev); }
+        if (s.clen > 1) { y = s.prev; cur = t_dprev; }
         if (bi != LK_NONE && bd < cur) { cur = bd; y = bi; }
         n.y = y;
         if (s.clen > 1 && y == s.prev) {
             // reciprocal nearest neighbours: merge, the new cluster lives in the higher slot; its row is updated by the
             // next step, which also scans from the new chain tip
             const int a = x < y ? x : y, b = x < y ? y : x;
-            const int na = size[a], nb = size[b];
+            const int na = x < y ? t_sx : t_sp, nb = x < y ? t_sp : t_sx;
             double* z = Zraw + 4 * (size_t)s.k;
             z[0] = (double)a; z[1] = (double)b; z[2] = cur; z[3] = (double)(na + nb);
             size[a] = 0; size[b] = na + nb;
@@ -194,7 +200,7 @@ __global__ void __launch_bounds__(LK_THREADS) linkage_step_kernel(LinkState* __r
                 n.first_live = f;
                 n.clen = s.clen - 2;
                 if (n.clen == 0) { chain[0] = f; n.clen = 1; n.x = f; n.prev = -1; }
-                else { n.x = chain[n.clen - 1]; n.prev = n.clen > 1 ? chain[n.clen - 2] : -1; }
+                else { n.x = t_c3; n.prev = t_c4; }
             }
         } else {
             chain[s.clen] = y;
