@@ -19,7 +19,10 @@
 // use explicitly rounded operations (__dmul_rn ...) so that the compiler cannot contract them into FMAs.
 #include "common.cuh"
 
+#include <cooperative_groups.h>
+
 #include <algorithm>
+#include <cstdlib>
 #include <numeric>
 #include <vector>
 
@@ -64,7 +67,8 @@ __device__ __forceinline__ double lw_update(int method, double dxi, double dyi, 
     }
 }
 
-// lexicographic minimum of (value, index) over the block; the result is valid in thread 0
+// lexicographic minimum of (value, index) over a block of NT threads; the result is valid in thread 0
+template <int NT>
 __device__ __forceinline__ void block_min_pair(double& d, int& i, double* sd, int* si) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -76,16 +80,34 @@ __device__ __forceinline__ void block_min_pair(double& d, int& i, double* sd, in
     if (l == 0) { sd[w] = d; si[w] = i; }
     __syncthreads();
     if (w == 0) {
-        d = l < LK_THREADS / 32 ? sd[l] : __longlong_as_double(0x7ff0000000000000LL);
-        i = l < LK_THREADS / 32 ? si[l] : LK_NONE;
+        d = l < NT / 32 ? sd[l] : __longlong_as_double(0x7ff0000000000000LL);
+        i = l < NT / 32 ? si[l] : LK_NONE;
 #pragma unroll
-        for (int o = 4; o > 0; o >>= 1) {
+        for (int o = NT / 64; o > 0; o >>= 1) {
             const double od = __shfl_xor_sync(0xffffffffu, d, o);
             const int oi = __shfl_xor_sync(0xffffffffu, i, o);
             if (od < d || (od == d && oi < i)) { d = od; i = oi; }
         }
     }
     __syncthreads();
+}
+
+// order-preserving 64-bit key of a double (no NaNs reach the reductions: a NaN distance never wins a '<')
+__device__ __forceinline__ unsigned long long dkey(double d) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(d);
+    return b ^ ((b >> 63) ? ~0ULL : 0x8000000000000000ULL);
+}
+__device__ __forceinline__ double dunkey(unsigned long long k) {
+    return __longlong_as_double((long long)(k ^ ((k >> 63) ? 0x8000000000000000ULL : ~0ULL)));
+}
+// lexicographic warp minimum of (key, index) with three REDUX operations; every lane gets the result
+__device__ __forceinline__ void warp_min_key(unsigned long long& k, int& i) {
+    const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+    const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+    const unsigned mi = __reduce_min_sync(0xffffffffu, (hi == mhi && lo == mlo) ? (unsigned)i : 0xffffffffu);
+    k = ((unsigned long long)mhi << 32) | mlo;
+    i = (int)mi;
 }
 
 // D: working copy of the condensed matrix (NN-chain methods: updated in place; single: read only)
@@ -154,7 +176,7 @@ __global__ void __launch_bounds__(LK_THREADS) linkage_step_kernel(LinkState* __r
             if (dm < bd) { bd = dm; bi = i; }
         }
     }
-    block_min_pair(bd, bi, sd, si);
+    block_min_pair<LK_THREADS>(bd, bi, sd, si);
     if (threadIdx.x == 0) {
         part_d[blockIdx.x] = bd;
         part_i[blockIdx.x] = bi;
@@ -170,7 +192,7 @@ __global__ void __launch_bounds__(LK_THREADS) linkage_step_kernel(LinkState* __r
         const int oi = __ldcg(part_i + b);
         if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
     }
-    block_min_pair(bd, bi, sd, si);
+    block_min_pair<LK_THREADS>(bd, bi, sd, si);
     if (threadIdx.x != 0) return;
     // ---- state machine, one thread ----
     LinkState n = s;
@@ -218,6 +240,171 @@ __global__ void __launch_bounds__(LK_THREADS) linkage_step_kernel(LinkState* __r
     *st = n;
 }
 
+
+// ---- the same state machine as ONE persistent kernel on a single thread-block cluster ------------------------------
+// For the sizes clusttraj meets (up to ~10^5 frames) a step is bound by a handful of dependent memory round trips, not
+// by bandwidth, so the fastest layout keeps everything that is not the matrix on chip: a cluster of 8 or 16 CTAs x 1024
+// threads covers the row, each CTA reduces its part, ONE hardware cluster barrier per step publishes the partial
+// results (read through distributed shared memory) together with the global writes of the step, and every CTA
+// advances its own replica of the state machine (identical inputs -> identical decisions; CTA 0 alone writes Z, the
+// chain and the cluster sizes).  No launches, tickets or state reloads between steps.  What CTA 0 wrote in step n is
+// only guaranteed visible to the others after the barrier of step n + 1; the replicas bridge that one step from their
+// own state (the merge just decided patches size[a], size[b]; chain entries are first read two steps after they are
+// written).  The matrix, the sizes and the chain are read with ld.global.cg (L1 is not coherent across the CTAs).
+constexpr int LC_THREADS = 1024;
+
+__global__ void __launch_bounds__(LC_THREADS, 1) linkage_cluster_kernel(LinkState* __restrict__ st_out, double* __restrict__ D,
+                                                                        int* __restrict__ size, int* __restrict__ chain,
+                                                                        double* __restrict__ Zraw, double* __restrict__ dmin,
+                                                                        int M, int method, long long max_steps) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank(), ncta = (int)cluster.num_blocks();
+    __shared__ LinkState s;
+    __shared__ unsigned long long sk[LC_THREADS / 32];
+    __shared__ int si[LC_THREADS / 32];
+    __shared__ __align__(16) ulonglong2 cpart[2];   // this CTA's partial result {key, index}, double-buffered by step parity
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    if (threadIdx.x == 0) s = *st_out;
+    __syncthreads();
+    const int gtid = rank * LC_THREADS + threadIdx.x, gthreads = ncta * LC_THREADS;
+    int par = 0;
+    for (long long step = 0; step < max_steps; ++step) {
+        const int action = s.action;
+        if (action == ACT_DONE) break;
+        const int x = s.x, upd = s.upd, a = s.a, b = s.b, na = s.na, nb = s.nb;
+        double t_dprev = INF;
+        int t_sx = 0, t_sp = 0, t_c3 = -1, t_c4 = -1;
+        if (threadIdx.x == 0 && action == ACT_SCAN && s.clen > 1) {
+            const int prev = s.prev;
+            t_dprev = __ldcg(D + cidx(M, x, prev));
+            t_sx = __ldcg(size + x); t_sp = __ldcg(size + prev);
+            if (upd) {
+                if (x == a) t_sx = 0; else if (x == b) t_sx = na + nb;
+                if (prev == a) t_sp = 0; else if (prev == b) t_sp = na + nb;
+            }
+            if (s.clen >= 3) t_c3 = __ldcg(chain + s.clen - 3);
+            if (s.clen >= 4) t_c4 = __ldcg(chain + s.clen - 4);
+        }
+        double bd = INF;
+        int bi = LK_NONE;
+        if (action == ACT_SCAN) {
+            const double dxy = s.dxy;
+            for (int i = gtid; i < M; i += gthreads) {
+                // all loads of the entry are issued together (addresses are valid whatever the slot's state): one
+                // memory round trip per step instead of "size, then distance"
+                int sz = __ldcg(size + i);
+                const double dxi = i != x ? __ldcg(D + cidx(M, x, i)) : INF;
+                double dai = 0.0, dbi = 0.0;
+                long long ib = 0;
+                if (upd && i != a && i != b) {
+                    ib = cidx(M, i, b);
+                    dai = __ldcg(D + cidx(M, i, a));
+                    dbi = __ldcg(D + ib);
+                }
+                if (upd) { if (i == a) sz = 0; else if (i == b) sz = na + nb; }
+                const bool live = sz != 0;
+                double cd = INF;
+                int ci = i;
+                bool has = false;
+                if (upd) {
+                    if (live && i != b) {
+                        const double dn = lw_update(method, dai, dbi, dxy, na, nb, sz);
+                        D[ib] = dn;
+                        if (x == b) { cd = dn; has = true; }
+                        else if (i == x) { cd = dn; ci = b; has = true; }
+                    }
+                    if (x != b && live && i != x && i != b) { cd = dxi; has = true; }
+                } else if (live && i != x) {
+                    cd = dxi;
+                    has = true;
+                }
+                if (has && (cd < bd || (cd == bd && ci < bi))) { bd = cd; bi = ci; }
+            }
+        } else {  // ACT_PRIM: x joined the tree in the step before (its flag may not have arrived yet)
+            for (int i = gtid; i < M; i += gthreads) {
+                const int sz = __ldcg(size + i);
+                const double d = i != x ? __ldcg(D + cidx(M, x, i)) : INF;
+                if (i == x || sz == 0) continue;
+                double dm = dmin[i];
+                if (dm > d) { dm = d; dmin[i] = d; }
+                if (dm < bd) { bd = dm; bi = i; }
+            }
+        }
+        // block minimum (REDUX per warp, then over the 32 warp results), published in this CTA's shared memory
+        unsigned long long bk = dkey(bd);
+        warp_min_key(bk, bi);
+        if ((threadIdx.x & 31) == 0) { sk[threadIdx.x >> 5] = bk; si[threadIdx.x >> 5] = bi; }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            bk = sk[threadIdx.x]; bi = si[threadIdx.x];
+            warp_min_key(bk, bi);
+            if (threadIdx.x == 0) cpart[par] = make_ulonglong2(bk, (unsigned long long)(unsigned)bi);
+        }
+        cluster.sync();   // partials (shared) and this step's matrix / bookkeeping writes (global) are now visible cluster-wide
+        if (threadIdx.x < 32) {
+            bk = ~0ULL; bi = LK_NONE;
+            if ((int)threadIdx.x < ncta) {
+                const ulonglong2 r = *cluster.map_shared_rank(&cpart[par], threadIdx.x);
+                bk = r.x; bi = (int)(unsigned)r.y;
+            }
+            warp_min_key(bk, bi);
+            bd = dunkey(bk);
+        }
+        if (threadIdx.x == 0) {
+            const bool writer = rank == 0;
+            LinkState n = s;
+            n.steps = s.steps + 1;
+            n.upd = 0;
+            if (action == ACT_SCAN) {
+                int y = s.y;
+                double cur = INF;
+                if (s.clen > 1) { y = s.prev; cur = t_dprev; }
+                if (bi != LK_NONE && bd < cur) { cur = bd; y = bi; }
+                n.y = y;
+                if (s.clen > 1 && y == s.prev) {
+                    const int ma = x < y ? x : y, mb = x < y ? y : x;
+                    const int mna = x < y ? t_sx : t_sp, mnb = x < y ? t_sp : t_sx;
+                    if (writer) {
+                        double* z = Zraw + 4 * (size_t)s.k;
+                        z[0] = (double)ma; z[1] = (double)mb; z[2] = cur; z[3] = (double)(mna + mnb);
+                        size[ma] = 0; size[mb] = mna + mnb;
+                    }
+                    n.k = s.k + 1;
+                    if (n.k == M - 1) n.action = ACT_DONE;
+                    else {
+                        n.upd = 1; n.a = ma; n.b = mb; n.na = mna; n.nb = mnb; n.dxy = cur;
+                        int f = s.first_live;
+                        if (ma == f) { do ++f; while (f != mb && __ldcg(size + f) == 0); }   // slots in (ma, mb) are stable
+                        n.first_live = f;
+                        n.clen = s.clen - 2;
+                        if (n.clen == 0) { if (writer) chain[0] = f; n.clen = 1; n.x = f; n.prev = -1; }
+                        else { n.x = t_c3; n.prev = t_c4; }
+                    }
+                } else {
+                    if (writer) chain[s.clen] = y;
+                    n.clen = s.clen + 1;
+                    n.prev = x; n.x = y;
+                }
+            } else {
+                const int y = bi != LK_NONE ? bi : s.y;
+                if (writer) {
+                    double* z = Zraw + 4 * (size_t)s.k;
+                    z[0] = (double)x; z[1] = (double)y; z[2] = bd; z[3] = 0.0;
+                    size[y] = 0;
+                }
+                n.x = y; n.y = y; n.k = s.k + 1;
+                if (n.k == M - 1) n.action = ACT_DONE;
+            }
+            s = n;
+        }
+        __syncthreads();
+        par ^= 1;
+    }
+    cluster.sync();   // nobody leaves while a neighbour may still read its shared memory
+    if (rank == 0 && threadIdx.x == 0) *st_out = s;
+}
+
 __global__ void linkage_init_kernel(LinkState* st, int* size, int* chain, double* dmin, int M, int method) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < M) {
@@ -256,8 +443,37 @@ cudaError_t run_linkage(double* D, int M, int method, unsigned char* scratch, in
     linkage_init_kernel<<<(M + 255) / 256, 256, 0, stream>>>(st, size, chain, dmin, M, method);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    // a graph of identical step launches, replayed until the state machine reports "done"
     const long long max_steps = 3LL * M + 8;
+    const char* force = std::getenv("CLUSTTRAJ_B200_LINKAGE");   // "graph" / "cluster": pick a variant (tests, timing)
+    if (!(force && force[0] == 'g')) {
+        // preferred: one persistent kernel on a single cluster (16 CTAs where the GPU allows it, else 8)
+        cudaFuncSetAttribute(linkage_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        for (int ncta = 16; ncta >= 8; ncta >>= 1) {
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = (unsigned)ncta; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3((unsigned)ncta); cfg.blockDim = dim3(LC_THREADS); cfg.stream = stream;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            int nclusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&nclusters, linkage_cluster_kernel, &cfg) != cudaSuccess || nclusters < 1) {
+                cudaGetLastError();
+                continue;
+            }
+            if ((e = cudaLaunchKernelEx(&cfg, linkage_cluster_kernel, st, D, size, chain, Zraw, dmin, M, method, max_steps)) != cudaSuccess)
+                return e;
+            LinkState fin;
+            if ((e = cudaMemcpyAsync(&fin, st, sizeof fin, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
+            if (M > 1 && (e = cudaMemcpyAsync(zraw_host, Zraw, sizeof(double) * 4 * (size_t)(M - 1), cudaMemcpyDeviceToHost, stream)) != cudaSuccess)
+                return e;
+            if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
+            if (fin.action != ACT_DONE) return cudaErrorUnknown;
+            *steps_out = fin.steps;
+            return cudaSuccess;
+        }
+        if (force && force[0] == 'c') return cudaErrorInvalidConfiguration;
+    }
+    // fall-back: a graph of identical step launches over the whole GPU, replayed until the state machine reports "done"
     const int batch = (int)std::min<long long>(max_steps, 2048);
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;

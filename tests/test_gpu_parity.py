@@ -745,13 +745,16 @@ def _linkage_inputs():
     return cases
 
 
+@pytest.mark.parametrize("variant", ["cluster", "graph"])
 @pytest.mark.parametrize("method", LINKAGE_METHODS)
-def test_linkage_is_scipys_linkage_bit_for_bit(method):
+def test_linkage_is_scipys_linkage_bit_for_bit(method, variant, monkeypatch):
     """Z from the GPU == scipy.cluster.hierarchy.linkage(distmat, method): same merges in the same order, identical
-    heights to the last bit, on random, tie-laden, duplicate-laden and constant matrices."""
+    heights to the last bit, on random, tie-laden, duplicate-laden and constant matrices — for the persistent
+    single-cluster kernel (default) and for the whole-GPU step-launch variant."""
     import scipy.cluster.hierarchy as hcl
     from clusttraj_b200.classify import linkage
 
+    monkeypatch.setenv("CLUSTTRAJ_B200_LINKAGE", variant)
     for name, d in _linkage_inputs().items():
         want = hcl.linkage(d, method)
         got = linkage(d, method)

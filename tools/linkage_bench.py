@@ -16,7 +16,7 @@ d = None
 for method in methods:
     Z, st = eng.linkage(M, method)
     Z, st = eng.linkage(M, method)
-    line = f"{method:9s} M={M} gpu {st['kernel_ms']:9.1f} ms  steps {st['launches']}  ({st['kernel_ms'] * 1e3 / st['launches']:.2f} us/step)"
+    line = f"{os.environ.get('CLUSTTRAJ_B200_LINKAGE', 'cluster'):7s} {method:9s} M={M} gpu {st['kernel_ms']:9.1f} ms  steps {st['launches']}  ({st['kernel_ms'] * 1e3 / st['launches']:.2f} us/step)"
     if "--no-cpu" not in sys.argv:
         import scipy.cluster.hierarchy as hcl
         if d is None:
