@@ -33,8 +33,8 @@ cudaError_t launch_consumers(const double* d, long long L, int M, const int* lab
 int consumers_scratch_doubles(int M);
 int consumers_sum_offset(int M);
 size_t linkage_scratch_bytes(int M, int sm_count);
-cudaError_t run_linkage(double* D, int M, int method, unsigned char* scratch, int sm_count, double* zraw_host, int* done_flag,
-                        long long* steps_out, cudaStream_t stream);
+cudaError_t run_linkage(const double* cond, double* work, size_t work_doubles, int M, int method, unsigned char* scratch,
+                        int sm_count, double* zraw_host, int* done_flag, long long* steps_out, cudaStream_t stream);
 void linkage_finish(const double* zraw, int M, double* Z);
 struct PairPlan;
 struct PairPlanHost;
@@ -646,18 +646,22 @@ int ct_linkage(ct_engine* e, const double* distmat, int64_t M, int32_t method, d
                                      "(pass distmat, or call ct_rmsd_rows_device(e, 0, M, ...) first)");
     }
     CT_CUDA(e, cudaEventRecord(e->ev_b, e->s_compute));
-    double* D = e->d_slab;
-    if (method != 0) {  // the chain methods update the matrix: work on a copy, like SciPy (the matrix stays usable)
-        if ((rc = ensure(e, e->d_link, e->link_cap, (size_t)L))) return rc;
-        CT_CUDA(e, cudaMemcpyAsync(e->d_link, e->d_slab, sizeof(double) * (size_t)L, cudaMemcpyDeviceToDevice, e->s_compute));
-        D = e->d_link;
+    // scratch for the matrix the algorithm updates (the matrix itself stays intact, like SciPy's input): the square form
+    // (M x M, persistent cluster kernel) when it fits, else a condensed copy (step-launch variant)
+    {
+        size_t want = (size_t)M * (size_t)M;
+        size_t free_b = 0, total_b = 0;
+        CT_CUDA(e, cudaMemGetInfo(&free_b, &total_b));
+        const size_t have = e->d_link ? e->link_cap * sizeof(double) : 0;
+        if (want * sizeof(double) > free_b + have) want = (size_t)L;
+        if ((rc = ensure(e, e->d_link, e->link_cap, want))) return rc;
     }
     if ((rc = ensure(e, e->d_link_scratch, e->link_scratch_cap, ct::linkage_scratch_bytes((int)M, e->sm_count)))) return rc;
     if (!e->h_link_flag) CT_CUDA(e, cudaHostAlloc((void**)&e->h_link_flag, sizeof(int), cudaHostAllocDefault));
     std::vector<double> zraw(4 * (size_t)(M - 1));
     long long steps = 0;
-    CT_CUDA(e, ct::run_linkage(D, (int)M, method, e->d_link_scratch, e->sm_count, zraw.data(), e->h_link_flag, &steps,
-                               e->s_compute));
+    CT_CUDA(e, ct::run_linkage(e->d_slab, e->d_link, e->link_cap, (int)M, method, e->d_link_scratch, e->sm_count, zraw.data(),
+                               e->h_link_flag, &steps, e->s_compute));
     CT_CUDA(e, cudaEventRecord(e->ev_c, e->s_compute));
     CT_CUDA(e, cudaEventSynchronize(e->ev_c));
     ct::linkage_finish(zraw.data(), (int)M, Z);

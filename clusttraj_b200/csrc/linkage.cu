@@ -251,6 +251,11 @@ __global__ void __launch_bounds__(LK_THREADS) linkage_step_kernel(LinkState* __r
 // only guaranteed visible to the others after the barrier of step n + 1; the replicas bridge that one step from their
 // own state (the merge just decided patches size[a], size[b]; chain entries are first read two steps after they are
 // written).  The matrix, the sizes and the chain are read with ld.global.cg (L1 is not coherent across the CTAs).
+// This kernel works on the SQUARE form of the matrix (M x M, expanded once from the condensed vector by
+// expand_square_kernel): every row it reads — the tip's, and the two rows of a merge — is then one contiguous,
+// coalesced stream with a one-add address per entry, where the condensed layout costs a 32-byte DRAM sector and two
+// 64-bit multiplies per entry of the column part; an update writes the merged cluster's row and (posted, off the
+// critical path) its column, so the square stays symmetric.
 constexpr int LC_THREADS = 1024;
 
 __global__ void __launch_bounds__(LC_THREADS, 1) linkage_cluster_kernel(LinkState* __restrict__ st_out, double* __restrict__ D,
@@ -275,9 +280,10 @@ __global__ void __launch_bounds__(LC_THREADS, 1) linkage_cluster_kernel(LinkStat
         const int x = s.x, upd = s.upd, a = s.a, b = s.b, na = s.na, nb = s.nb;
         double t_dprev = INF;
         int t_sx = 0, t_sp = 0, t_c3 = -1, t_c4 = -1;
+        const double* __restrict__ rowx = D + (size_t)x * M;
         if (threadIdx.x == 0 && action == ACT_SCAN && s.clen > 1) {
             const int prev = s.prev;
-            t_dprev = __ldcg(D + cidx(M, x, prev));
+            t_dprev = __ldcg(rowx + prev);
             t_sx = __ldcg(size + x); t_sp = __ldcg(size + prev);
             if (upd) {
                 if (x == a) t_sx = 0; else if (x == b) t_sx = na + nb;
@@ -290,17 +296,17 @@ __global__ void __launch_bounds__(LC_THREADS, 1) linkage_cluster_kernel(LinkStat
         int bi = LK_NONE;
         if (action == ACT_SCAN) {
             const double dxy = s.dxy;
+            const double* __restrict__ rowa = D + (size_t)(upd ? a : 0) * M;
+            double* __restrict__ rowb = D + (size_t)(upd ? b : 0) * M;
             for (int i = gtid; i < M; i += gthreads) {
                 // all loads of the entry are issued together (addresses are valid whatever the slot's state): one
                 // memory round trip per step instead of "size, then distance"
                 int sz = __ldcg(size + i);
-                const double dxi = i != x ? __ldcg(D + cidx(M, x, i)) : INF;
+                const double dxi = i != x ? __ldcg(rowx + i) : INF;
                 double dai = 0.0, dbi = 0.0;
-                long long ib = 0;
                 if (upd && i != a && i != b) {
-                    ib = cidx(M, i, b);
-                    dai = __ldcg(D + cidx(M, i, a));
-                    dbi = __ldcg(D + ib);
+                    dai = __ldcg(rowa + i);
+                    dbi = __ldcg(rowb + i);
                 }
                 if (upd) { if (i == a) sz = 0; else if (i == b) sz = na + nb; }
                 const bool live = sz != 0;
@@ -310,7 +316,8 @@ __global__ void __launch_bounds__(LC_THREADS, 1) linkage_cluster_kernel(LinkStat
                 if (upd) {
                     if (live && i != b) {
                         const double dn = lw_update(method, dai, dbi, dxy, na, nb, sz);
-                        D[ib] = dn;
+                        rowb[i] = dn;
+                        D[(size_t)i * M + b] = dn;
                         if (x == b) { cd = dn; has = true; }
                         else if (i == x) { cd = dn; ci = b; has = true; }
                     }
@@ -324,7 +331,7 @@ __global__ void __launch_bounds__(LC_THREADS, 1) linkage_cluster_kernel(LinkStat
         } else {  // ACT_PRIM: x joined the tree in the step before (its flag may not have arrived yet)
             for (int i = gtid; i < M; i += gthreads) {
                 const int sz = __ldcg(size + i);
-                const double d = i != x ? __ldcg(D + cidx(M, x, i)) : INF;
+                const double d = i != x ? __ldcg(rowx + i) : INF;
                 if (i == x || sz == 0) continue;
                 double dm = dmin[i];
                 if (dm > d) { dm = d; dmin[i] = d; }
@@ -405,6 +412,14 @@ __global__ void __launch_bounds__(LC_THREADS, 1) linkage_cluster_kernel(LinkStat
     if (rank == 0 && threadIdx.x == 0) *st_out = s;
 }
 
+// square form of the condensed vector (zero diagonal); one block row per matrix row
+__global__ void __launch_bounds__(256) expand_square_kernel(const double* __restrict__ cond, double* __restrict__ sq, int M) {
+    const int r = blockIdx.x;
+    const int c = blockIdx.y * 256 + threadIdx.x;
+    if (c >= M) return;
+    sq[(size_t)r * M + c] = r == c ? 0.0 : cond[cidx(M, r, c)];
+}
+
 __global__ void linkage_init_kernel(LinkState* st, int* size, int* chain, double* dmin, int M, int method) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < M) {
@@ -426,10 +441,14 @@ size_t linkage_scratch_bytes(int M, int sm_count) {
            sizeof(double) * 4 * (size_t)M;
 }
 
-// Runs the clustering on `D` (NN-chain methods overwrite it) and leaves the raw merges in `zraw_host` (pinned or
-// pageable, 4 (M - 1) doubles).  `done_flag` is a pinned int the state's action is copied to between graph replays.
-cudaError_t run_linkage(double* D, int M, int method, unsigned char* scratch, int sm_count, double* zraw_host,
-                        int* done_flag, long long* steps_out, cudaStream_t stream) {
+// Clusters the condensed matrix `cond` (left untouched) and leaves the raw merges in `zraw_host` (pinned or pageable,
+// 4 (M - 1) doubles).  `work` is scratch for the matrix the algorithm updates: M * M doubles select the persistent
+// cluster kernel on the square form, M (M - 1) / 2 the step-launch variant on a condensed copy.  `done_flag` is a pinned
+// int the state's action is copied to between graph replays.
+cudaError_t run_linkage(const double* cond, double* work, size_t work_doubles, int M, int method, unsigned char* scratch,
+                        int sm_count, double* zraw_host, int* done_flag, long long* steps_out, cudaStream_t stream) {
+    const size_t L = (size_t)M * (M - 1) / 2;
+    double* D = nullptr;
     LinkState* st = reinterpret_cast<LinkState*>(scratch);
     int* size = reinterpret_cast<int*>(scratch + 256);
     int* chain = size + M;
@@ -445,8 +464,9 @@ cudaError_t run_linkage(double* D, int M, int method, unsigned char* scratch, in
     if (e != cudaSuccess) return e;
     const long long max_steps = 3LL * M + 8;
     const char* force = std::getenv("CLUSTTRAJ_B200_LINKAGE");   // "graph" / "cluster": pick a variant (tests, timing)
-    if (!(force && force[0] == 'g')) {
+    if (!(force && force[0] == 'g') && work_doubles >= (size_t)M * M) {
         // preferred: one persistent kernel on a single cluster (16 CTAs where the GPU allows it, else 8)
+        D = work;
         cudaFuncSetAttribute(linkage_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         for (int ncta = 16; ncta >= 8; ncta >>= 1) {
             cudaLaunchAttribute attr[1];
@@ -460,6 +480,8 @@ cudaError_t run_linkage(double* D, int M, int method, unsigned char* scratch, in
                 cudaGetLastError();
                 continue;
             }
+            expand_square_kernel<<<dim3(M, (M + 255) / 256), 256, 0, stream>>>(cond, D, M);
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
             if ((e = cudaLaunchKernelEx(&cfg, linkage_cluster_kernel, st, D, size, chain, Zraw, dmin, M, method, max_steps)) != cudaSuccess)
                 return e;
             LinkState fin;
@@ -472,6 +494,13 @@ cudaError_t run_linkage(double* D, int M, int method, unsigned char* scratch, in
             return cudaSuccess;
         }
         if (force && force[0] == 'c') return cudaErrorInvalidConfiguration;
+    }
+    if (force && force[0] == 'c') return cudaErrorInvalidConfiguration;
+    if (method == LK_SINGLE) D = const_cast<double*>(cond);   // Prim only reads
+    else {
+        if (work_doubles < L) return cudaErrorInvalidValue;
+        if ((e = cudaMemcpyAsync(work, cond, sizeof(double) * L, cudaMemcpyDeviceToDevice, stream)) != cudaSuccess) return e;
+        D = work;
     }
     // fall-back: a graph of identical step launches over the whole GPU, replayed until the state machine reports "done"
     const int batch = (int)std::min<long long>(max_steps, 2048);
