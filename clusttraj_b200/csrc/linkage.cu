@@ -257,6 +257,84 @@ __global__ void __launch_bounds__(LK_THREADS) linkage_step_kernel(LinkState* __r
 // 64-bit multiplies per entry of the column part; an update writes the merged cluster's row and (posted, off the
 // critical path) its column, so the square stays symmetric.
 constexpr int LC_THREADS = 1024;
+constexpr int LC_BATCH = 4;   // entries a thread has in flight at once
+
+// One pass over the row of the current step for the entries i = gtid, gtid + gthreads, ...: B entries per thread are
+// fetched together (all their loads in flight at once), then processed.
+template <int B>
+__device__ __forceinline__ void row_pass(const LinkState& s, double* __restrict__ D, const int* __restrict__ size,
+                                         double* __restrict__ dmin, int M, int method, int gtid, int gthreads, double& bd,
+                                         int& bi) {
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    const int action = s.action, x = s.x, upd = s.upd, a = s.a, b = s.b, na = s.na, nb = s.nb;
+    const double* __restrict__ rowx = D + (size_t)x * M;
+    if (action == ACT_SCAN) {
+        const double dxy = s.dxy;
+        const double* __restrict__ rowa = D + (size_t)(upd ? a : 0) * M;
+        double* __restrict__ rowb = D + (size_t)(upd ? b : 0) * M;
+        for (int i0 = gtid; i0 < M; i0 += B * gthreads) {
+            // all loads of a batch of entries are issued together (addresses are valid whatever the slot's state):
+            // one memory round trip per step instead of "size, then distance", entry after entry
+            int sz[B];
+            double dxi[B], dai[B], dbi[B];
+#pragma unroll
+            for (int u = 0; u < B; ++u) {
+                const int i = i0 + u * gthreads;
+                sz[u] = 0; dxi[u] = INF; dai[u] = 0.0; dbi[u] = 0.0;
+                if (i < M) {
+                    sz[u] = __ldcg(size + i);
+                    if (i != x) dxi[u] = __ldcg(rowx + i);
+                    if (upd && i != a && i != b) { dai[u] = __ldcg(rowa + i); dbi[u] = __ldcg(rowb + i); }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < B; ++u) {
+                const int i = i0 + u * gthreads;
+                if (i >= M) break;
+                int szi = sz[u];
+                if (upd) { if (i == a) szi = 0; else if (i == b) szi = na + nb; }
+                const bool live = szi != 0;
+                double cd = INF;
+                int ci = i;
+                bool has = false;
+                if (upd) {
+                    if (live && i != b) {
+                        const double dn = lw_update(method, dai[u], dbi[u], dxy, na, nb, szi);
+                        rowb[i] = dn;
+                        D[(size_t)i * M + b] = dn;
+                        if (x == b) { cd = dn; has = true; }
+                        else if (i == x) { cd = dn; ci = b; has = true; }
+                    }
+                    if (x != b && live && i != x && i != b) { cd = dxi[u]; has = true; }
+                } else if (live && i != x) {
+                    cd = dxi[u];
+                    has = true;
+                }
+                if (has && (cd < bd || (cd == bd && ci < bi))) { bd = cd; bi = ci; }
+            }
+        }
+    } else {  // ACT_PRIM: x joined the tree in the step before (its flag may not have arrived yet)
+        for (int i0 = gtid; i0 < M; i0 += B * gthreads) {
+            int sz[B];
+            double d[B], dm[B];
+#pragma unroll
+            for (int u = 0; u < B; ++u) {
+                const int i = i0 + u * gthreads;
+                sz[u] = 0; d[u] = INF; dm[u] = INF;
+                if (i < M && i != x) { sz[u] = __ldcg(size + i); d[u] = __ldcg(rowx + i); dm[u] = dmin[i]; }
+            }
+#pragma unroll
+            for (int u = 0; u < B; ++u) {
+                const int i = i0 + u * gthreads;
+                if (i >= M) break;
+                if (sz[u] == 0) continue;
+                double m = dm[u];
+                if (m > d[u]) { m = d[u]; dmin[i] = m; }
+                if (m < bd) { bd = m; bi = i; }
+            }
+        }
+    }
+}
 
 __global__ void __launch_bounds__(LC_THREADS, 1) linkage_cluster_kernel(LinkState* __restrict__ st_out, double* __restrict__ D,
                                                                         int* __restrict__ size, int* __restrict__ chain,
@@ -294,57 +372,16 @@ __global__ void __launch_bounds__(LC_THREADS, 1) linkage_cluster_kernel(LinkStat
         }
         double bd = INF;
         int bi = LK_NONE;
-        if (action == ACT_SCAN) {
-            const double dxy = s.dxy;
-            const double* __restrict__ rowa = D + (size_t)(upd ? a : 0) * M;
-            double* __restrict__ rowb = D + (size_t)(upd ? b : 0) * M;
-            for (int i = gtid; i < M; i += gthreads) {
-                // all loads of the entry are issued together (addresses are valid whatever the slot's state): one
-                // memory round trip per step instead of "size, then distance"
-                int sz = __ldcg(size + i);
-                const double dxi = i != x ? __ldcg(rowx + i) : INF;
-                double dai = 0.0, dbi = 0.0;
-                if (upd && i != a && i != b) {
-                    dai = __ldcg(rowa + i);
-                    dbi = __ldcg(rowb + i);
-                }
-                if (upd) { if (i == a) sz = 0; else if (i == b) sz = na + nb; }
-                const bool live = sz != 0;
-                double cd = INF;
-                int ci = i;
-                bool has = false;
-                if (upd) {
-                    if (live && i != b) {
-                        const double dn = lw_update(method, dai, dbi, dxy, na, nb, sz);
-                        rowb[i] = dn;
-                        D[(size_t)i * M + b] = dn;
-                        if (x == b) { cd = dn; has = true; }
-                        else if (i == x) { cd = dn; ci = b; has = true; }
-                    }
-                    if (x != b && live && i != x && i != b) { cd = dxi; has = true; }
-                } else if (live && i != x) {
-                    cd = dxi;
-                    has = true;
-                }
-                if (has && (cd < bd || (cd == bd && ci < bi))) { bd = cd; bi = ci; }
-            }
-        } else {  // ACT_PRIM: x joined the tree in the step before (its flag may not have arrived yet)
-            for (int i = gtid; i < M; i += gthreads) {
-                const int sz = __ldcg(size + i);
-                const double d = i != x ? __ldcg(rowx + i) : INF;
-                if (i == x || sz == 0) continue;
-                double dm = dmin[i];
-                if (dm > d) { dm = d; dmin[i] = d; }
-                if (dm < bd) { bd = dm; bi = i; }
-            }
-        }
+        if (M <= 2 * gthreads) row_pass<1>(s, D, size, dmin, M, method, gtid, gthreads, bd, bi);
+        else row_pass<LC_BATCH>(s, D, size, dmin, M, method, gtid, gthreads, bd, bi);
         // block minimum (REDUX per warp, then over the 32 warp results), published in this CTA's shared memory
         unsigned long long bk = dkey(bd);
         warp_min_key(bk, bi);
         if ((threadIdx.x & 31) == 0) { sk[threadIdx.x >> 5] = bk; si[threadIdx.x >> 5] = bi; }
         __syncthreads();
         if (threadIdx.x < 32) {
-            bk = sk[threadIdx.x]; bi = si[threadIdx.x];
+            bk = threadIdx.x < LC_THREADS / 32 ? sk[threadIdx.x] : ~0ULL;
+            bi = threadIdx.x < LC_THREADS / 32 ? si[threadIdx.x] : LK_NONE;
             warp_min_key(bk, bi);
             if (threadIdx.x == 0) cpart[par] = make_ulonglong2(bk, (unsigned long long)(unsigned)bi);
         }
