@@ -1,6 +1,7 @@
 """Turn the scratch ncu output under gpurun_out/ into the tracked summaries under profiles/.
 
     python tools/make_profiles.py <round-tag> <gram .ncu-rep> [<pair .ncu-rep>|-] [<launch list csv>|-] [<label>]
+    python tools/make_profiles.py <round-tag> --only <.ncu-rep> <name>      (just the summary of one capture)
 
 <label> (default "gram") names the Gram kernel the capture is of: "gram" = FP64 DMMA kernel, "gram_i8" = int8 tcgen05 kernel.
 """
@@ -57,6 +58,9 @@ def summarise(rep, name):
     return ms
 
 
+if sys.argv[2] == "--only":
+    summarise(sys.argv[3], sys.argv[4])
+    sys.exit(0)
 ms = summarise(sys.argv[2], label)
 m = ms[-1]
 traffic = to_bytes(*m["dram__bytes_read.sum"]) + to_bytes(*m["dram__bytes_write.sum"])
