@@ -268,10 +268,27 @@ __device__ __forceinline__ void row_pass(const LinkState& s, double* __restrict_
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     const int action = s.action, x = s.x, upd = s.upd, a = s.a, b = s.b, na = s.na, nb = s.nb;
     const double* __restrict__ rowx = D + (size_t)x * M;
-    if (action == ACT_SCAN) {
+    if (action == ACT_SCAN && !upd) {
+        // plain scan (two steps out of three): nearest live cluster of the tip
+        for (int i0 = gtid; i0 < M; i0 += B * gthreads) {
+            int sz[B];
+            double dxi[B];
+#pragma unroll
+            for (int u = 0; u < B; ++u) {
+                const int i = i0 + u * gthreads;
+                sz[u] = 0; dxi[u] = INF;
+                if (i < M && i != x) { sz[u] = __ldcg(size + i); dxi[u] = __ldcg(rowx + i); }
+            }
+#pragma unroll
+            for (int u = 0; u < B; ++u) {
+                const int i = i0 + u * gthreads;
+                if (sz[u] != 0 && dxi[u] < bd) { bd = dxi[u]; bi = i; }   // ascending i per thread: '<' keeps the lowest index
+            }
+        }
+    } else if (action == ACT_SCAN) {
         const double dxy = s.dxy;
-        const double* __restrict__ rowa = D + (size_t)(upd ? a : 0) * M;
-        double* __restrict__ rowb = D + (size_t)(upd ? b : 0) * M;
+        const double* __restrict__ rowa = D + (size_t)a * M;
+        double* __restrict__ rowb = D + (size_t)b * M;
         for (int i0 = gtid; i0 < M; i0 += B * gthreads) {
             // all loads of a batch of entries are issued together (addresses are valid whatever the slot's state):
             // one memory round trip per step instead of "size, then distance", entry after entry
@@ -284,7 +301,7 @@ __device__ __forceinline__ void row_pass(const LinkState& s, double* __restrict_
                 if (i < M) {
                     sz[u] = __ldcg(size + i);
                     if (i != x) dxi[u] = __ldcg(rowx + i);
-                    if (upd && i != a && i != b) { dai[u] = __ldcg(rowa + i); dbi[u] = __ldcg(rowb + i); }
+                    if (i != a && i != b) { dai[u] = __ldcg(rowa + i); dbi[u] = __ldcg(rowb + i); }
                 }
             }
 #pragma unroll
@@ -292,24 +309,19 @@ __device__ __forceinline__ void row_pass(const LinkState& s, double* __restrict_
                 const int i = i0 + u * gthreads;
                 if (i >= M) break;
                 int szi = sz[u];
-                if (upd) { if (i == a) szi = 0; else if (i == b) szi = na + nb; }
+                if (i == a) szi = 0; else if (i == b) szi = na + nb;
                 const bool live = szi != 0;
                 double cd = INF;
                 int ci = i;
                 bool has = false;
-                if (upd) {
-                    if (live && i != b) {
-                        const double dn = lw_update(method, dai[u], dbi[u], dxy, na, nb, szi);
-                        rowb[i] = dn;
-                        D[(size_t)i * M + b] = dn;
-                        if (x == b) { cd = dn; has = true; }
-                        else if (i == x) { cd = dn; ci = b; has = true; }
-                    }
-                    if (x != b && live && i != x && i != b) { cd = dxi[u]; has = true; }
-                } else if (live && i != x) {
-                    cd = dxi[u];
-                    has = true;
+                if (live && i != b) {
+                    const double dn = lw_update(method, dai[u], dbi[u], dxy, na, nb, szi);
+                    rowb[i] = dn;
+                    D[(size_t)i * M + b] = dn;
+                    if (x == b) { cd = dn; has = true; }
+                    else if (i == x) { cd = dn; ci = b; has = true; }
                 }
+                if (x != b && live && i != x && i != b) { cd = dxi[u]; has = true; }
                 if (has && (cd < bd || (cd == bd && ci < bi))) { bd = cd; bi = ci; }
             }
         }
@@ -502,10 +514,12 @@ cudaError_t run_linkage(const double* cond, double* work, size_t work_doubles, i
     const long long max_steps = 3LL * M + 8;
     const char* force = std::getenv("CLUSTTRAJ_B200_LINKAGE");   // "graph" / "cluster": pick a variant (tests, timing)
     if (!(force && force[0] == 'g') && work_doubles >= (size_t)M * M) {
-        // preferred: one persistent kernel on a single cluster (16 CTAs where the GPU allows it, else 8)
+        // preferred: one persistent kernel on a single cluster (up to 16 CTAs where the GPU allows it, else 8)
         D = work;
         cudaFuncSetAttribute(linkage_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        for (int ncta = 16; ncta >= 8; ncta >>= 1) {
+        int want = 1;   // smallest power of two of CTAs that gives every entry of a row its own thread, at most 16
+        while (want < 16 && want * LC_THREADS < M) want <<= 1;
+        for (int ncta = want; ncta >= (want == 16 ? 8 : want); ncta >>= 1) {
             cudaLaunchAttribute attr[1];
             attr[0].id = cudaLaunchAttributeClusterDimension;
             attr[0].val.clusterDim.x = (unsigned)ncta; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
