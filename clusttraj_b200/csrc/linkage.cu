@@ -375,10 +375,6 @@ __global__ void __launch_bounds__(LC_THREADS, 1) linkage_cluster_kernel(LinkStat
             const int prev = s.prev;
             t_dprev = __ldcg(rowx + prev);
             t_sx = __ldcg(size + x); t_sp = __ldcg(size + prev);
-            if (upd) {
-                if (x == a) t_sx = 0; else if (x == b) t_sx = na + nb;
-                if (prev == a) t_sp = 0; else if (prev == b) t_sp = na + nb;
-            }
             if (s.clen >= 3) t_c3 = __ldcg(chain + s.clen - 3);
             if (s.clen >= 4) t_c4 = __ldcg(chain + s.clen - 4);
         }
@@ -419,6 +415,10 @@ __global__ void __launch_bounds__(LC_THREADS, 1) linkage_cluster_kernel(LinkStat
                 if (bi != LK_NONE && bd < cur) { cur = bd; y = bi; }
                 n.y = y;
                 if (s.clen > 1 && y == s.prev) {
+                    if (upd) {   // the sizes of the merge decided one step ago may not have arrived in memory yet
+                        if (x == a) t_sx = 0; else if (x == b) t_sx = na + nb;
+                        if (y == a) t_sp = 0; else if (y == b) t_sp = na + nb;
+                    }
                     const int ma = x < y ? x : y, mb = x < y ? y : x;
                     const int mna = x < y ? t_sx : t_sp, mnb = x < y ? t_sp : t_sx;
                     if (writer) {
