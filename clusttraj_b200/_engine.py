@@ -120,7 +120,7 @@ def make_opts(no_hydrogen=False, solute_natoms=None, reorder=False, reorder_solv
     o = ct_opts()
     o.no_hydrogen = 1 if no_hydrogen else 0
     o.solute_natoms = int(solute_natoms) if solute_natoms else 0
-    o.reorder_mode = 1 if reorder else 0
+    o.reorder_mode = (2 if reorder in (2, "distance") else 1) if reorder else 0   # 1 hungarian, 2 distance
     o.reorder_solvent_only = 1 if reorder_solvent_only else 0
     o.final_kabsch = 1 if final_kabsch else 0
     o.weight_solute = float(weight_solute) if weight_solute else 0.0

@@ -233,8 +233,8 @@ int ct_load_frames(ct_engine* e, const double* coords, const int32_t* atomic_num
     if (M > (int64_t)1 << 30) return fail(e, CT_ERR_ARG, "ct_load_frames: too many frames");
     if (opts->n_excl < 0 || (opts->n_excl > 0 && !opts->reorder_excl))
         return fail(e, CT_ERR_ARG, "ct_load_frames: bad reorder_excl");
-    if (opts->reorder_mode != 0 && opts->reorder_mode != 1)
-        return fail(e, CT_ERR_UNSUPPORTED, "only reorder_mode 0 (none) and 1 (hungarian) are implemented");
+    if (opts->reorder_mode < 0 || opts->reorder_mode > 2)
+        return fail(e, CT_ERR_UNSUPPORTED, "only reorder_mode 0 (none), 1 (hungarian) and 2 (distance) are implemented");
     if (opts->solute_natoms < 0 || opts->solute_natoms > N)
         return fail(e, CT_ERR_ARG, "ct_load_frames: solute_natoms out of range");
     CT_CUDA(e, cudaSetDevice(e->device));

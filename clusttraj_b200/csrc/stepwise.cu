@@ -26,6 +26,7 @@ struct PairPlan {
     int K;            // kept atoms
     int natoms;       // kept solute atoms (0 without -ns)
     int has_ns, do_reorder, solute_phase, final_direct, weighted, final_kabsch;
+    int by_distance;  // reorder_mode 2: rank matching by distance from the origin instead of the assignment problem
     double w_solute, w_solvent;  // per-atom weights (distmat.py:259-262)
     // element blocks: phase 0 = solute reorder (distmat.py:184-223), phase 1 = main reorder (:231-256)
     int nblocks[2];
@@ -328,6 +329,35 @@ __device__ __forceinline__ void mat3_rmul(double* R, const double* U) {
     for (int t = 0; t < 9; ++t) R[t] = T[t];
 }
 
+// ---- rmsd.reorder_distance (io.py:562-563): within an element block the k-th closest atom to the origin of the
+// reference frame is paired with the k-th closest atom of the moving frame.  Ranks by counting (lanes own atoms, the
+// norms of the block are broadcast from shared memory), equal norms ordered by index; on return c4r[r] is the column
+// matched to row r.  Norms as numpy computes them: sqrt((x*x + y*y) + z*z), every operation rounded on its own.
+__device__ void match_by_norm(int n, const double* Qe, const double* Pe, double* nq, double* np_, int* rank_q, int* inv_p,
+                              int* c4r, int lane) {
+    for (int t = lane; t < n; t += 32) {
+        nq[t] = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(Qe[3 * t], Qe[3 * t]), __dmul_rn(Qe[3 * t + 1], Qe[3 * t + 1])),
+                                     __dmul_rn(Qe[3 * t + 2], Qe[3 * t + 2])));
+        np_[t] = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(Pe[3 * t], Pe[3 * t]), __dmul_rn(Pe[3 * t + 1], Pe[3 * t + 1])),
+                                      __dmul_rn(Pe[3 * t + 2], Pe[3 * t + 2])));
+    }
+    __syncwarp();
+    for (int t = lane; t < n; t += 32) {
+        const double a = nq[t], b = np_[t];
+        int ra = 0, rb = 0;
+        for (int o = 0; o < n; ++o) {
+            const double oa = nq[o], ob = np_[o];
+            ra += (oa < a || (oa == a && o < t)) ? 1 : 0;
+            rb += (ob < b || (ob == b && o < t)) ? 1 : 0;
+        }
+        rank_q[t] = ra;
+        inv_p[rb] = t;
+    }
+    __syncwarp();
+    for (int t = lane; t < n; t += 32) c4r[t] = inv_p[rank_q[t]];
+    __syncwarp();
+}
+
 __device__ int reorder_phase(const PairPlan& pl, int phase, double* W, int* perm, const double* Q, unsigned char* sm,
                              int lane) {
     const int nmax = pl.nmax;
@@ -354,6 +384,10 @@ __device__ int reorder_phase(const PairPlan& pl, int phase, double* W, int* perm
         }
         __syncwarp();
         int st;
+        if (pl.by_distance) {
+            match_by_norm(n, Qe, Pe, u, v, pred, r4c, c4r, lane);
+            st = 0;
+        } else
         switch ((n + 31) >> 5) {
             case 1: st = lsap_warp_reg<1>(n, Qe, Pe, u, pred, r4c, c4r, v, reinterpret_cast<int*>(sh), scanned, lane); break;
             case 2: st = lsap_warp_reg<2>(n, Qe, Pe, u, pred, r4c, c4r, v, reinterpret_cast<int*>(sh), scanned, lane); break;
@@ -574,6 +608,7 @@ int pair_plan_build(PairPlanHost** out, const int32_t* kept_z, int K, int natoms
     p.has_ns = o->solute_natoms != 0;
     p.natoms = p.has_ns ? natoms : 0;
     p.do_reorder = o->reorder_mode != 0;
+    p.by_distance = o->reorder_mode == 2;
     p.solute_phase = p.has_ns && p.do_reorder && !o->reorder_solvent_only;
     p.final_direct = p.has_ns && p.do_reorder && !o->final_kabsch;
     p.weighted = o->weight_solute != 0.0;

@@ -67,7 +67,7 @@ def _opts_from(noh, reorder, reorder_solvent_only, nsatoms, weight_solute, reord
     excl = np.asarray(reorderexcl if reorderexcl is not None else [], dtype=np.int32).ravel()
     if mode == 0:
         excl = excl[:0]  # the reference only reads the exclusions inside `if reorder` blocks
-    return _engine.make_opts(no_hydrogen=bool(noh), solute_natoms=nsatoms, reorder=bool(mode),
+    return _engine.make_opts(no_hydrogen=bool(noh), solute_natoms=nsatoms, reorder=mode,
                              reorder_solvent_only=bool(reorder_solvent_only), final_kabsch=bool(final_kabsch),
                              weight_solute=weight_solute, reorder_excl=excl)
 

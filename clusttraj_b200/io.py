@@ -198,8 +198,8 @@ def configure_runtime(args_in) -> ClustOptions:
         parser.error(f"The method you selected with -m ({args.method}) is not valid.")
     if args.reorder_alg not in REORDER_ALGS:
         parser.error(f"The reorder method you selected with --reorder-method ({args.reorder_alg}) is not valid.")
-    if args.reorder and args.reorder_alg in ("brute", "distance", "qml"):
-        parser.error(f"--reorder-alg {args.reorder_alg} is not implemented by the B200 engine (use hungarian).")
+    if args.reorder and args.reorder_alg in ("brute", "qml"):
+        parser.error(f"--reorder-alg {args.reorder_alg} is not implemented by the B200 engine (use hungarian or distance).")
     if args.clusters_configurations or args.medoids_configurations or args.plot:
         parser.error("-cc / -mc / -p need OpenBabel writers and matplotlib, which are outside the B200 engine.")
     if args.reorder_exclusions and args.no_hydrogen:
@@ -224,6 +224,8 @@ def parse_args(args: argparse.Namespace) -> ClustOptions:
     alg = None
     if args.reorder and args.reorder_alg == "hungarian":
         alg = _reorder.reorder_hungarian  # "inertia-hungarian" binds nothing in the reference either (io.py:559-567)
+    elif args.reorder and args.reorder_alg == "distance":
+        alg = _reorder.reorder_distance   # io.py:562-563
     if not args.input and os.path.exists(args.outputdistmat) and not args.force:
         raise FileExistsError(
             f"File {args.outputdistmat} already exists, specify a new filename with the -od command option or use "

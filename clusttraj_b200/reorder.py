@@ -19,12 +19,20 @@ def reorder_hungarian(ref_atoms, mov_atoms, ref_coords, mov_coords):
         "CPU implementation.  Use clusttraj_b200.distmat (or Engine.pair_values(..., want_perms=True)).")
 
 
-GPU_REORDER_MODES = {reorder_hungarian: 1}
+def reorder_distance(ref_atoms, mov_atoms, ref_coords, mov_coords):
+    """Handle for the per-element reordering by distance from the centroid (``--reorder-alg distance``,
+    rmsd.reorder_distance, bound at io.py:562-563): same calling convention, same GPU-only policy."""
+    raise NotImplementedError(
+        "clusttraj_b200 runs the distance reordering inside its CUDA per-pair kernel; this handle is not a "
+        "CPU implementation.  Use clusttraj_b200.distmat (or Engine.pair_values(..., want_perms=True)).")
+
+
+GPU_REORDER_MODES = {reorder_hungarian: 1, reorder_distance: 2}
 
 
 def reorder_mode_of(callable_or_none):
-    """0 = no reordering, 1 = Hungarian.  Any other callable is rejected loudly (the reference's
-    distance/brute/qml reorders are outside the accelerated path)."""
+    """0 = no reordering, 1 = Hungarian, 2 = distance.  Any other callable is rejected loudly (the reference's
+    brute/qml reorders are outside the accelerated path)."""
     if not callable_or_none:
         return 0
     name = getattr(callable_or_none, "__name__", "")
@@ -32,6 +40,8 @@ def reorder_mode_of(callable_or_none):
         return GPU_REORDER_MODES[callable_or_none]
     if name == "reorder_hungarian":  # e.g. rmsd.reorder_hungarian from a user's own ClustOptions
         return 1
+    if name == "reorder_distance":
+        return 2
     raise NotImplementedError(
         f"reorder algorithm {name or callable_or_none!r} is not implemented by the B200 engine "
-        "(only --reorder-alg hungarian)")
+        "(only --reorder-alg hungarian and distance)")

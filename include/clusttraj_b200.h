@@ -34,7 +34,8 @@ enum ct_status {
 typedef struct ct_opts {
     int32_t no_hydrogen;          /* -n   : drop atoms with atomic number 1 (distmat.py:135-141,150-156) */
     int32_t solute_natoms;        /* -ns  : solute size before the H mask; 0 = off (distmat.py:116-118,134) */
-    int32_t reorder_mode;         /* -e   : 0 = none, 1 = hungarian (io.py:559-561 -> rmsd.reorder_hungarian) */
+    int32_t reorder_mode;         /* -e   : 0 = none, 1 = hungarian (io.py:559-561 -> rmsd.reorder_hungarian),
+                                     2 = distance (io.py:562-563 -> rmsd.reorder_distance) */
     int32_t reorder_solvent_only; /* -rs  : skip the solute reorder block (distmat.py:184) */
     int32_t final_kabsch;         /* --final-kabsch (distmat.py:265,271-275) */
     int32_t n_excl;               /* length of reorder_excl */

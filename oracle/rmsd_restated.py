@@ -107,3 +107,22 @@ def reorder_hungarian(p_atoms, q_atoms, p_coord, q_coord):
         (q_idx,) = np.where(q_atoms == element)
         view[p_idx] = q_idx[hungarian(p_coord[p_idx], q_coord[q_idx])]
     return view
+
+
+def reorder_distance(p_atoms, q_atoms, p_coord, q_coord):
+    """Per-element reordering by distance from the origin (the frames are centred when clusttraj calls it):
+    the k-th closest atom of an element in the reference is paired with the k-th closest atom of that element in
+    the moving frame.  Bound at io.py:562-563 (``--reorder-alg distance``), same call sites as reorder_hungarian.
+
+    Restated from the published rmsd 1.6.x algorithm (np.linalg.norm per atom, np.argsort of both sets, the rank of
+    each reference atom looked up in the moving frame's order).  PARITY UNPINNED: the package is not importable here
+    and the reference's tests never run this mode; equal norms (measure zero) are ordered by index here."""
+    view = np.zeros(np.asarray(q_atoms).shape, dtype=int)
+    for element in np.unique(p_atoms):
+        (p_idx,) = np.where(p_atoms == element)
+        (q_idx,) = np.where(q_atoms == element)
+        a_order = np.argsort(np.linalg.norm(p_coord[p_idx], axis=1), kind="stable")
+        b_order = np.argsort(np.linalg.norm(q_coord[q_idx], axis=1), kind="stable")
+        rank_of_a = np.argsort(a_order, kind="stable")
+        view[p_idx] = q_idx[b_order[rank_of_a]]
+    return view

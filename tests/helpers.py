@@ -6,9 +6,15 @@ from oracle import distmat_restated as O
 from oracle import rmsd_restated as R
 
 
+def _alg(reorder):
+    if not reorder:
+        return None
+    return R.reorder_distance if reorder == "distance" else R.reorder_hungarian
+
+
 def oracle_rows(atoms, coords, rows, noh=False, reorder=False, rs=False, ns=None, ws=None, excl=(), fk=False,
                 n_workers=1):
-    return O.build_distance_matrix(atoms, coords, noh=noh, reorder=R.reorder_hungarian if reorder else None,
+    return O.build_distance_matrix(atoms, coords, noh=noh, reorder=_alg(reorder),
                                    reorder_solvent_only=rs, nsatoms=ns, weight_solute=ws,
                                    reorderexcl=np.asarray(excl, np.int32), final_kabsch=fk, rows=rows,
                                    n_workers=n_workers)
@@ -18,7 +24,7 @@ def oracle_pairs(atoms, coords, pairs, noh=False, reorder=False, rs=False, ns=No
     """values and composite permutations for explicit (i, j) pairs."""
     vals, perms = [], []
     for i, j in pairs:
-        (v, p), = O.distmat_line(i, atoms, coords, noh, R.reorder_hungarian if reorder else None, rs, ns, ws,
+        (v, p), = O.distmat_line(i, atoms, coords, noh, _alg(reorder), rs, ns, ws,
                                  np.asarray(excl, np.int32), fk, columns=[j], return_perm=True)
         vals.append(v)
         perms.append(p)

@@ -191,9 +191,13 @@ def test_fixup_list_overflow_path(golden_dir):
     dict(reorder=True, ns=12, fk=True),
     dict(reorder=True, ns=12, ws=0.6),
     dict(reorder=True, ns=12, noh=True),
+    dict(reorder="distance"),
+    dict(reorder="distance", ns=12),
+    dict(reorder="distance", ns=12, rs=True, fk=True),
+    dict(reorder="distance", ns=12, ws=0.6, excl=(1, 14, 15)),
 ])
 def test_hungarian_permutations_identical(eng, kw):
-    """Identical permutation on non-degenerate Hungarian reorders + value parity."""
+    """Identical permutation on non-degenerate Hungarian reorders (and on --reorder-alg distance) + value parity."""
     from clusttraj_b200.synth import make_solute_solvent
 
     atoms, coords = make_solute_solvent(24, n_solute=12, n_solvent_mol=40, seed=77, box=9.0)
@@ -204,7 +208,7 @@ def test_hungarian_permutations_identical(eng, kw):
     assert np.abs(vals - want_v).max() <= TOL
     assert np.abs(vals - want_v).max() <= 1e-9
     assert (perms == want_p).all()
-    assert st["lsap_steps"] > 0
+    assert (st["lsap_steps"] > 0) == (kw["reorder"] is True)
     full, _ = eng.rmsd_rows(0, 24)
     for (i, j), v in zip(pairs, vals):
         assert full[condensed_index(24, i, j)] == v

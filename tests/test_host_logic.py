@@ -261,3 +261,21 @@ def test_structure_output_host_side(tmp_path, golden_dir):
     with pytest.raises(NotImplementedError):
         bio._writer("pdb", str(tmp_path / "o.pdb"), True)
     assert bio._xyz_titles(os.path.join(golden_dir, "ref_testtraj.xyz")).__len__() == 3
+
+
+def test_reorder_alg_distance_binds_its_handle(tmp_path):
+    """--reorder-alg distance (rmsd.reorder_distance in the reference, io.py:562-563) selects assignment mode 2; brute / qml
+    are refused."""
+    from clusttraj_b200 import reorder
+    from clusttraj_b200.io import configure_runtime
+
+    traj = tmp_path / "t.xyz"
+    traj.write_text("1\n\nC 0 0 0\n")
+    base = [str(traj), "-rmsd", "1.0", "-oc", str(tmp_path / "c.dat"), "-od", str(tmp_path / "d.npy")]
+    opt = configure_runtime(base + ["-e", "--reorder-alg", "distance"])
+    assert opt.reorder_alg is reorder.reorder_distance and reorder.reorder_mode_of(opt.reorder_alg) == 2
+    assert reorder.reorder_mode_of(configure_runtime(base + ["-e"]).reorder_alg) == 1
+    with pytest.raises(SystemExit):
+        configure_runtime(base + ["-e", "--reorder-alg", "brute"])
+    with pytest.raises(NotImplementedError):
+        reorder.reorder_distance(None, None, None, None)
