@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the all-pairs minimum-RMSD hot path (BASELINE.json metric: RMSD pairs/s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg2|cfg3|cfg4|cfg5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg2|cfg3|cfg4|cfg5] [--scaling weak|strong]
 
 One "step" = one pass of the hot path over one synthetic trajectory: centre/pack (K1), the Gram kernel with
 its fused RMSD epilogue (K2: the int8 tcgen05 kernel by default, the FP64 DMMA kernel with
@@ -194,7 +194,9 @@ def run_b200_arm(args, rank, world, local_rank):
 
     name = args.workload
     M0, _, kw, desc = WORKLOADS[name]
-    M = int(round(M0 * np.sqrt(world)))  # weak scaling: every GPU keeps the single-GPU pair count
+    # weak scaling (default): every GPU keeps the single-GPU pair count; --scaling strong: the named matrix itself is
+    # sharded over the GPUs (BASELINE config 5 = the 100k x 300 matrix on 8 GPUs)
+    M = M0 if args.scaling == "strong" else int(round(M0 * np.sqrt(world)))
     atoms, coords = make_workload(name, M)
     N = coords.shape[1]
     K = kept_atoms(atoms, kw)
@@ -360,9 +362,10 @@ def run_b200_arm(args, rank, world, local_rank):
 
     line = {
         "metric": "rmsd_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{name}: {desc}; M={M} (= {M0} x sqrt(n_gpus)), N={N}, K={K}", "frames": M,
+        "config": {"workload": f"{name}: {desc}; M={M} " + ("(the named size, sharded over the GPUs)" if args.scaling == "strong"
+                                                            else f"(= {M0} x sqrt(n_gpus))") + f", N={N}, K={K}", "frames": M,
                    "atoms": int(N), "kept_atoms": K, "mode": kw, "pairs_total": int(total_pairs),
                    "sharding": "equal-area row slabs, no collective on the data path",
                    "l2": "256 MiB buffer zeroed between steps (L2 flush); the 1.6 GB output also exceeds L2"},
@@ -391,6 +394,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = frames x sqrt(N) (fixed pairs per GPU, default); strong = the named matrix sharded over the GPUs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
