@@ -3,6 +3,8 @@
 20k frames, 80 GB at 100k):
 
   linkage(distmat, method, optimal_ordering)     the hcl.linkage call at classify.py:30,99,127
+  classify_structures_silhouette(clust_opt, ..)  classify.py:11-81 (linkage on the GPU; the silhouette scan itself is the
+                                                 reference's unchanged scikit-learn call on the host)
   classify_structures(clust_opt, distmat)        classify.py:84-110
   classify_structures_nclusters(clust_opt, ...)  classify.py:113-143
   find_medoids_from_clusters(distmat, clusters)  classify.py:146-165
@@ -44,6 +46,42 @@ def linkage(distmat, method="average", optimal_ordering=False):
     if optimal_ordering:
         Z = hcl.optimal_leaf_ordering(Z, distmat)
     return Z
+
+
+def classify_structures_silhouette(clust_opt, distmat, dstep=0.1):
+    """Linkage, then the RMSD threshold with the highest silhouette score among min(Z[:, 2]) + k * dstep
+    (classify.py:11-81): ties keep every tying threshold in clust_opt.optimal_cut and adopt the smallest."""
+    import scipy.cluster.hierarchy as hcl
+    from scipy.spatial.distance import squareform
+    from sklearn import metrics
+
+    Z = linkage(distmat, clust_opt.method, optimal_ordering=clust_opt.opt_order)
+    square = squareform(distmat)
+    best_score, best_t, best_labels = np.float64(-1.0), [], []
+    for t in np.arange(min(Z[:, 2]), max(Z[:, 2]), dstep):
+        labels = hcl.fcluster(Z, t=t, criterion="distance")
+        score = metrics.silhouette_score(square, labels, metric="precomputed")
+        if score == best_score:
+            best_t.append(t)
+            best_labels.append(labels)
+        elif score > best_score:
+            best_score, best_t, best_labels = score, [t], [labels]
+    clusters = best_labels[0]
+    clust_opt.update({"optimal_cut": np.array(best_t)})
+    np.savetxt(clust_opt.out_clust_name, clusters, fmt="%d")
+    return Z, clusters
+
+
+def compute_metrics(distmat, z_matrix, clusters):
+    """(silhouette, Calinski-Harabasz, Davies-Bouldin, cophenetic correlation) of a clustering, as clusttraj/metrics.py:14-45
+    computes them: unchanged scikit-learn / SciPy calls on the host."""
+    from scipy.cluster.hierarchy import cophenet
+    from scipy.spatial.distance import squareform
+    from sklearn.metrics import calinski_harabasz_score, davies_bouldin_score, silhouette_score
+
+    square = squareform(distmat)
+    return (silhouette_score(square, clusters, metric="precomputed"), calinski_harabasz_score(square, clusters),
+            davies_bouldin_score(square, clusters), cophenet(z_matrix, distmat)[0])
 
 
 def classify_structures(clust_opt, distmat):

@@ -5,8 +5,8 @@ import time
 
 import numpy as np
 
-from .classify import (classify_structures, classify_structures_nclusters, find_medoids_from_clusters,
-                       sum_distmat)
+from .classify import (classify_structures, classify_structures_nclusters, classify_structures_silhouette,
+                       compute_metrics, find_medoids_from_clusters, sum_distmat)
 from .distmat import get_distmat
 from .io import Logger, configure_runtime, save_clusters_config, save_medoids_config
 
@@ -14,6 +14,8 @@ from .io import Logger, configure_runtime, save_clusters_config, save_medoids_co
 def classify(clust_opt, distmat):
     """The clustering step as the reference's main dispatches it (main.py:47-57): -nc -> classify_structures_nclusters,
     else classify_structures; the linkage runs on the GPU (clusttraj_b200/classify.py)."""
+    if clust_opt.silhouette_score:
+        return classify_structures_silhouette(clust_opt, distmat)
     if clust_opt.n_clusters is not None:
         return classify_structures_nclusters(clust_opt, distmat)
     return classify_structures(clust_opt, distmat)
@@ -22,15 +24,13 @@ def classify(clust_opt, distmat):
 def main(args=None):
     t0 = time.monotonic()
     clust_opt = configure_runtime(sys.argv[1:] if args is None else args)
-    if clust_opt.silhouette_score:
-        raise SystemExit("-ss (silhouette scan) is downstream of the B200 engine's scope; use -rmsd or -nc")
     t1 = time.monotonic()
     distmat = get_distmat(clust_opt)
     t2 = time.monotonic()
     n = distmat.size
     Logger.logger.info(f"Time spent computing (or loading) RMSD matrix: {t2 - t1:.6f} s "
                        f"({n / max(t2 - t1, 1e-12):.3e} pairs/s)\n")
-    _, clusters = classify(clust_opt, distmat)
+    Z, clusters = classify(clust_opt, distmat)
     Logger.logger.info(f"A total {len(clusters)} snapshots were read and {clusters.max()} cluster(s) was(were) found.\n")
     # superposed structures per cluster / medoids (main.py:67-92,116-137): transforms from the GPU, .xyz written natively
     if clust_opt.save_confs:
@@ -49,6 +49,10 @@ def main(args=None):
         fh.write("\nCluster\tSize\tMedoid\n")
         for c in range(1, int(clusters.max()) + 1):
             fh.write(f"{c}\t{int((clusters == c).sum())}\t{int(medoids[c - 1])}\n")
+        if clust_opt.metrics:   # main.py:140-153
+            ss, ch, db, cpcc = compute_metrics(distmat, Z, clusters)
+            fh.write(f"\nSilhouette score: {ss:.3f}\nCalinski Harabsz score: {ch:.3f}\n"
+                     f"Davies-Bouldin score: {db:.3f}\nCophenetic correlation coefficient: {cpcc:.3f}\n\n")
     if clust_opt.save_medoids:
         save_medoids_config(clust_opt.trajfile, medoids, clust_opt.no_hydrogen, clust_opt.reorder_alg,
                             clust_opt.reorder_solvent_only, clust_opt.solute_natoms, clust_opt.weight_solute,

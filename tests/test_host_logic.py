@@ -279,3 +279,41 @@ def test_reorder_alg_distance_binds_its_handle(tmp_path):
         configure_runtime(base + ["-e", "--reorder-alg", "brute"])
     with pytest.raises(NotImplementedError):
         reorder.reorder_distance(None, None, None, None)
+
+
+def test_silhouette_and_metrics_match_the_unmodified_reference(tmp_path, monkeypatch):
+    """classify_structures_silhouette / compute_metrics (host side: scikit-learn, SciPy) against the unmodified
+    clusttraj/classify.py:11-81 and clusttraj/metrics.py:14-45, imported from /root/reference over the oracle's shims.
+    The linkage itself is the GPU's job (identical Z, test_gpu_parity.py); here it is stubbed with SciPy's."""
+    import logging
+
+    import scipy.cluster.hierarchy as hcl
+    from scipy.spatial.distance import pdist
+
+    ref = "/root/reference"
+    if not os.path.isdir(ref):
+        pytest.skip("the reference is only present in the build container")
+    shims = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "ref_shims")
+    monkeypatch.syspath_prepend(ref)
+    monkeypatch.syspath_prepend(shims)
+    import clusttraj.classify as RC
+    import clusttraj.metrics as RM
+    from clusttraj.io import ClustOptions as RefOptions
+    from clusttraj.io import Logger as RefLogger
+
+    from clusttraj_b200 import classify as C
+    from clusttraj_b200.io import ClustOptions
+
+    RefLogger.logger = logging.getLogger("reference-under-test")
+    monkeypatch.setattr(C, "linkage", lambda d, method, optimal_ordering=False: hcl.linkage(d, method, optimal_ordering=bool(optimal_ordering)))
+    rng = np.random.default_rng(3)
+    x = np.concatenate([rng.normal(c, 0.3, size=(12, 3)) for c in (0, 3, 6)])
+    d = pdist(x)
+    ro = RefOptions(method="average", opt_order=False, out_clust_name=str(tmp_path / "r.dat"), silhouette_score=True)
+    Zr, cr = RC.classify_structures_silhouette(ro, d)
+    mo = ClustOptions(method="average", opt_order=False, out_clust_name=str(tmp_path / "m.dat"), silhouette_score=True)
+    Zm, cm = C.classify_structures_silhouette(mo, d)
+    assert Zm.tobytes() == Zr.tobytes() and (cm == cr).all()
+    assert np.array_equal(np.asarray(mo.optimal_cut), np.asarray(ro.optimal_cut))
+    assert (np.loadtxt(tmp_path / "m.dat", dtype=int) == np.loadtxt(tmp_path / "r.dat", dtype=int)).all()
+    assert np.allclose(C.compute_metrics(d, Zm, cm), RM.compute_metrics(d, Zr, cr), rtol=0, atol=0)
