@@ -96,7 +96,7 @@ __device__ int lsap_warp_reg(int n, const double* Qe, const double* Pe, double* 
             qx[c] = in ? Qe[3 * i] : 0.0; qy[c] = in ? Qe[3 * i + 1] : 0.0; qz[c] = in ? Qe[3 * i + 2] : 0.0;
             bd[c] = INF; bj[c] = -1;
         }
-#pragma unroll 2
+#pragma unroll 1
         for (int j = 0; j < n; ++j) {
             const double x = Pe[3 * j], y = Pe[3 * j + 1], z = Pe[3 * j + 2];
 #pragma unroll
@@ -128,6 +128,7 @@ __device__ int lsap_warp_reg(int n, const double* Qe, const double* Pe, double* 
     for (int c = 0; c < C; ++c) if (lane + 32 * c < n) valid |= 1u << c;
     int steps = 0;   // frontier scans + direct assignments (each stands for the first scan of its row)
     int cur = 0;
+#pragma unroll 1
     while (cur < n) {
         // direct assignments, 32 consecutive rows at a time: a row takes its nearest column when that column is
         // unmatched, its dual has not moved and no earlier row of the batch wants it too; the rows before the first
@@ -155,6 +156,7 @@ __device__ int lsap_warp_reg(int n, const double* Qe, const double* Pe, double* 
         unsigned open = valid;  // owned columns not yet scanned
         int i = cur, sink = -1;
         double minVal = 0.0;
+#pragma unroll 1
         while (sink < 0) {
             const double qx = Qe[3 * i], qy = Qe[3 * i + 1], qz = Qe[3 * i + 2];
             const double mu = minVal - u[i];
@@ -293,8 +295,12 @@ __device__ int lsap_warp(int n, const double* Qe, const double* Pe, double* u, d
     return steps;
 }
 
+// One copy of the 4x4 Jacobi instead of one per call site: the per-pair kernel is bound by instruction fetch before
+// anything else (ncu: "no instruction" is its largest stall), so code size is a first-order quantity here.
+__device__ __noinline__ double kabsch_rotation_shared(const double* s, double* U) { return kabsch_rotation(s, U); }
+
 // rotate the working frame in place: W[k] = W[k] * U (row vector times matrix)
-__device__ __forceinline__ void warp_rotate(double* W, int K, const double* U, int lane) {
+__device__ __noinline__ void warp_rotate(double* W, int K, const double* U, int lane) {
     for (int k = lane; k < K; k += 32) {
         const double x = W[3 * k], y = W[3 * k + 1], z = W[3 * k + 2];
         W[3 * k] = fma(x, U[0], fma(y, U[3], z * U[6]));
@@ -304,7 +310,7 @@ __device__ __forceinline__ void warp_rotate(double* W, int K, const double* U, i
     __syncwarp();
 }
 
-__device__ __forceinline__ void warp_cov(const double* P, const double* Q, int k1, int lane, double* s) {
+__device__ __noinline__ void warp_cov(const double* P, const double* Q, int k1, int lane, double* s) {
 #pragma unroll
     for (int t = 0; t < 9; ++t) s[t] = 0.0;
     for (int k = lane; k < k1; k += 32) {
@@ -358,7 +364,7 @@ __device__ void match_by_norm(int n, const double* Qe, const double* Pe, double*
     __syncwarp();
 }
 
-__device__ int reorder_phase(const PairPlan& pl, int phase, double* W, int* perm, const double* Q, unsigned char* sm,
+__device__ __noinline__ int reorder_phase(const PairPlan& pl, int phase, double* W, int* perm, const double* Q, unsigned char* sm,
                              int lane) {
     const int nmax = pl.nmax;
     double* Qe = reinterpret_cast<double*>(sm);
@@ -389,12 +395,11 @@ __device__ int reorder_phase(const PairPlan& pl, int phase, double* W, int* perm
             st = 0;
         } else
         switch ((n + 31) >> 5) {
-            case 1: st = lsap_warp_reg<1>(n, Qe, Pe, u, pred, r4c, c4r, v, reinterpret_cast<int*>(sh), scanned, lane); break;
-            case 2: st = lsap_warp_reg<2>(n, Qe, Pe, u, pred, r4c, c4r, v, reinterpret_cast<int*>(sh), scanned, lane); break;
-            case 3: st = lsap_warp_reg<3>(n, Qe, Pe, u, pred, r4c, c4r, v, reinterpret_cast<int*>(sh), scanned, lane); break;
-            case 4: st = lsap_warp_reg<4>(n, Qe, Pe, u, pred, r4c, c4r, v, reinterpret_cast<int*>(sh), scanned, lane); break;
-            case 5: case 6: st = lsap_warp_reg<6>(n, Qe, Pe, u, pred, r4c, c4r, v, reinterpret_cast<int*>(sh), scanned, lane); break;
-            case 7: case 8: st = lsap_warp_reg<8>(n, Qe, Pe, u, pred, r4c, c4r, v, reinterpret_cast<int*>(sh), scanned, lane); break;
+            // three register-resident instances (2, 4, 8 columns per lane) rather than one per block size: code size
+            case 1: case 2: st = lsap_warp_reg<2>(n, Qe, Pe, u, pred, r4c, c4r, v, reinterpret_cast<int*>(sh), scanned, lane); break;
+            case 3: case 4: st = lsap_warp_reg<4>(n, Qe, Pe, u, pred, r4c, c4r, v, reinterpret_cast<int*>(sh), scanned, lane); break;
+            case 5: case 6: case 7: case 8:
+                st = lsap_warp_reg<8>(n, Qe, Pe, u, pred, r4c, c4r, v, reinterpret_cast<int*>(sh), scanned, lane); break;
             default: st = lsap_warp(n, Qe, Pe, u, v, sh, pred, r4c, c4r, scanned, lane); break;
         }
         steps += st < 0 ? -st : st;
@@ -436,17 +441,20 @@ __device__ double pair_value_warp(const PairPlan& pl, const double* __restrict__
     __syncwarp();
     // rotation(s) before the main reorder (distmat.py:172-228)
     warp_cov(W, Qg, pl.has_ns ? ns : K, lane, s);
-    kabsch_rotation(s, U);
+    kabsch_rotation_shared(s, U);
     warp_rotate(W, K, U, lane);
     if (XF) mat3_rmul(Rt, U);
-    if (pl.solute_phase) {
-        steps += reorder_phase(pl, 0, W, perm, Qg, sm, lane);
-        warp_cov(W, Qg, ns, lane, s);
-        kabsch_rotation(s, U);
-        warp_rotate(W, K, U, lane);
-        if (XF) mat3_rmul(Rt, U);
+    // phase 0: solute reorder + second solute rotation (distmat.py:184-223); phase 1: main reorder (:231-256).  One call
+    // site in a loop, so that the compiler keeps ONE copy of the solver instead of one clone per constant phase
+    for (int phase = pl.solute_phase ? 0 : 1; phase < 2 && pl.do_reorder; ++phase) {
+        steps += reorder_phase(pl, phase, W, perm, Qg, sm, lane);
+        if (phase == 0) {
+            warp_cov(W, Qg, ns, lane, s);
+            kabsch_rotation_shared(s, U);
+            warp_rotate(W, K, U, lane);
+            if (XF) mat3_rmul(Rt, U);
+        }
     }
-    if (pl.do_reorder) steps += reorder_phase(pl, 1, W, perm, Qg, sm, lane);
 
     // final value (distmat.py:259-275)
     if (pl.final_direct) {
@@ -467,7 +475,7 @@ __device__ double pair_value_warp(const PairPlan& pl, const double* __restrict__
     if (!pl.weighted) {
         // rmsd.kabsch_rmsd: rotate again (no re-centring) and measure directly
         warp_cov(W, Qg, K, lane, s);
-        kabsch_rotation(s, U);
+        kabsch_rotation_shared(s, U);
         if (XF) {
             if (pl.has_ns && pl.do_reorder && pl.final_kabsch) mat3_rmul(Rt, U);   // io.py:743-746
             if (lane == 0) {
@@ -519,7 +527,7 @@ __device__ double pair_value_warp(const PairPlan& pl, const double* __restrict__
     for (int a = 0; a < 3; ++a)
 #pragma unroll
         for (int b = 0; b < 3; ++b) s[a * 3 + b] = (s[a * 3 + b] - cp[a] * cq[b] * iw) * iw;
-    const double lam = kabsch_rotation(s, U);
+    const double lam = kabsch_rotation_shared(s, U);
     const double msd = pqs * iw - 2.0 * lam;
     if (XF) {
         // rmsd.kabsch_weighted(Q, Pr, W) as used at io.py:733-741: x_ref ~ x_mov U + (c_ref - c_mov U), weighted centres
