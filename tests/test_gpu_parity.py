@@ -851,3 +851,24 @@ def test_classify_on_golden_vector(tmp_path, ref_golden_distmat):
     assert list(clusters) == [1, 2, 3]
     opt.update({"n_clusters": 2})
     assert list(classify(opt, ref_golden_distmat)[1]) == [1, 1, 2]
+
+
+def test_linkage_abi_argument_errors():
+    """ct_linkage refuses what SciPy would raise on (fewer than two observations) and what it does not implement
+    (method codes of centroid / median), with the engine's error string instead of an exception across the ABI."""
+    import ctypes as C
+
+    from clusttraj_b200 import _engine
+
+    e = _engine.Engine(0)
+    lib = e._lib
+    Z = np.zeros((4, 4))
+    d = np.arange(10, dtype=np.float64)                 # 5 observations
+    for M, method, zptr, needle in ((1, 2, Z.ctypes.data, "2 <= M"), (5, 3, Z.ctypes.data, "centroid"),
+                                    (5, 4, Z.ctypes.data, "centroid"), (5, 2, None, "Z is NULL")):
+        rc = lib.ct_linkage(e._h, d.ctypes.data, M, method, zptr, None)
+        assert rc != 0 and needle in lib.ct_last_error(e._h).decode(), (M, method)
+    assert lib.ct_linkage(e._h, d.ctypes.data, 5, 2, Z.ctypes.data, None) == 0
+    import scipy.cluster.hierarchy as hcl
+    assert Z.tobytes() == hcl.linkage(d, "average").tobytes()
+    e.close()
