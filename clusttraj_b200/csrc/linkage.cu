@@ -590,7 +590,11 @@ void linkage_finish(const double* zraw, int M, double* Z) {
     const int n = M - 1;
     std::vector<int> order(n);
     std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [zraw](int a, int b) { return zraw[4 * (size_t)a + 2] < zraw[4 * (size_t)b + 2]; });
+    // numpy's order: ascending, NaNs (a ward radicand rounded below zero) last, equal keys in input order
+    std::stable_sort(order.begin(), order.end(), [zraw](int a, int b) {
+        const double za = zraw[4 * (size_t)a + 2], zb = zraw[4 * (size_t)b + 2];
+        return za < zb || (za == za && zb != zb);
+    });
     std::vector<int> parent(2 * (size_t)M - 1), csize(2 * (size_t)M - 1, 0);
     std::iota(parent.begin(), parent.end(), 0);
     std::fill(csize.begin(), csize.begin() + M, 1);
