@@ -8,11 +8,15 @@
 //
 // The algorithm is a chain of dependent steps, each a pass over ONE row of the matrix (M entries): "nearest live cluster
 // of the chain tip" (<= 3 M of them; the Lance-Williams update of the row of a cluster merged in the step before rides
-// in the same pass, the one entry the two share being handed over in registers), or one Prim step.  A step is one launch of linkage_step_kernel over the whole GPU (the row is spread over up to 148 CTAs so that
-// its column part, one 32-byte sector per entry in the condensed layout, is fetched in one round of memory latency); the
-// last CTA to finish (ticket counter) folds the per-CTA partial results and advances the state machine in device
-// memory, so the host never reads anything back between steps: it replays a CUDA graph of identical step launches until
-// the state says "done" (steps after that are no-ops).  Kernel boundaries are the only grid-wide synchronisation.
+// in the same pass, the one entry the two share being handed over in registers), or one Prim step.  8 M bytes per
+// step: a step is bound by memory latency and synchronisation, never by bandwidth.  Two drivers of the same state
+// machine (LinkState, in device memory):
+//   * linkage_cluster_kernel (default): ONE persistent launch on a single thread-block cluster over the square form
+//     of the matrix; one hardware cluster barrier and one distributed-shared-memory fold per step (see its comment);
+//   * linkage_step_kernel (fall-back when the square form does not fit or the cluster cannot be placed): one launch per
+//     step over up to 148 CTAs on the condensed layout; the last CTA to finish (ticket counter) folds the per-CTA
+//     partial results and advances the state machine, so the host never reads anything back between steps: it replays
+//     a CUDA graph of identical step launches until the state says "done" (steps after that are no-ops).
 //
 // Exactness: the step order, the tie rules (previous chain element first, then the lowest index; the merged cluster
 // lives in the higher slot) and the floating-point operation order of the update formulas are SciPy's; the formulas
