@@ -374,8 +374,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) gram_i8_kernel(const OzParams p
                 const int jj = 3 * m + a;
                 const int j = j0 + jj;
                 const double eh = hg[m] - lam[m];
-                const double v = fmax(eh, 0.0) * p.inv_k2;
-                const double y = rsqrt_approx_f64(fmax(v, 1e-300));        // sqrt(v) = v / sqrt(v), one Newton step
+                const double v = (eh > 0.0 ? eh : 0.0) * p.inv_k2;
+                const double y = rsqrt_approx_f64(v + 1e-300);        // sqrt(v) = v / sqrt(v), one Newton step
                 double r = v * y;
                 r = fma(fma(-r, r, v), 0.5 * y, r);
                 const bool ok = (okmask >> m) & 1u;
@@ -685,8 +685,8 @@ __global__ void __launch_bounds__(TsCfg<NWG>::THREADS, 1) gram_i8_ts_kernel(cons
             for (int r = 0; r < 3; ++r) {
                 const int i = pi[r], j = pj[r];
                 const double eh = hg[r] - lam[r];
-                const double v = fmax(eh, 0.0) * p.inv_k2;
-                const double y = rsqrt_approx_f64(fmax(v, 1e-300));        // sqrt(v) = v / sqrt(v), one Newton step
+                const double v = (eh > 0.0 ? eh : 0.0) * p.inv_k2;
+                const double y = rsqrt_approx_f64(v + 1e-300);        // sqrt(v) = v / sqrt(v), one Newton step
                 double rm = v * y;
                 rm = fma(fma(-rm, rm, v), 0.5 * y, rm);
                 const bool ok = (okmask >> r) & 1u;

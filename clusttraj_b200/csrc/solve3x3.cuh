@@ -193,8 +193,10 @@ __device__ __forceinline__ unsigned largest_root_f64(const double (&a)[NP], cons
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
         const double a3 = 3.0 * a[p];
-        const double s = a3 * rsqrt_approx_f64(fmax(a3, 1e-300)) * 1.000001;   // >= sqrt(3a)
-        const double x0 = fmin(half_g[p], s);
+        // '+ 1e-300' instead of fmax, '<' instead of fmin: same values on every input that matters (a3 = 0 stays 0, any
+        // a3 >= 1e-284 is unchanged to the bit) without fmax/fmin's NaN-handling instruction sequences
+        const double s = a3 * rsqrt_approx_f64(a3 + 1e-300) * 1.000001;   // >= sqrt(3a)
+        const double x0 = half_g[p] < s ? half_g[p] : s;
         x[p] = x0 > 0.0 ? x0 : 0.0;   // S == 0 (zero padding): every root is 0 and the iteration stays there
         m8d[p] = -8.0 * d[p];
         m4b[p] = -4.0 * b[p];

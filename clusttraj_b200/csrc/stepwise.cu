@@ -58,7 +58,9 @@ __host__ __device__ inline int pair_smem_per_warp(int nmax) {
 // + two FP64 Newton steps on the residual: within 1 ulp of the correctly rounded value, ~3x cheaper than the IEEE
 // sequence and free of long dependent chains
 __device__ __forceinline__ double cost_sqrt(double d2) {
-    const double yd = rsqrt_approx_f64(fmax(d2, 1e-300)), h = 0.5 * yd;
+    // + 1e-300: keeps d2 = 0 away from rsqrt's infinity and changes no other input by a bit (one DADD where fmax's NaN
+    // handling costs eight instructions per entry)
+    const double yd = rsqrt_approx_f64(d2 + 1e-300), h = 0.5 * yd;
     double s = d2 * yd;
     s = fma(fma(-s, s, d2), h, s);
     s = fma(fma(-s, s, d2), h, s);
