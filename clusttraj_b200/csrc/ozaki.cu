@@ -52,8 +52,9 @@ constexpr int OZ_STAGES = 2;
 constexpr int OZ_THREADS = 384;
 constexpr int OZ_SMEM_BYTES = OZ_STAGES * OZ_STAGE_BYTES + 128;
 constexpr int OZ_TMEM_COLS = 512;
-constexpr int OZ_NPAIR = 3;                  // level pairs (levels 0..5), issued in the order (2,3), (4,5), (0,1): the pair the
-                                             // epilogue waits for last is the cheapest one (3 of the 15 products)
+constexpr int OZ_NPAIR = 3;                  // level pairs (levels 0..5): the A-in-TMEM kernels issue them from the most
+                                             // significant down (their recombination needs that order), the shared-memory
+                                             // kernel in the order (2,3), (4,5), (0,1)
 
 
 // ---- tcgen05 / TMEM PTX ------------------------------------------------------------------------------------
@@ -172,6 +173,14 @@ __device__ __forceinline__ double level_pair(int e, int o) {
 
 // The same for kp <= 128 atoms: every level sum is below 4 * 2^14 * 128 = 2^23 there, so even * 256 + odd still fits
 // 32 bits (|v| < 1.62e9) and the 64-bit multiply-add and sign extension are not needed.
+// the same two conversions WITHOUT the final subtraction: MAGIC + v, exactly (see the folded recombination in the epilogue)
+__device__ __forceinline__ double level_pair_biased(int e, int o) {
+    const long long v = (long long)e * 256 + (long long)o;  // |v| < 2^34
+    return __hiloint2double((int)(v >> 32) + 0x43380000, (int)(unsigned)(v & 0xffffffffLL));   // 2^52 + 2^51 + v
+}
+__device__ __forceinline__ double level_pair32_biased(int e, int o) {
+    return __hiloint2double(0x43300000, (e * 256 + o) ^ (int)0x80000000);   // 2^52 + 2^31 + v
+}
 __device__ __forceinline__ double level_pair32(int e, int o) {
     const int v = e * 256 + o;
     return __hiloint2double(0x43300000, v ^ (int)0x80000000) - 4503601774854144.0;   // 2^52 + 2^31
@@ -530,7 +539,7 @@ __global__ void __launch_bounds__(TsCfg<NWG>::THREADS, 1) gram_i8_ts_kernel(cons
                     if (elect_one()) {
 #pragma unroll
                         for (int lv = 0; lv < 2; ++lv) {
-                            const int q = 2 * ((pr + 1) % OZ_NPAIR) + lv;   // level pairs in the order (2,3), (4,5), (0,1)
+                            const int q = 2 * pr + lv;   // level pairs from the most significant down: (0,1), (2,3), (4,5)
                             const uint32_t d = tmem_base + (uint32_t)(tb * 2 * N + lv * N);
                             const int s_lo = q > 3 ? q - 3 : 0, s_hi = q < 3 ? q : 3;
 #pragma unroll
@@ -566,7 +575,16 @@ __global__ void __launch_bounds__(TsCfg<NWG>::THREADS, 1) gram_i8_ts_kernel(cons
         const bool row_ok = lane < 30;
         const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
         const double s2 = p.qinfo[0];
-        const double sc[OZ_NPAIR] = {s2 * 16777216.0, s2 * 256.0, s2 * 1099511627776.0};   // 2^24, 2^8, 2^40 (issue order)
+        const double sc[OZ_NPAIR] = {s2 * 1099511627776.0, s2 * 16777216.0, s2 * 256.0};   // 2^40, 2^24, 2^8 (issue order)
+        // The int32 level sums enter the FP64 recombination still carrying the bias of the integer -> double trick
+        // (xm = MAGIC + v, exact); the bias is taken out inside the FMAs instead of by a subtraction per value:
+        //   acc = fma(xm_hi, s_hi, -MAGIC (s_hi + s_mid))   = v_hi s_hi - MAGIC s_mid          (exact: 37 significant bits)
+        //   acc = fma(xm_mid, s_mid, acc)                    = v_hi s_hi + v_mid s_mid          (exact: < 2^51 units of s_mid)
+        //   acc = fma(xm_lo, s_lo, acc - MAGIC s_lo)         = the whole element, rounded ONCE  (the subtraction is exact)
+        // (scales are powers of two 2^16 apart, |v| < 2^34.)  4 FP64 operations per value instead of 6, on the pipe the
+        // epilogue is throttled by, and a correctly rounded sum.
+        constexpr double MAGIC = NWG == 4 ? 4503601774854144.0 : 6755399441055744.0;   // 2^52 + 2^31 | 2^52 + 2^51
+        const double kfold0 = -MAGIC * (sc[0] + sc[1]), kfold2 = -MAGIC * sc[2];
         double* wg_scratch = scratch + wg * (OZ_FI * TS_WG_PITCH);
         double* my_row = wg_scratch + (quarter * 10 + g) * TS_WG_PITCH + 3 * a;
         const int last_row = min(p.row_end, p.M - 1);
@@ -617,12 +635,15 @@ __global__ void __launch_bounds__(TsCfg<NWG>::THREADS, 1) gram_i8_ts_kernel(cons
                     tmem_ld8(t0 + N + 16, od2);
                     tmem_wait_ld();
 #pragma unroll
-                    for (int n = 0; n < 16; ++n)
-                        acc[n] = fma(NWG == 4 ? level_pair32((int)ev[n], (int)od[n]) : level_pair((int)ev[n], (int)od[n]), sc[pr], acc[n]);
+                    for (int n = 0; n < 16; ++n) {
+                        const double xm = NWG == 4 ? level_pair32_biased((int)ev[n], (int)od[n]) : level_pair_biased((int)ev[n], (int)od[n]);
+                        acc[n] = fma(xm, sc[pr], pr == 0 ? kfold0 : (pr == 1 ? acc[n] : acc[n] + kfold2));
+                    }
 #pragma unroll
-                    for (int n = 0; n < 8; ++n)
-                        acc[16 + n] = fma(NWG == 4 ? level_pair32((int)ev2[n], (int)od2[n]) : level_pair((int)ev2[n], (int)od2[n]), sc[pr],
-                                          acc[16 + n]);
+                    for (int n = 0; n < 8; ++n) {
+                        const double xm = NWG == 4 ? level_pair32_biased((int)ev2[n], (int)od2[n]) : level_pair_biased((int)ev2[n], (int)od2[n]);
+                        acc[16 + n] = fma(xm, sc[pr], pr == 0 ? kfold0 : (pr == 1 ? acc[16 + n] : acc[16 + n] + kfold2));
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
