@@ -11,7 +11,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "_libclusttraj_b200.so")
-SOURCES = ["engine.cu", "pack.cu", "gram.cu", "ozaki.cu", "consumers.cu", "linkage.cu", "pair.cu", "stepwise.cu"]
+SOURCES = ["engine.cu", "pack.cu", "gram.cu", "ozaki.cu", "consumers.cu", "linkage.cu", "xyzio.cu", "pair.cu", "stepwise.cu"]
 HEADERS = ["common.cuh", "solve3x3.cuh", os.path.join("..", "..", "include", "clusttraj_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -103,6 +103,10 @@ struct ct_engine {
 
 static thread_local std::string g_err;
 
+namespace ct {
+void set_global_error(const std::string& msg) { g_err = msg; }   // for the host-only sources (xyzio.cu)
+}  // namespace ct
+
 #define CT_CUDA(e, call)                                                                                   \
     do {                                                                                                    \
         cudaError_t _c = (call);                                                                            \

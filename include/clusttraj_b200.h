@@ -145,6 +145,15 @@ int ct_matrix_consumers(ct_engine* e, const double* distmat, int64_t M, const in
  * launches (step kernels). */
 int ct_linkage(ct_engine* e, const double* distmat, int64_t M, int32_t method, double* Z, ct_stats* stats);
 
+/* One-shot trajectory ingest, replacing the per-pair OpenBabel parse of clusttraj/distmat.py:56-61,
+ * 123-131 + utils.get_mol_info (utils.py:20-31): a regular multi-frame XYZ file -> atomic_numbers[M][N] and
+ * coords[M][N][3], parsed once by n_threads host threads (0 = all cores).  Call with coords = NULL to learn
+ * *n_frames and *n_atoms, allocate, and call again with capacity_frames >= *n_frames.  Host-only: needs no GPU.
+ * Irregular files (frames of different sizes, blank separator lines, short atom lines, unknown element symbols) are
+ * refused with CT_ERR_ARG and a message in ct_last_error(NULL); clusttraj_b200.xyz then uses its general parser. */
+int ct_read_xyz(const char* path, int64_t* n_frames, int32_t* n_atoms, double* coords, int32_t* atomic_numbers,
+                int64_t capacity_frames, int32_t n_threads);
+
 int ct_get_stats(const ct_engine* e, ct_stats* stats);
 const char* ct_version(void);
 

@@ -349,3 +349,51 @@ def test_folded_level_recombination_is_exact():
                 u = a + k2
                 assert F(u) == F(a) + F(k2)
                 assert fma(xm[2], sc[2], u) == float(v[0] * F(sc[0]) + v[1] * F(sc[1]) + v[2] * F(sc[2]))
+
+
+def test_native_xyz_parser_matches_the_line_parser_bit_for_bit(tmp_path, golden_dir):
+    """ct_read_xyz (parallel native parser in the engine library, host-only) against the general Python line parser:
+    identical atomic numbers and identical float64 bits on the reference's trajectory, on odd but regular formatting
+    (tabs, CRLF, exponents, extra columns, numeric / lower-case / decorated element tokens, no trailing newline), and a
+    clean refusal (None -> fall-back) of irregular files."""
+    from clusttraj_b200 import _engine, xyz
+
+    def slow(path):
+        with open(path) as fh:
+            lines = fh.read().split("\n")
+        while lines and not lines[-1].strip():
+            lines.pop()
+        return xyz._read_xyz_slow(lines, path)
+
+    ref = os.path.join(golden_dir, "ref_testtraj.xyz")
+    a0, c0 = slow(ref)
+    a1, c1 = _engine.read_xyz_native(ref)
+    assert (a0 == a1).all() and c0.tobytes() == c1.tobytes() and a1.dtype == np.int32 and c1.dtype == np.float64
+    a2, c2 = xyz.read_xyz(ref)
+    assert (a0 == a2).all() and c0.tobytes() == c2.tobytes()
+    odd = tmp_path / "odd.xyz"
+    odd.write_bytes(b"3\r\ncomment 1\r\nC\t1.0e-3 -2.5E+01  3 extra\r\n 8 0.1 0.2 0.30000000000000004\r\nhe1 1 2 3\r\n"
+                    b"3\nsecond frame\ncl 123456789.123456789 -0.0 1e-320\nXx 1 2 3\nH 4 5 6")
+    a3, c3 = slow(str(odd))
+    a4, c4 = _engine.read_xyz_native(str(odd))
+    assert (a3 == a4).all() and c3.tobytes() == c4.tobytes()
+    assert a4.tolist() == [[6, 8, 2], [17, 0, 1]]
+    rng = np.random.default_rng(0)
+    big = tmp_path / "big.xyz"
+    coords = rng.normal(scale=20.0, size=(300, 17, 3))
+    xyz.write_xyz(str(big), rng.integers(1, 90, size=17), coords, decimals=9)
+    a5, c5 = slow(str(big))
+    for threads in (0, 1, 3):
+        a6, c6 = _engine.read_xyz_native(str(big), n_threads=threads)
+        assert (a5 == a6).all() and c5.tobytes() == c6.tobytes()
+    for text in ("2\nc\nC 0 0 0\nC 1 1 1\n\n2\nc\nC 0 0 0\nC 1 1 1\n",      # blank separator line
+                 "2\nc\nC 0 0 0\nC 1 1 1\n1\nc\nC 0 0 0\n",                  # frames of different sizes
+                 "1\nc\nC 0 0\n", "1\nc\nQq 0 0 0\n", "1\nc\nC 0 0 1x\n", "x\n"):
+        bad = tmp_path / "bad.xyz"
+        bad.write_text(text)
+        assert _engine.read_xyz_native(str(bad)) is None
+    bad.write_text("1\nc\nQq 0 0 0\n")
+    with pytest.raises(ValueError, match="unknown element"):
+        xyz.read_xyz(str(bad))                                              # the fall-back words the error
+    bad.write_text("2\nc\nC 0 0 0\nC 1 1 1\n\n2\nc\nC 0 0 0\nC 1 1 1\n")
+    assert xyz.read_xyz(str(bad))[1].shape == (2, 2, 3)                     # ... and accepts what the fast path refuses
