@@ -43,7 +43,7 @@ EXPORTS = [
     "ct_version", "ct_device_count", "ct_last_error", "ct_engine_create", "ct_engine_destroy", "ct_host_alloc",
     "ct_host_free", "ct_load_frames", "ct_rows_pairs", "ct_rmsd_rows", "ct_rmsd_rows_device", "ct_copy_slab",
     "ct_rmsd_condensed", "ct_pair_values", "ct_get_stats", "ct_pack_resident", "ct_matrix_consumers",
-    "ct_pair_transforms", "ct_linkage", "ct_read_xyz",
+    "ct_pair_transforms", "ct_linkage", "ct_read_xyz", "ct_format_xyz", "ct_buffer_free",
 ]
 
 _lib = None
@@ -88,6 +88,9 @@ def load_library(build_if_missing=True):
         lib.ct_get_stats.argtypes = [C.c_void_p, P(ct_stats)]
         lib.ct_pack_resident.argtypes = [C.c_void_p, P(ct_stats)]
         lib.ct_pair_transforms.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, P(ct_stats)]
+        lib.ct_format_xyz.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_char_p, P(C.c_void_p), P(C.c_int64), C.c_int32]
+        lib.ct_buffer_free.argtypes = [C.c_void_p]
+        lib.ct_buffer_free.restype = None
         lib.ct_read_xyz.argtypes = [C.c_char_p, P(C.c_int64), P(C.c_int32), C.c_void_p, C.c_void_p, C.c_int64, C.c_int32]
         lib.ct_linkage.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, P(ct_stats)]
         lib.ct_matrix_consumers.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p,
@@ -128,6 +131,29 @@ def read_xyz_native(path, n_threads=0):
     if lib.ct_read_xyz(raw, C.byref(M), C.byref(N), coords.ctypes.data, atoms.ctypes.data, M.value, int(n_threads)) != 0:
         return None
     return atoms, coords
+
+
+def format_xyz_native(atomic_numbers, coords, titles=None, n_threads=0):
+    """bytes: the XYZ text of the frames coords[F, N, 3] (same atoms in every frame) as the reference's OpenBabel writer
+    lays it out, formatted by the library's host threads (ct_format_xyz)."""
+    lib = load_library()
+    z = np.ascontiguousarray(atomic_numbers, dtype=np.int32)
+    x = np.ascontiguousarray(coords, dtype=np.float64)
+    if x.ndim != 3 or x.shape[1:] != (z.size, 3):
+        raise ValueError("coords must be [frames, atoms, 3] for the given atoms")
+    blob = None
+    if titles is not None:
+        if len(titles) != x.shape[0]:
+            raise ValueError("one title per frame")
+        blob = b"".join(t.replace("\x00", "").encode() + b"\x00" for t in titles)
+    ptr, n = C.c_void_p(), C.c_int64()
+    rc = lib.ct_format_xyz(z.ctypes.data, x.ctypes.data, x.shape[0], z.size, blob, C.byref(ptr), C.byref(n), int(n_threads))
+    if rc != 0:
+        raise EngineError("ct_format_xyz: " + (lib.ct_last_error(None) or b"").decode())
+    try:
+        return C.string_at(ptr.value, n.value)
+    finally:
+        lib.ct_buffer_free(ptr)
 
 
 def make_opts(no_hydrogen=False, solute_natoms=None, reorder=False, reorder_solvent_only=False, final_kabsch=False,

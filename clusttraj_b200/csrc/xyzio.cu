@@ -177,4 +177,63 @@ int ct_read_xyz(const char* path, int64_t* n_frames, int32_t* n_atoms, double* c
     return CT_OK;
 }
 
+// Text of F consecutive XYZ frames in the layout the reference emits through pybel.Outputfile("xyz", ...)
+// (clusttraj/io.py:870-899,1000-1015): "<N>\n<title>\n" then "%-3s%15.5f%15.5f%15.5f\n" per atom.  Frames are formatted
+// by n_threads host threads into one malloc'ed buffer (*out, *length bytes; release it with ct_buffer_free).
+int ct_format_xyz(const int32_t* atomic_numbers, const double* coords, int64_t n_frames, int32_t n_atoms, const char* titles,
+                  char** out, int64_t* length, int32_t n_threads) {
+    if (!atomic_numbers || !coords || !out || !length || n_frames < 0 || n_atoms < 1) {
+        ct::set_global_error("ct_format_xyz: bad argument");
+        return CT_ERR_ARG;
+    }
+    for (int k = 0; k < n_atoms; ++k)
+        if (atomic_numbers[k] < 0 || atomic_numbers[k] >= ct::N_SYMBOLS) {
+            ct::set_global_error("ct_format_xyz: atomic number out of range");
+            return CT_ERR_ARG;
+        }
+    std::vector<const char*> title((size_t)n_frames, "");
+    if (titles) {
+        const char* t = titles;
+        for (int64_t f = 0; f < n_frames; ++f) { title[(size_t)f] = t; t += strlen(t) + 1; }
+    }
+    int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    if (nt < 1) nt = 1;
+    if (nt > 64) nt = 64;
+    if ((int64_t)nt > n_frames) nt = n_frames > 0 ? (int)n_frames : 1;
+    std::vector<std::string> part((size_t)nt);
+    auto work = [&](int t) {
+        const int64_t lo = n_frames * t / nt, hi = n_frames * (t + 1) / nt;
+        std::string& s = part[(size_t)t];
+        s.reserve((size_t)(hi - lo) * ((size_t)n_atoms * 49 + 64));
+        char line[1100];
+        for (int64_t f = lo; f < hi; ++f) {
+            s += std::to_string(n_atoms);
+            s += '\n';
+            s += title[(size_t)f];
+            s += '\n';
+            const double* x = coords + (size_t)f * n_atoms * 3;
+            for (int k = 0; k < n_atoms; ++k) {
+                const int len = snprintf(line, sizeof line, "%-3s%15.5f%15.5f%15.5f\n", ct::SYMBOLS[atomic_numbers[k]], x[3 * k],
+                                         x[3 * k + 1], x[3 * k + 2]);
+                s.append(line, (size_t)(len < (int)sizeof line ? len : (int)sizeof line - 1));
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto& th : pool) th.join();
+    size_t total = 0;
+    for (const auto& s : part) total += s.size();
+    char* buf = (char*)malloc(total ? total : 1);
+    if (!buf) { ct::set_global_error("ct_format_xyz: out of memory"); return CT_ERR_ARG; }
+    size_t pos = 0;
+    for (const auto& s : part) { memcpy(buf + pos, s.data(), s.size()); pos += s.size(); }
+    *out = buf;
+    *length = (int64_t)total;
+    return CT_OK;
+}
+
+void ct_buffer_free(void* p) { free(p); }
+
 }  // extern "C"

@@ -303,19 +303,33 @@ def _xyz_titles(trajfile):
 
 
 class _XyzWriter:
-    """Minimal stand-in for pybel.Outputfile("xyz", ...): refuses to overwrite unless asked (like OpenBabel's)."""
+    """Minimal stand-in for pybel.Outputfile("xyz", ...): refuses to overwrite unless asked (like OpenBabel's).  The text is
+    formatted by the engine library's host threads (ct_format_xyz), a frame loop in Python only if it cannot be loaded."""
 
     def __init__(self, path, overwrite):
         if os.path.exists(path) and not overwrite:
             raise IOError(f"{path} already exists. Use 'overwrite=True' to overwrite it.")
-        self.fh = open(path, "w")
+        self.fh = open(path, "wb")
 
-    def write(self, atoms, coords, title):
+    def write_many(self, atoms, frames, titles):
+        frames = np.asarray(frames, dtype=np.float64)
+        if frames.shape[0] == 0:
+            return
+        try:
+            from . import _engine
+            self.fh.write(_engine.format_xyz_native(atoms, frames, list(titles)))
+            return
+        except (ImportError, OSError):
+            pass
         from .xyz import SYMBOLS
 
-        self.fh.write(f"{len(atoms)}\n{title}\n")
-        for z, (x, y, w) in zip(atoms, coords):
-            self.fh.write(f"{SYMBOLS[int(z)]:<3s}{x:15.5f}{y:15.5f}{w:15.5f}\n")
+        for coords, title in zip(frames, titles):
+            self.fh.write(f"{len(atoms)}\n{title}\n".encode())
+            for z, (x, y, w) in zip(atoms, coords):
+                self.fh.write(f"{SYMBOLS[int(z)]:<3s}{x:15.5f}{y:15.5f}{w:15.5f}\n".encode())
+
+    def write(self, atoms, coords, title):
+        self.write_many(atoms, np.asarray(coords)[None], [title])
 
     def close(self):
         self.fh.close()
@@ -343,8 +357,7 @@ def save_clusters_config(trajfile, clusters, distmat, noh, reorder, reorder_solv
                                               weight_solute, reorderexcl, final_kabsch)
         out = _writer(outfmt, f"{outbasename}_{cnum}.{outfmt}", overwrite)
         out.write(atoms, ref, titles[medoid] if titles else "")
-        for m, xyz in zip(members, moved):
-            out.write(atoms, xyz, titles[m] if titles else "")
+        out.write_many(atoms, moved, [titles[m] if titles else "" for m in members])
         out.close()
 
 
@@ -357,6 +370,5 @@ def save_medoids_config(trajfile, medoids, noh, reorder, reorder_solvent_only, n
                                           weight_solute, reorderexcl, final_kabsch)
     out = _writer(outfmt, f"{outbasename}.{outfmt}", overwrite)
     out.write(atoms, ref, titles[medoids[0]] if titles else "")
-    for m, xyz in zip(medoids[1:], moved):
-        out.write(atoms, xyz, titles[m] if titles else "")
+    out.write_many(atoms, moved, [titles[m] if titles else "" for m in medoids[1:]])
     out.close()

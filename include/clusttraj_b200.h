@@ -154,6 +154,14 @@ int ct_linkage(ct_engine* e, const double* distmat, int64_t M, int32_t method, d
 int ct_read_xyz(const char* path, int64_t* n_frames, int32_t* n_atoms, double* coords, int32_t* atomic_numbers,
                 int64_t capacity_frames, int32_t n_threads);
 
+/* Text of n_frames consecutive XYZ frames of the same atoms, in the layout the reference writes through
+ * pybel.Outputfile("xyz") in save_clusters_config / save_medoids_config (io.py:870-899,1000-1015): "<N>\n<title>\n" and
+ * "%-3s%15.5f%15.5f%15.5f\n" per atom.  atomic_numbers[N]; coords[n_frames][N][3]; titles: n_frames NUL-terminated
+ * strings back to back, or NULL.  The buffer is malloc'ed: *out, *length bytes, release with ct_buffer_free.  Host-only. */
+int ct_format_xyz(const int32_t* atomic_numbers, const double* coords, int64_t n_frames, int32_t n_atoms, const char* titles,
+                  char** out, int64_t* length, int32_t n_threads);
+void ct_buffer_free(void* p);
+
 int ct_get_stats(const ct_engine* e, ct_stats* stats);
 const char* ct_version(void);
 

@@ -397,3 +397,33 @@ def test_native_xyz_parser_matches_the_line_parser_bit_for_bit(tmp_path, golden_
         xyz.read_xyz(str(bad))                                              # the fall-back words the error
     bad.write_text("2\nc\nC 0 0 0\nC 1 1 1\n\n2\nc\nC 0 0 0\nC 1 1 1\n")
     assert xyz.read_xyz(str(bad))[1].shape == (2, 2, 3)                     # ... and accepts what the fast path refuses
+
+
+def test_native_xyz_formatter_writes_what_the_python_writer_writes():
+    """ct_format_xyz (the layout OpenBabel's XYZ writer gives the reference, io.py:870-899) against Python's own
+    formatting of the same frames: identical bytes, including -0.0, values that round at the fifth decimal, wide values,
+    non-ASCII titles and thread counts that do not divide the frame count."""
+    from clusttraj_b200 import _engine
+    from clusttraj_b200.xyz import SYMBOLS
+
+    rng = np.random.default_rng(1)
+    z = rng.integers(0, 118, size=23)
+    x = rng.normal(scale=30, size=(37, 23, 3))
+    x[0, 0] = [0.0, -0.0, 123456789.987654321]
+    x[1, 1] = [1e-7, -1e-7, 0.000005]
+    x[2, 2] = [2.5e-6, 0.0000149999, -99999.999995]
+    titles = [f"frame {i} é energy = {i * 0.1:.3f}" for i in range(37)]
+    want = []
+    for c, t in zip(x, titles):
+        want.append(f"{len(z)}\n{t}\n")
+        for a, (p, q, w) in zip(z, c):
+            want.append(f"{SYMBOLS[int(a)]:<3s}{p:15.5f}{q:15.5f}{w:15.5f}\n")
+    want = "".join(want).encode()
+    for threads in (0, 1, 5):
+        assert _engine.format_xyz_native(z, x, titles, n_threads=threads) == want
+    assert _engine.format_xyz_native(z, x[:0], []) == b""
+    assert _engine.format_xyz_native(z, x[:1], None).startswith(b"23\n\n")
+    with pytest.raises(_engine.EngineError, match="atomic number"):
+        _engine.format_xyz_native(np.array([200]), np.zeros((1, 1, 3)))
+    with pytest.raises(ValueError):
+        _engine.format_xyz_native(z, x[:, :5], titles)
