@@ -43,7 +43,7 @@ EXPORTS = [
     "ct_version", "ct_device_count", "ct_last_error", "ct_engine_create", "ct_engine_destroy", "ct_host_alloc",
     "ct_host_free", "ct_load_frames", "ct_rows_pairs", "ct_rmsd_rows", "ct_rmsd_rows_device", "ct_copy_slab",
     "ct_rmsd_condensed", "ct_pair_values", "ct_get_stats", "ct_pack_resident", "ct_matrix_consumers",
-    "ct_pair_transforms", "ct_linkage", "ct_read_xyz", "ct_format_xyz", "ct_buffer_free",
+    "ct_pair_transforms", "ct_linkage", "ct_read_xyz", "ct_format_xyz", "ct_buffer_free", "ct_device_memory",
 ]
 
 _lib = None
@@ -88,6 +88,7 @@ def load_library(build_if_missing=True):
         lib.ct_get_stats.argtypes = [C.c_void_p, P(ct_stats)]
         lib.ct_pack_resident.argtypes = [C.c_void_p, P(ct_stats)]
         lib.ct_pair_transforms.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, P(ct_stats)]
+        lib.ct_device_memory.argtypes = [C.c_void_p, P(C.c_int64), P(C.c_int64)]
         lib.ct_format_xyz.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_char_p, P(C.c_void_p), P(C.c_int64), C.c_int32]
         lib.ct_buffer_free.argtypes = [C.c_void_p]
         lib.ct_buffer_free.restype = None
@@ -226,8 +227,23 @@ class Engine:
         self._check(self._lib.ct_rmsd_rows(self._h, row_begin, row_end, out.ctypes.data, C.byref(st)), "ct_rmsd_rows")
         return out[:n], st.as_dict()
 
+    def free_memory(self):
+        """Free bytes on this engine's GPU."""
+        f, t = C.c_int64(), C.c_int64()
+        self._check(self._lib.ct_device_memory(self._h, C.byref(f), C.byref(t)), "ct_device_memory")
+        return int(f.value)
+
+    # ---- which host array the matrix resident on the GPU corresponds to (so that trusted callers can skip re-uploads) ----
+    def _note_resident(self, array):
+        self._resident_ref = weakref.ref(array) if isinstance(array, np.ndarray) else None
+
+    def _resident_is(self, array):
+        ref = getattr(self, "_resident_ref", None)
+        return ref is not None and ref() is array
+
     def rmsd_rows_device(self, row_begin, row_end):
         """Leaves the slab on the GPU; returns (device pointer, entries, stats)."""
+        self._resident_ref = None
         st = ct_stats()
         ptr = C.c_void_p()
         self._check(self._lib.ct_rmsd_rows_device(self._h, row_begin, row_end, C.byref(ptr), C.byref(st)),
@@ -260,16 +276,21 @@ class Engine:
                                                  C.byref(st)), "ct_pair_transforms")
         return vals, xf[:, :9].reshape(-1, 3, 3).copy(), xf[:, 9:].copy()
 
-    def matrix_consumers(self, n_frames, clusters=None, distmat=None):
+    def matrix_consumers(self, n_frames, clusters=None, distmat=None, trusted=False):
         """(total sum, medoid frame index per cluster, stats) of a condensed matrix: `distmat` (host array) or, with
-        distmat=None, the whole matrix the last rmsd_rows_device(0, M) left on the GPU.  `clusters` = 1-based labels."""
+        distmat=None, the whole matrix the last rmsd_rows_device(0, M) left on the GPU.  `clusters` = 1-based labels.
+        trusted=True: the caller vouches that `distmat` has not been written to since this engine produced / uploaded
+        it, so the copy still resident on the GPU is used instead of another upload."""
         M = int(n_frames)
         ptr = None
         if distmat is not None:
+            given = distmat
             distmat = np.ascontiguousarray(distmat, dtype=np.float64)
             if distmat.shape != (M * (M - 1) // 2,):
                 raise ValueError("distmat must be the condensed vector of n_frames frames")
-            ptr = distmat.ctypes.data
+            if not (trusted and self._resident_is(given)):
+                ptr = distmat.ctypes.data
+                self._note_resident(given if given is distmat else None)
         if clusters is None:
             labels, n_clusters, med = None, 0, None
         else:
@@ -287,18 +308,22 @@ class Engine:
 
     LINKAGE_METHODS = {"single": 0, "complete": 1, "average": 2, "ward": 5, "weighted": 6}   # SciPy's codes
 
-    def linkage(self, n_frames, method="average", distmat=None):
+    def linkage(self, n_frames, method="average", distmat=None, trusted=False):
         """(Z float64[M-1, 4], stats): scipy.cluster.hierarchy.linkage(distmat, method) on the GPU, for `distmat` (host
-        array) or, with distmat=None, the whole matrix the last rmsd_rows_device(0, M) left there."""
+        array) or, with distmat=None, the whole matrix the last rmsd_rows_device(0, M) left there.  trusted: as in
+        matrix_consumers."""
         M = int(n_frames)
         if method not in self.LINKAGE_METHODS:
             raise ValueError(f"linkage method {method!r} does not run on the GPU (single, complete, average, weighted, ward do)")
         ptr = None
         if distmat is not None:
+            given = distmat
             distmat = np.ascontiguousarray(distmat, dtype=np.float64)
             if distmat.shape != (M * (M - 1) // 2,):
                 raise ValueError("distmat must be the condensed vector of n_frames frames")
-            ptr = distmat.ctypes.data
+            if not (trusted and self._resident_is(given)):
+                ptr = distmat.ctypes.data
+                self._note_resident(given if given is distmat else None)
         Z = np.empty((max(M - 1, 0), 4), dtype=np.float64)
         st = ct_stats()
         self._check(self._lib.ct_linkage(self._h, ptr, M, self.LINKAGE_METHODS[method], Z.ctypes.data, C.byref(st)),

@@ -20,6 +20,23 @@ import numpy as np
 from .distmat import _engine_for, visible_devices
 
 
+_trusted_ref = None
+
+
+def trust_resident(distmat):
+    """The caller (clusttraj_b200.main) vouches that it will not write to `distmat` between the calls of this module:
+    the copy an engine call leaves on the GPU is then reused by the next one instead of being uploaded again (1.6 GB
+    at 20k frames).  Without this every function uploads what it is given, like any library function would."""
+    global _trusted_ref
+    import weakref
+
+    _trusted_ref = weakref.ref(distmat) if isinstance(distmat, np.ndarray) else None
+
+
+def _trusted(distmat):
+    return _trusted_ref is not None and _trusted_ref() is distmat
+
+
 def _n_frames(distmat):
     L = int(np.asarray(distmat).shape[0])
     M = int(round((1.0 + np.sqrt(1.0 + 8.0 * L)) / 2.0))
@@ -42,7 +59,7 @@ def linkage(distmat, method="average", optimal_ordering=False):
         return hcl.linkage(distmat, method, optimal_ordering=bool(optimal_ordering))
     M = _n_frames(distmat)
     eng = _engine_for(visible_devices()[0])
-    Z, _ = eng.linkage(M, method, distmat=distmat)
+    Z, _ = eng.linkage(M, method, distmat=distmat, trusted=_trusted(distmat))
     if optimal_ordering:
         Z = hcl.optimal_leaf_ordering(Z, distmat)
     return Z
@@ -115,7 +132,7 @@ def find_medoids_from_clusters(distmat, clusters):
     if clusters.shape != (M,):
         raise ValueError("clusters must hold one label per frame")
     eng = _engine_for(visible_devices()[0])
-    _, medoids, _ = eng.matrix_consumers(M, clusters=clusters, distmat=distmat)
+    _, medoids, _ = eng.matrix_consumers(M, clusters=clusters, distmat=distmat, trusted=_trusted(distmat))
     return medoids.astype(int)
 
 
@@ -123,5 +140,5 @@ def sum_distmat(distmat):
     """Sum of the RMSD matrix (classify.py:168-177)."""
     M = _n_frames(distmat)
     eng = _engine_for(visible_devices()[0])
-    total, _, _ = eng.matrix_consumers(M, clusters=None, distmat=distmat)
+    total, _, _ = eng.matrix_consumers(M, clusters=None, distmat=distmat, trusted=_trusted(distmat))
     return np.float64(total)

@@ -678,6 +678,16 @@ int ct_linkage(ct_engine* e, const double* distmat, int64_t M, int32_t method, d
     return CT_OK;
 }
 
+int ct_device_memory(ct_engine* e, int64_t* free_bytes, int64_t* total_bytes) {
+    if (!e || !free_bytes || !total_bytes) return fail(e, CT_ERR_ARG, "ct_device_memory: NULL argument");
+    CT_CUDA(e, cudaSetDevice(e->device));
+    size_t f = 0, t = 0;
+    CT_CUDA(e, cudaMemGetInfo(&f, &t));
+    *free_bytes = (int64_t)f;
+    *total_bytes = (int64_t)t;
+    return CT_OK;
+}
+
 int ct_get_stats(const ct_engine* e, ct_stats* stats) {
     if (!e || !stats) return CT_ERR_ARG;
     *stats = e->stats;

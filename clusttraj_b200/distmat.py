@@ -101,8 +101,22 @@ def condensed_matrix(atomic_nums, coords, opts, devices=None, out=None, return_s
         res = np.empty(0, dtype=np.float64)
         return (res, []) if return_stats else res
     devices = devices[: max(1, min(len(devices), M - 1))]
+    if out is None and len(devices) == 1:
+        # One GPU, one shot: the matrix is computed into HBM, stays resident there for the consumers that follow
+        # (clusttraj_b200.classify) and is copied into a plain numpy array.  Page-locking 1.6 GB for a single use costs
+        # 0.6-0.7 s, the driver's staged copy into pageable memory 0.35-0.4 s in all (measured at 20k frames).  Matrices
+        # that would not leave room for the clustering's working copy are streamed in chunks instead (below).
+        eng = _engine_for(devices[0])
+        if 8 * total * 4 < eng.free_memory():
+            eng.load_frames(coords, atomic_nums, opts)
+            _, n, st = eng.rmsd_rows_device(0, M)
+            out = eng.copy_slab(0, n)
+            eng._note_resident(out)
+            stats = [dict(st, device=devices[0], rows=(0, M))]
+            return (out, stats) if return_stats else out
     if out is None:
-        out = _engine.pinned_empty(total)
+        # several GPUs stream concurrently into one vector: that needs pinned memory to run at full PCIe rate
+        out = np.empty(total, dtype=np.float64) if len(devices) == 1 else _engine.pinned_empty(total)
     cuts = slab_bounds(M, len(devices))
     stats = [None] * len(devices)
     errors = []

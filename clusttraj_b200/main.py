@@ -6,7 +6,7 @@ import time
 import numpy as np
 
 from .classify import (classify_structures, classify_structures_nclusters, classify_structures_silhouette,
-                       compute_metrics, find_medoids_from_clusters, sum_distmat)
+                       compute_metrics, find_medoids_from_clusters, sum_distmat, trust_resident)
 from .distmat import get_distmat
 from .io import Logger, configure_runtime, save_clusters_config, save_medoids_config
 
@@ -30,6 +30,7 @@ def main(args=None):
     n = distmat.size
     Logger.logger.info(f"Time spent computing (or loading) RMSD matrix: {t2 - t1:.6f} s "
                        f"({n / max(t2 - t1, 1e-12):.3e} pairs/s)\n")
+    trust_resident(distmat)   # nothing below writes to the matrix: one upload serves linkage, sum and medoids
     Z, clusters = classify(clust_opt, distmat)
     Logger.logger.info(f"A total {len(clusters)} snapshots were read and {clusters.max()} cluster(s) was(were) found.\n")
     # superposed structures per cluster / medoids (main.py:67-92,116-137): transforms from the GPU, .xyz written natively

@@ -162,6 +162,9 @@ int ct_format_xyz(const int32_t* atomic_numbers, const double* coords, int64_t n
                   char** out, int64_t* length, int32_t n_threads);
 void ct_buffer_free(void* p);
 
+/* Free / total memory of the engine's GPU (how the host side decides between a device-resident matrix and streaming). */
+int ct_device_memory(ct_engine* e, int64_t* free_bytes, int64_t* total_bytes);
+
 int ct_get_stats(const ct_engine* e, ct_stats* stats);
 const char* ct_version(void);
 

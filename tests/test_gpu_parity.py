@@ -872,3 +872,40 @@ def test_linkage_abi_argument_errors():
     import scipy.cluster.hierarchy as hcl
     assert Z.tobytes() == hcl.linkage(d, "average").tobytes()
     e.close()
+
+
+def test_resident_matrix_is_reused_only_for_the_trusted_array():
+    """One GPU, one shot: the matrix stays resident after condensed_matrix; clusttraj_b200.main vouches (trust_resident)
+    that it does not touch the host copy, and linkage / sum / medoids then skip the 8 L-byte upload.  Any other array —
+    a copy, a modified copy, the same values under another identity — is uploaded like before."""
+    import scipy.cluster.hierarchy as hcl
+
+    from clusttraj_b200 import classify
+    from clusttraj_b200 import distmat as D
+    from clusttraj_b200.synth import make_trajectory
+
+    atoms, coords = make_trajectory(1500, 20, seed=9, n_modes=5)
+    d = D.condensed_matrix(atoms, coords, engine_opts(), devices=[0])
+    assert type(d) is np.ndarray and d.flags.writeable and d.flags.c_contiguous and d.dtype == np.float64
+    want = oracle_rows(atoms, coords, [0, 700, 1498])
+    assert np.abs(np.concatenate([d[:1499], d[condensed_index(1500, 700, 701):condensed_index(1500, 700, 701) + 799],
+                                  d[-1:]]) - want).max() <= 1e-6
+    eng = D._engine_for(0)
+    Z0 = hcl.linkage(d, "average")
+    labels = hcl.fcluster(Z0, 6, criterion="maxclust")
+    classify.trust_resident(d)
+    assert classify.linkage(d, "average").tobytes() == Z0.tobytes()
+    assert eng.stats()["h2d_ms"] < 0.2                                    # nothing was uploaded (9 MB would take ~0.3 ms+)
+    total = classify.sum_distmat(d)
+    assert abs(total - d.sum()) <= 1e-12 * d.sum() and eng.stats()["h2d_ms"] < 0.2
+    med = classify.find_medoids_from_clusters(d, labels)
+    d2 = d.copy()
+    d2[:1499] += 5.0                                                      # frame 0 moved away from everything
+    Z2 = classify.linkage(d2, "average")                                  # not the trusted array: uploaded, honoured
+    assert Z2.tobytes() == hcl.linkage(d2, "average").tobytes() and Z2.tobytes() != Z0.tobytes()
+    assert abs(classify.sum_distmat(d2) - d2.sum()) <= 1e-12 * d2.sum()
+    # the GPU now holds d2: the trusted array must be uploaded again, not confused with it
+    assert classify.linkage(d, "average").tobytes() == Z0.tobytes()
+    assert (classify.find_medoids_from_clusters(d, labels) == med).all()
+    classify.trust_resident(None)
+    assert classify.linkage(d, "average").tobytes() == Z0.tobytes()
