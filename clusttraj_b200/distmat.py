@@ -115,8 +115,9 @@ def condensed_matrix(atomic_nums, coords, opts, devices=None, out=None, return_s
             stats = [dict(st, device=devices[0], rows=(0, M))]
             return (out, stats) if return_stats else out
     if out is None:
-        # several GPUs stream concurrently into one vector: that needs pinned memory to run at full PCIe rate
-        out = np.empty(total, dtype=np.float64) if len(devices) == 1 else _engine.pinned_empty(total)
+        # several GPUs (or one GPU whose memory cannot hold the whole matrix) stream chunks concurrently with the compute
+        # into one vector: that needs pinned memory to run at full PCIe rate
+        out = _engine.pinned_empty(total)
     cuts = slab_bounds(M, len(devices))
     stats = [None] * len(devices)
     errors = []
