@@ -148,14 +148,38 @@ def condensed_matrix(atomic_nums, coords, opts, devices=None, out=None, return_s
 
 def get_distmat(clust_opt):
     """Read (-i) or compute and save the condensed RMSD matrix (distmat.py:15-41)."""
+    distmat, wait = get_distmat_saving_in_background(clust_opt)
+    wait()
+    return distmat
+
+
+def get_distmat_saving_in_background(clust_opt):
+    """get_distmat for a caller that has GPU work to do next (clusttraj_b200.main): returns (distmat, wait) as soon as the
+    matrix is in host memory, while the 8 L bytes of the .npy file (0.3 s at 20k frames) are written by a background
+    thread; `wait()` joins it and re-raises what it raised.  The array must not be written to before `wait()` returns."""
     if clust_opt.input_distmat:
         Logger.logger.info(f"Reading condensed RMSD matrix from {clust_opt.distmat_name}\n")
-        return np.load(clust_opt.distmat_name)
+        return np.load(clust_opt.distmat_name), (lambda: None)
     Logger.logger.info(f"Calculating RMSD matrix on {len(visible_devices())} GPU(s)\n")
     distmat = build_distance_matrix(clust_opt)
     Logger.logger.info(f"Saving condensed RMSD matrix to {clust_opt.distmat_name}\n")
-    np.save(clust_opt.distmat_name, distmat)
-    return distmat
+    failure = []
+
+    def save():
+        try:
+            np.save(clust_opt.distmat_name, distmat)
+        except BaseException as exc:   # surfaced by wait(), on the caller's thread
+            failure.append(exc)
+
+    worker = threading.Thread(target=save, name="clusttraj-b200-npy-writer")
+    worker.start()
+
+    def wait():
+        worker.join()
+        if failure:
+            raise failure[0]
+
+    return distmat, wait
 
 
 def build_distance_matrix(clust_opt):

@@ -7,7 +7,7 @@ import numpy as np
 
 from .classify import (classify_structures, classify_structures_nclusters, classify_structures_silhouette,
                        compute_metrics, find_medoids_from_clusters, sum_distmat, trust_resident)
-from .distmat import get_distmat
+from .distmat import get_distmat_saving_in_background
 from .io import Logger, configure_runtime, save_clusters_config, save_medoids_config
 
 
@@ -25,7 +25,7 @@ def main(args=None):
     t0 = time.monotonic()
     clust_opt = configure_runtime(sys.argv[1:] if args is None else args)
     t1 = time.monotonic()
-    distmat = get_distmat(clust_opt)
+    distmat, matrix_saved = get_distmat_saving_in_background(clust_opt)   # the .npy is written while the GPU clusters
     t2 = time.monotonic()
     n = distmat.size
     Logger.logger.info(f"Time spent computing (or loading) RMSD matrix: {t2 - t1:.6f} s "
@@ -59,5 +59,6 @@ def main(args=None):
                             clust_opt.reorder_solvent_only, clust_opt.solute_natoms, clust_opt.weight_solute,
                             clust_opt.out_medoids_name, clust_opt.out_medoids_fmt, clust_opt.reorder_excl,
                             clust_opt.final_kabsch, clust_opt.overwrite)
+    matrix_saved()
     Logger.logger.info(f"Total wall time: {time.monotonic() - t0:.6f} s\n")
     return 0
