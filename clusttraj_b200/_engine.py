@@ -43,7 +43,7 @@ EXPORTS = [
     "ct_version", "ct_device_count", "ct_last_error", "ct_engine_create", "ct_engine_destroy", "ct_host_alloc",
     "ct_host_free", "ct_load_frames", "ct_rows_pairs", "ct_rmsd_rows", "ct_rmsd_rows_device", "ct_copy_slab",
     "ct_rmsd_condensed", "ct_pair_values", "ct_get_stats", "ct_pack_resident", "ct_matrix_consumers",
-    "ct_pair_transforms", "ct_linkage", "ct_read_xyz", "ct_format_xyz", "ct_buffer_free", "ct_device_memory",
+    "ct_pair_transforms", "ct_linkage", "ct_read_xyz", "ct_read_pdb", "ct_read_gro", "ct_format_xyz", "ct_buffer_free", "ct_device_memory",
 ]
 
 _lib = None
@@ -92,7 +92,8 @@ def load_library(build_if_missing=True):
         lib.ct_format_xyz.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_char_p, P(C.c_void_p), P(C.c_int64), C.c_int32]
         lib.ct_buffer_free.argtypes = [C.c_void_p]
         lib.ct_buffer_free.restype = None
-        lib.ct_read_xyz.argtypes = [C.c_char_p, P(C.c_int64), P(C.c_int32), C.c_void_p, C.c_void_p, C.c_int64, C.c_int32]
+        for _name in ("ct_read_xyz", "ct_read_pdb", "ct_read_gro"):
+            getattr(lib, _name).argtypes = [C.c_char_p, P(C.c_int64), P(C.c_int32), C.c_void_p, C.c_void_p, C.c_int64, C.c_int32]
         lib.ct_linkage.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, P(ct_stats)]
         lib.ct_matrix_consumers.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p,
                                             P(C.c_double), P(ct_stats)]
@@ -119,17 +120,19 @@ def pinned_empty(n, dtype=np.float64):
     return arr
 
 
-def read_xyz_native(path, n_threads=0):
-    """(atomic numbers int32[M, N], coords float64[M, N, 3]) of a regular multi-frame XYZ file through the library's
-    parallel parser (ct_read_xyz; host-only, no GPU needed), or None when the file is not regular enough for it."""
+def read_xyz_native(path, n_threads=0, fmt="xyz"):
+    """(atomic numbers int32[M, N], coords float64[M, N, 3]) of a regular multi-frame XYZ (or, with fmt, PDB / GRO) file
+    through the library's parallel parser (ct_read_xyz / ct_read_pdb / ct_read_gro; host-only, no GPU needed), or None
+    when the file is not regular enough for it."""
     lib = load_library()
+    reader = getattr(lib, "ct_read_" + fmt)
     M, N = C.c_int64(), C.c_int32()
     raw = os.fsencode(path)
-    if lib.ct_read_xyz(raw, C.byref(M), C.byref(N), None, None, 0, 0) != 0:
+    if reader(raw, C.byref(M), C.byref(N), None, None, 0, 0) != 0:
         return None
     atoms = np.empty((M.value, N.value), dtype=np.int32)
     coords = np.empty((M.value, N.value, 3), dtype=np.float64)
-    if lib.ct_read_xyz(raw, C.byref(M), C.byref(N), coords.ctypes.data, atoms.ctypes.data, M.value, int(n_threads)) != 0:
+    if reader(raw, C.byref(M), C.byref(N), coords.ctypes.data, atoms.ctypes.data, M.value, int(n_threads)) != 0:
         return None
     return atoms, coords
 

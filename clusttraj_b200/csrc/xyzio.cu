@@ -141,9 +141,232 @@ static bool parse_frame(const XyzFile& f, size_t fr, double* xyz, int32_t* zs, s
     return true;
 }
 
+// ---- PDB (MODEL ... ENDMDL frames, fixed columns) and GRO (title, count, fixed-column atom lines in nm, box) -----------
+// Same two rules as clusttraj_b200/xyz.py:read_pdb / read_gro, which remain the fall-back for anything refused here.
+
+static int load_text(const char* path, std::vector<char>& text, std::string& err) {
+    FILE* fh = fopen(path, "rb");
+    if (!fh) { err = std::string("cannot open ") + path; return CT_ERR_ARG; }
+    fseek(fh, 0, SEEK_END);
+    const long size = ftell(fh);
+    fseek(fh, 0, SEEK_SET);
+    if (size <= 0) { fclose(fh); err = "empty file"; return CT_ERR_ARG; }
+    text.resize((size_t)size + 1);
+    const size_t got = fread(text.data(), 1, (size_t)size, fh);
+    fclose(fh);
+    if (got != (size_t)size) { err = "short read"; return CT_ERR_ARG; }
+    text[(size_t)size] = '\0';
+    return CT_OK;
+}
+
+// float(line[a:b]) for a fixed-column field: the whole field, blanks stripped, must be one number
+static bool field_number(const char* line, const char* eol, int a, int b, double& v) {
+    const char* lo = line + a < eol ? line + a : eol;
+    const char* hi = line + b < eol ? line + b : eol;
+    while (lo < hi && (*lo == ' ' || *lo == '\t' || *lo == '\r')) ++lo;
+    while (hi > lo && (hi[-1] == ' ' || hi[-1] == '\t' || hi[-1] == '\r')) --hi;
+    if (lo >= hi || hi - lo > 63) return false;
+    char buf[64];
+    memcpy(buf, lo, (size_t)(hi - lo));
+    buf[hi - lo] = '\0';
+    char* stop = nullptr;
+    v = strtod(buf, &stop);
+    return stop == buf + (hi - lo);
+}
+
+static int letters_of(const char* line, const char* eol, int a, int b, char* out) {   // the alphabetic characters of line[a:b]
+    int n = 0;
+    for (const char* c = line + a; c < line + b && c < eol; ++c)
+        if (std::isalpha((unsigned char)*c)) out[n++] = *c;
+    out[n] = '\0';
+    return n;
+}
+
+struct Frames {
+    std::vector<char> text;
+    std::vector<size_t> start, stop;   // byte range of every frame
+    long n_atoms = 0;
+};
+
+// PDB: a frame ends at a record starting with "END" (ENDMDL, END) or at the end of the file; only frames with atoms count
+static int index_pdb(Frames& f, std::string& err) {
+    const char* base = f.text.data();
+    const char* end = base + f.text.size() - 1;
+    const char* p = base;
+    size_t frame_begin = 0;
+    long atoms = 0;
+    auto flush = [&](size_t upto) {
+        if (atoms > 0) {
+            if (f.n_atoms == 0) f.n_atoms = atoms;
+            if (atoms != f.n_atoms) return false;
+            f.start.push_back(frame_begin);
+            f.stop.push_back(upto);
+        }
+        atoms = 0;
+        frame_begin = upto;
+        return true;
+    };
+    while (p < end) {
+        const char* q = line_end(p, end);
+        if (q - p >= 6 && (!memcmp(p, "ATOM  ", 6) || !memcmp(p, "HETATM", 6))) ++atoms;
+        else if (q - p >= 3 && !memcmp(p, "END", 3)) {
+            if (!flush((size_t)((q < end ? q + 1 : end) - base))) { err = "frames have different atom counts"; return CT_ERR_ARG; }
+        }
+        p = q < end ? q + 1 : end;
+    }
+    if (!flush((size_t)(end - base))) { err = "frames have different atom counts"; return CT_ERR_ARG; }
+    if (f.start.empty()) { err = "no ATOM/HETATM records"; return CT_ERR_ARG; }
+    return CT_OK;
+}
+
+static bool parse_pdb_frame(const Frames& f, size_t fr, double* xyz, int32_t* zs, std::string& err) {
+    const char* base = f.text.data();
+    const char* p = base + f.start[fr];
+    const char* end = base + f.stop[fr];
+    long k = 0;
+    while (p < end) {
+        const char* q = line_end(p, end);
+        if (q - p >= 6 && (!memcmp(p, "ATOM  ", 6) || !memcmp(p, "HETATM", 6))) {
+            const char* eol = q;
+            while (eol > p && eol[-1] == '\r') --eol;
+            char el[8];
+            int n = 0;
+            for (const char* c = p + 76; c < p + 78 && c < eol; ++c)           // line[76:78].strip()
+                if (!(*c == ' ' || *c == '\t')) el[n++] = *c;
+            el[n] = '\0';
+            int z;
+            if (n > 0) z = atomic_number(el, n);
+            else {
+                char name[8];
+                int m = letters_of(p, eol, 12, 16, name);
+                if (m > 2) m = 2;                                              // [:2]
+                if (lookup_symbol(name, m) < 0) m = m > 1 ? 1 : m;              // not an element: its first letter
+                z = atomic_number(name, m);
+            }
+            if (z < 0) { err = "frame " + std::to_string(fr) + ": unknown element"; return false; }
+            if (!field_number(p, eol, 30, 38, xyz[3 * k]) || !field_number(p, eol, 38, 46, xyz[3 * k + 1]) ||
+                !field_number(p, eol, 46, 54, xyz[3 * k + 2])) {
+                err = "frame " + std::to_string(fr) + ": bad coordinate field";
+                return false;
+            }
+            zs[k++] = z;
+        }
+        p = q < end ? q + 1 : end;
+    }
+    return k == f.n_atoms;
+}
+
+// GRO: title line, atom count, N fixed-column atom lines, box line; two consecutive blank lines are skipped one at a time
+static int index_gro(Frames& f, std::string& err) {
+    const char* base = f.text.data();
+    const char* end = base + f.text.size() - 1;
+    std::vector<size_t> line_at;
+    for (const char* p = base; p < end;) { line_at.push_back((size_t)(p - base)); const char* q = line_end(p, end); p = q < end ? q + 1 : end; }
+    if (end > base && end[-1] == '\n') line_at.push_back((size_t)(end - base));   // Python's split("\n") yields a last empty line
+    const size_t nl = line_at.size();
+    auto blank = [&](size_t i) {
+        const char* a = base + line_at[i];
+        const char* b = i + 1 < nl ? base + line_at[i + 1] : end;
+        for (const char* c = a; c < b; ++c) if (!(*c == ' ' || *c == '\t' || *c == '\r' || *c == '\n')) return false;
+        return true;
+    };
+    size_t pos = 0;
+    while (pos + 1 < nl) {
+        if (blank(pos) && blank(pos + 1)) { ++pos; continue; }
+        const char* c = base + line_at[pos + 1];
+        char* stop = nullptr;
+        const long n = strtol(c, &stop, 10);
+        if (stop == c || n < 1) { err = "bad atom count line"; return CT_ERR_ARG; }
+        if (pos + 2 + (size_t)n > nl) {
+            err = "truncated frame";
+            return CT_ERR_ARG;
+        }
+        if (f.n_atoms == 0) f.n_atoms = n;
+        if (n != f.n_atoms) { err = "frames have different atom counts"; return CT_ERR_ARG; }
+        f.start.push_back(line_at[pos + 2]);
+        f.stop.push_back(pos + 2 + (size_t)n < nl ? line_at[pos + 2 + (size_t)n] : (size_t)(end - base));
+        pos += 3 + (size_t)n;
+    }
+    if (f.start.empty()) { err = "no frames"; return CT_ERR_ARG; }
+    return CT_OK;
+}
+
+static bool parse_gro_frame(const Frames& f, size_t fr, double* xyz, int32_t* zs, std::string& err) {
+    const char* base = f.text.data();
+    const char* p = base + f.start[fr];
+    const char* end = base + f.stop[fr];
+    for (long k = 0; k < f.n_atoms; ++k) {
+        if (p >= end) { err = "frame " + std::to_string(fr) + ": truncated"; return false; }
+        const char* q = line_end(p, end);
+        const char* eol = q;
+        while (eol > p && eol[-1] == '\r') --eol;
+        char name[8];
+        const int m = letters_of(p, eol, 10, 15, name);
+        // name[:2] if it is an element, has a second letter and that letter is lower case, else name[:1]
+        int len = (m > 1 && std::islower((unsigned char)name[1]) && lookup_symbol(name, 2) >= 0) ? 2 : (m > 0 ? 1 : 0);
+        const int z = atomic_number(name, len);
+        if (z < 0 || len == 0) { err = "frame " + std::to_string(fr) + ": unknown element"; return false; }
+        double v[3];
+        if (!field_number(p, eol, 20, 28, v[0]) || !field_number(p, eol, 28, 36, v[1]) || !field_number(p, eol, 36, 44, v[2])) {
+            err = "frame " + std::to_string(fr) + ": bad coordinate field";
+            return false;
+        }
+        zs[k] = z;
+        xyz[3 * k] = 10.0 * v[0]; xyz[3 * k + 1] = 10.0 * v[1]; xyz[3 * k + 2] = 10.0 * v[2];   // nm -> Angstrom
+        p = q < end ? q + 1 : end;
+    }
+    return true;
+}
+
+template <class Index, class Parse>
+static int read_frames(const char* what, const char* path, int64_t* n_frames, int32_t* n_atoms, double* coords,
+                       int32_t* atomic_numbers, int64_t capacity_frames, int32_t n_threads, Index index, Parse parse) {
+    if (!path || !n_frames || !n_atoms) { set_global_error(std::string(what) + ": NULL argument"); return CT_ERR_ARG; }
+    Frames f;
+    std::string err;
+    int rc = load_text(path, f.text, err);
+    if (rc == CT_OK) rc = index(f, err);
+    if (rc != CT_OK) { set_global_error(std::string(what) + ": " + err); return rc; }
+    const int64_t M = (int64_t)f.start.size();
+    *n_frames = M;
+    *n_atoms = (int32_t)f.n_atoms;
+    if (!coords || !atomic_numbers) return CT_OK;   // size query
+    if (capacity_frames < M) { set_global_error(std::string(what) + ": output arrays are too small"); return CT_ERR_ARG; }
+    int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    nt = nt < 1 ? 1 : (nt > 64 ? 64 : nt);
+    if ((int64_t)nt > M) nt = (int)M;
+    std::vector<std::string> errs((size_t)nt);
+    std::vector<char> failed((size_t)nt, 0);
+    const size_t N = (size_t)f.n_atoms;
+    auto work = [&](int t) {
+        const int64_t lo = M * t / nt, hi = M * (t + 1) / nt;
+        for (int64_t fr = lo; fr < hi; ++fr)
+            if (!parse(f, (size_t)fr, coords + (size_t)fr * N * 3, atomic_numbers + (size_t)fr * N, errs[(size_t)t])) { failed[(size_t)t] = 1; return; }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto& th : pool) th.join();
+    for (int t = 0; t < nt; ++t)
+        if (failed[(size_t)t]) { set_global_error(std::string(what) + ": " + (errs[(size_t)t].empty() ? "malformed frame" : errs[(size_t)t])); return CT_ERR_ARG; }
+    return CT_OK;
+}
+
 }  // namespace ct
 
 extern "C" {
+
+int ct_read_pdb(const char* path, int64_t* n_frames, int32_t* n_atoms, double* coords, int32_t* atomic_numbers,
+                int64_t capacity_frames, int32_t n_threads) {
+    return ct::read_frames("ct_read_pdb", path, n_frames, n_atoms, coords, atomic_numbers, capacity_frames, n_threads,
+                           ct::index_pdb, ct::parse_pdb_frame);
+}
+
+int ct_read_gro(const char* path, int64_t* n_frames, int32_t* n_atoms, double* coords, int32_t* atomic_numbers,
+                int64_t capacity_frames, int32_t n_threads) {
+    return ct::read_frames("ct_read_gro", path, n_frames, n_atoms, coords, atomic_numbers, capacity_frames, n_threads,
+                           ct::index_gro, ct::parse_gro_frame);
+}
 
 int ct_read_xyz(const char* path, int64_t* n_frames, int32_t* n_atoms, double* coords, int32_t* atomic_numbers,
                 int64_t capacity_frames, int32_t n_threads) {

@@ -89,9 +89,23 @@ def read_xyz(path):
     return atoms, coords
 
 
-def read_pdb(path):
+def _native(path, fmt):
+    try:
+        from . import _engine
+        return _engine.read_xyz_native(path, fmt=fmt)
+    except (ImportError, OSError, AttributeError):
+        return None
+    except Exception:   # EngineError when the library cannot be built/loaded: the Python readers below need no library
+        return None
+
+
+def read_pdb(path, native=True):
     """MODEL/ENDMDL frames of a PDB file (or a single frame without MODEL records): ATOM/HETATM records, element
-    from columns 77-78 when present, else from the atom name (columns 13-16) the way OpenBabel guesses it."""
+    from columns 77-78 when present, else from the atom name (columns 13-16) the way OpenBabel guesses it.  Parsed by the
+    engine library's parallel reader (ct_read_pdb) when it accepts the file, else by the line loop below."""
+    got = _native(path, "pdb") if native else None
+    if got is not None:
+        return got
     atoms, frames = [], []
     z, x = [], []
 
@@ -122,9 +136,13 @@ def read_pdb(path):
     return np.stack(atoms), np.stack(frames)
 
 
-def read_gro(path):
+def read_gro(path, native=True):
     """Frames of a GROMACS .gro file: title, atom count, fixed-column atom lines (positions in nm), box line.
-    The element is guessed from the atom name's leading letters."""
+    The element is guessed from the atom name's leading letters.  Parsed by the engine library's parallel reader
+    (ct_read_gro) when it accepts the file, else by the line loop below."""
+    got = _native(path, "gro") if native else None
+    if got is not None:
+        return got
     atoms, frames = [], []
     with open(path) as fh:
         lines = fh.read().split("\n")

@@ -153,6 +153,13 @@ int ct_linkage(ct_engine* e, const double* distmat, int64_t M, int32_t method, d
  * refused with CT_ERR_ARG and a message in ct_last_error(NULL); clusttraj_b200.xyz then uses its general parser. */
 int ct_read_xyz(const char* path, int64_t* n_frames, int32_t* n_atoms, double* coords, int32_t* atomic_numbers,
                 int64_t capacity_frames, int32_t n_threads);
+/* The same for multi-MODEL PDB files (ATOM / HETATM records, frames closed by END* records; element from columns 77-78,
+ * else guessed from the atom name) and GROMACS .gro trajectories (positions converted from nm to Angstrom, element
+ * guessed from the atom name): the rules of clusttraj_b200/xyz.py:read_pdb / read_gro, which stand in for OpenBabel's. */
+int ct_read_pdb(const char* path, int64_t* n_frames, int32_t* n_atoms, double* coords, int32_t* atomic_numbers,
+                int64_t capacity_frames, int32_t n_threads);
+int ct_read_gro(const char* path, int64_t* n_frames, int32_t* n_atoms, double* coords, int32_t* atomic_numbers,
+                int64_t capacity_frames, int32_t n_threads);
 
 /* Text of n_frames consecutive XYZ frames of the same atoms, in the layout the reference writes through
  * pybel.Outputfile("xyz") in save_clusters_config / save_medoids_config (io.py:870-899,1000-1015): "<N>\n<title>\n" and

@@ -427,3 +427,64 @@ def test_native_xyz_formatter_writes_what_the_python_writer_writes():
         _engine.format_xyz_native(np.array([200]), np.zeros((1, 1, 3)))
     with pytest.raises(ValueError):
         _engine.format_xyz_native(z, x[:, :5], titles)
+
+
+def test_native_pdb_and_gro_parsers_match_the_python_readers(tmp_path):
+    """ct_read_pdb / ct_read_gro (parallel, in the engine library) against clusttraj_b200.xyz's own line readers: identical
+    element guesses and float64 bits on multi-frame files with element columns present and absent, HETATM records, TER /
+    ENDMDL / END records, CRLF line ends; irregular files are refused (None) and left to the Python readers."""
+    from clusttraj_b200 import _engine, xyz
+
+    rng = np.random.default_rng(2)
+    M, N = 23, 31
+    names = ["CA", "N", "O", "HB1", "CL1", "FE", "1HG2", "OW", "HW1", "Na", "SOD", "C12", "Br", "X"]
+    elems = ["C", "N", "O", "", "", "FE", "", "", "", "", "", "", "", ""]
+    coords = rng.normal(scale=25, size=(M, N, 3))
+    for eol in ("\n", "\r\n"):
+        pdb = []
+        for m in range(M):
+            pdb.append(f"MODEL     {m + 1:4d}")
+            for k in range(N):
+                x, y, z = coords[m, k]
+                rec = "HETATM" if k % 7 == 0 else "ATOM  "
+                pdb.append(f"{rec}{k + 1:5d} {names[k % 14]:<4s} RES A{1:4d}    {x:8.3f}{y:8.3f}{z:8.3f}{1.0:6.2f}{0.0:6.2f}"
+                           f"          {elems[k % 14]:>2s}")
+            pdb += ["TER", "ENDMDL"]
+        pdb.append("END")
+        p = tmp_path / "t.pdb"
+        p.write_bytes((eol.join(pdb) + eol).encode())
+        a0, c0 = xyz.read_pdb(str(p), native=False)
+        a1, c1 = _engine.read_xyz_native(str(p), fmt="pdb")
+        assert a0.shape == (M, N) and (a0 == a1).all() and c0.tobytes() == c1.tobytes()
+        a2, c2 = xyz.read_pdb(str(p))
+        assert (a0 == a2).all() and c0.tobytes() == c2.tobytes()
+        gro = []
+        for m in range(M):
+            gro += [f"frame t= {m}.0", f"{N:5d}"]
+            for k in range(N):
+                x, y, z = coords[m, k] / 10
+                gro.append(f"{1:5d}{'RES':<5s}{names[k % 14]:>5s}{k + 1:5d}{x:8.3f}{y:8.3f}{z:8.3f}{0.1:8.4f}{0.2:8.4f}{0.3:8.4f}")
+            gro.append(f"{3.0:10.5f}{3.0:10.5f}{3.0:10.5f}")
+        g = tmp_path / "t.gro"
+        g.write_bytes((eol.join(gro) + eol).encode())
+        a0, c0 = xyz.read_gro(str(g), native=False)
+        a1, c1 = _engine.read_xyz_native(str(g), fmt="gro")
+        assert a0.shape == (M, N) and (a0 == a1).all() and c0.tobytes() == c1.tobytes()
+        assert xyz.read_trajectory(str(g))[1].tobytes() == c0.tobytes()
+    single = tmp_path / "one.pdb"
+    single.write_text("\n".join(pdb[1:1 + N]) + "\n")                       # no MODEL / END records at all
+    a0, c0 = xyz.read_pdb(str(single), native=False)
+    a1, c1 = _engine.read_xyz_native(str(single), fmt="pdb")
+    assert a0.shape == (1, N) and (a0 == a1).all() and c0.tobytes() == c1.tobytes()
+    bad = tmp_path / "bad.pdb"
+    bad.write_text("\n".join(pdb[:N + 3] + pdb[N + 3:2 * N + 3]) + "\n")    # second frame one atom short
+    assert _engine.read_xyz_native(str(bad), fmt="pdb") is None
+    with pytest.raises(ValueError):
+        xyz.read_pdb(str(bad))
+    bad.write_text("ATOM      1  CA  RES A   1      1.000   2.000\n")         # line too short for z
+    assert _engine.read_xyz_native(str(bad), fmt="pdb") is None
+    badg = tmp_path / "bad.gro"
+    badg.write_text("\n".join(gro[:N + 1]) + "\n")                          # truncated frame
+    assert _engine.read_xyz_native(str(badg), fmt="gro") is None
+    with pytest.raises(ValueError):
+        xyz.read_gro(str(badg))
