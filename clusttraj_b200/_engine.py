@@ -43,7 +43,7 @@ EXPORTS = [
     "ct_version", "ct_device_count", "ct_last_error", "ct_engine_create", "ct_engine_destroy", "ct_host_alloc",
     "ct_host_free", "ct_load_frames", "ct_rows_pairs", "ct_rmsd_rows", "ct_rmsd_rows_device", "ct_copy_slab",
     "ct_rmsd_condensed", "ct_pair_values", "ct_get_stats", "ct_pack_resident", "ct_matrix_consumers",
-    "ct_pair_transforms", "ct_linkage", "ct_read_xyz", "ct_read_pdb", "ct_read_gro", "ct_format_xyz", "ct_buffer_free", "ct_device_memory",
+    "ct_pair_transforms", "ct_linkage", "ct_matrix_reserve", "ct_rmsd_rows_gather", "ct_matrix_commit", "ct_read_xyz", "ct_read_pdb", "ct_read_gro", "ct_format_xyz", "ct_buffer_free", "ct_device_memory",
 ]
 
 _lib = None
@@ -82,6 +82,9 @@ def load_library(build_if_missing=True):
         lib.ct_rmsd_rows.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, P(ct_stats)]
         lib.ct_rmsd_rows_device.argtypes = [C.c_void_p, C.c_int64, C.c_int64, P(C.c_void_p), P(ct_stats)]
         lib.ct_copy_slab.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
+        lib.ct_matrix_reserve.argtypes = [C.c_void_p, C.c_int64]
+        lib.ct_rmsd_rows_gather.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, P(ct_stats)]
+        lib.ct_matrix_commit.argtypes = [C.c_void_p, C.c_int64]
         lib.ct_rmsd_condensed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, P(ct_opts),
                                           C.c_void_p, P(ct_stats)]
         lib.ct_pair_values.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, P(ct_stats)]
@@ -229,6 +232,31 @@ class Engine:
         st = ct_stats()
         self._check(self._lib.ct_rmsd_rows(self._h, row_begin, row_end, out.ctypes.data, C.byref(st)), "ct_rmsd_rows")
         return out[:n], st.as_dict()
+
+    def matrix_reserve(self, n_frames):
+        """Room for the whole condensed matrix of n_frames frames on this engine's GPU (target of rmsd_rows_gather)."""
+        self._resident_ref = None
+        self._check(self._lib.ct_matrix_reserve(self._h, int(n_frames)), "ct_matrix_reserve")
+
+    def rmsd_rows_gather(self, row_begin, row_end, root, out=None, to_host=True):
+        """rmsd_rows that also lands the rows in `root`'s reserved matrix (GPU -> GPU over NVLink, or in place when root is
+        this engine); to_host=False skips the host copy.  Returns (host slab or None, stats)."""
+        n = self.rows_pairs(row_begin, row_end)
+        if to_host:
+            if out is None:
+                out = np.empty(n, dtype=np.float64)
+            if out.dtype != np.float64 or not out.flags.c_contiguous or out.size < n:
+                raise ValueError("out must be a C-contiguous float64 array with room for the slab")
+        st = ct_stats()
+        self._check(self._lib.ct_rmsd_rows_gather(self._h, row_begin, row_end, out.ctypes.data if to_host else None, root._h,
+                                                  C.byref(st)), "ct_rmsd_rows_gather")
+        return (out[:n] if to_host else None), st.as_dict()
+
+    def matrix_commit(self, n_frames, array=None):
+        """Every gathering call has returned: the reserved matrix is complete; `array` = the host vector it equals (for
+        trusted callers, see matrix_consumers)."""
+        self._check(self._lib.ct_matrix_commit(self._h, int(n_frames)), "ct_matrix_commit")
+        self._note_resident(array)
 
     def free_memory(self):
         """Free bytes on this engine's GPU."""

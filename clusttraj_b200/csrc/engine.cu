@@ -53,7 +53,7 @@ struct ct_engine {
     int device = 0;
     int sm_count = 0;
     std::string err;
-    cudaStream_t s_compute = nullptr, s_copy = nullptr;
+    cudaStream_t s_compute = nullptr, s_copy = nullptr, s_peer = nullptr;
     // frames
     int64_t M = 0;
     int N = 0, K = 0, natoms = 0, m_pad = 0, kq_total = 0;
@@ -94,7 +94,8 @@ struct ct_engine {
     double* d_chunk[2] = {nullptr, nullptr}; size_t chunk_cap = 0;  // streaming double buffer
     int2* d_fix_pairs = nullptr; unsigned int* d_fix_count = nullptr; unsigned int fix_cap = 1u << 20;
     unsigned long long* d_counters = nullptr;  // [0] flagged pairs, [1] lsap steps
-    cudaEvent_t ev_chunk_done[2] = {nullptr, nullptr}, ev_copy_done[2] = {nullptr, nullptr};
+    cudaEvent_t ev_chunk_done[2] = {nullptr, nullptr}, ev_copy_done[2] = {nullptr, nullptr}, ev_peer_done[2] = {nullptr, nullptr};
+    int64_t reserved_M = 0;                                  // > 0: d_slab has room for the whole matrix of that many frames
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
     ct_stats stats{};
     int gram_variant = -1;  // -1 = auto: int8 tensor-core kernel when the coordinates quantise finely enough, else
@@ -148,6 +149,33 @@ int ct_device_count(void) {
 
 const char* ct_last_error(const ct_engine* e) { return e ? e->err.c_str() : g_err.c_str(); }
 
+static int engine_init(ct_engine* e, int device) {
+    e->device = device;
+    CT_CUDA(e, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CT_CUDA(e, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(e, CT_ERR_UNSUPPORTED, "clusttraj_b200 kernels are built for sm_100a (B200) only");
+    e->sm_count = prop.multiProcessorCount;
+    CT_CUDA(e, cudaStreamCreateWithFlags(&e->s_compute, cudaStreamNonBlocking));
+    CT_CUDA(e, cudaStreamCreateWithFlags(&e->s_copy, cudaStreamNonBlocking));
+    CT_CUDA(e, cudaStreamCreateWithFlags(&e->s_peer, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+        CT_CUDA(e, cudaEventCreateWithFlags(&e->ev_chunk_done[k], cudaEventDisableTiming));
+        CT_CUDA(e, cudaEventCreateWithFlags(&e->ev_copy_done[k], cudaEventDisableTiming));
+        CT_CUDA(e, cudaEventCreateWithFlags(&e->ev_peer_done[k], cudaEventDisableTiming));
+    }
+    CT_CUDA(e, cudaEventCreate(&e->ev_a));
+    CT_CUDA(e, cudaEventCreate(&e->ev_b));
+    CT_CUDA(e, cudaEventCreate(&e->ev_c));
+    CT_CUDA(e, cudaEventCreate(&e->ev_d));
+    CT_CUDA(e, cudaMalloc(&e->d_fix_pairs, sizeof(int2) * e->fix_cap));
+    CT_CUDA(e, cudaMalloc(&e->d_fix_count, sizeof(unsigned int)));
+    CT_CUDA(e, cudaMalloc(&e->d_counters, sizeof(unsigned long long) * 4));
+    CT_CUDA(e, cudaMalloc(&e->d_qinfo, sizeof(double) * 4));
+    CT_CUDA(e, cudaMalloc(&e->d_maxbits, sizeof(unsigned long long)));
+    return CT_OK;
+}
+
 int ct_engine_create(int device, ct_engine** out) {
     if (!out) return fail(nullptr, CT_ERR_ARG, "ct_engine_create: out is NULL");
     *out = nullptr;
@@ -158,30 +186,12 @@ int ct_engine_create(int device, ct_engine** out) {
                                               " (clusttraj_b200 has no CPU fallback)");
     if (device < 0 || device >= n) return fail(nullptr, CT_ERR_ARG, "ct_engine_create: bad device ordinal");
     ct_engine* e = new ct_engine();
-    e->device = device;
-    CT_CUDA((ct_engine*)nullptr, cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CT_CUDA((ct_engine*)nullptr, cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10) {
-        delete e;
-        return fail(nullptr, CT_ERR_UNSUPPORTED, "clusttraj_b200 kernels are built for sm_100a (B200) only");
+    const int rc = engine_init(e, device);
+    if (rc != CT_OK) {
+        g_err = e->err;            // the handle does not survive: the message goes to ct_last_error(NULL)
+        ct_engine_destroy(e);      // frees whatever was created before the failure (every member starts out NULL)
+        return rc;
     }
-    e->sm_count = prop.multiProcessorCount;
-    CT_CUDA((ct_engine*)nullptr, cudaStreamCreateWithFlags(&e->s_compute, cudaStreamNonBlocking));
-    CT_CUDA((ct_engine*)nullptr, cudaStreamCreateWithFlags(&e->s_copy, cudaStreamNonBlocking));
-    for (int k = 0; k < 2; ++k) {
-        CT_CUDA((ct_engine*)nullptr, cudaEventCreateWithFlags(&e->ev_chunk_done[k], cudaEventDisableTiming));
-        CT_CUDA((ct_engine*)nullptr, cudaEventCreateWithFlags(&e->ev_copy_done[k], cudaEventDisableTiming));
-    }
-    CT_CUDA((ct_engine*)nullptr, cudaEventCreate(&e->ev_a));
-    CT_CUDA((ct_engine*)nullptr, cudaEventCreate(&e->ev_b));
-    CT_CUDA((ct_engine*)nullptr, cudaEventCreate(&e->ev_c));
-    CT_CUDA((ct_engine*)nullptr, cudaEventCreate(&e->ev_d));
-    CT_CUDA((ct_engine*)nullptr, cudaMalloc(&e->d_fix_pairs, sizeof(int2) * e->fix_cap));
-    CT_CUDA((ct_engine*)nullptr, cudaMalloc(&e->d_fix_count, sizeof(unsigned int)));
-    CT_CUDA((ct_engine*)nullptr, cudaMalloc(&e->d_counters, sizeof(unsigned long long) * 4));
-    CT_CUDA((ct_engine*)nullptr, cudaMalloc(&e->d_qinfo, sizeof(double) * 4));
-    CT_CUDA((ct_engine*)nullptr, cudaMalloc(&e->d_maxbits, sizeof(unsigned long long)));
     const char* v = getenv("CLUSTTRAJ_B200_GRAM_VARIANT");
     if (v) e->gram_variant = atoi(v);
     const char* mq = getenv("CLUSTTRAJ_B200_MIN_QUANT_BITS");  // test hook: force the fall-back decision
@@ -209,10 +219,15 @@ void ct_engine_destroy(ct_engine* e) {
     if (e->h_link_flag) cudaFreeHost(e->h_link_flag);
     cudaFree(e->d_slab); cudaFree(e->d_chunk[0]); cudaFree(e->d_chunk[1]);
     cudaFree(e->d_fix_pairs); cudaFree(e->d_fix_count); cudaFree(e->d_counters);
-    for (int k = 0; k < 2; ++k) { cudaEventDestroy(e->ev_chunk_done[k]); cudaEventDestroy(e->ev_copy_done[k]); }
-    cudaEventDestroy(e->ev_a); cudaEventDestroy(e->ev_b); cudaEventDestroy(e->ev_c); cudaEventDestroy(e->ev_d);
-    cudaStreamDestroy(e->s_compute); cudaStreamDestroy(e->s_copy);
+    for (int k = 0; k < 2; ++k) {
+        if (e->ev_chunk_done[k]) cudaEventDestroy(e->ev_chunk_done[k]);
+        if (e->ev_copy_done[k]) cudaEventDestroy(e->ev_copy_done[k]);
+        if (e->ev_peer_done[k]) cudaEventDestroy(e->ev_peer_done[k]);
+    }
+    for (cudaEvent_t ev : {e->ev_a, e->ev_b, e->ev_c, e->ev_d}) if (ev) cudaEventDestroy(ev);
+    for (cudaStream_t st : {e->s_compute, e->s_copy, e->s_peer}) if (st) cudaStreamDestroy(st);
     if (e->plan) ct::pair_plan_free(e->plan);
+    cudaGetLastError();   // a partially built engine leaves nothing sticky behind
     delete e;
 }
 
@@ -424,6 +439,7 @@ int ct_rmsd_rows_device(ct_engine* e, int64_t row_begin, int64_t row_end, const 
     CT_CUDA(e, cudaSetDevice(e->device));
     const int64_t n = ct_rows_pairs(e->M, row_begin, row_end);
     e->slab_full_M = 0;
+    e->reserved_M = 0;
     if ((rc = ensure(e, e->d_slab, e->slab_cap, (size_t)std::max<int64_t>(n, 1)))) return rc;
     CT_CUDA(e, cudaMemsetAsync(e->d_counters, 0, sizeof(unsigned long long) * 4, e->s_compute));
     int64_t launches = 0;
@@ -494,14 +510,32 @@ int ct_copy_slab(ct_engine* e, int64_t offset, int64_t count, double* out) {
     return CT_OK;
 }
 
-int ct_rmsd_rows(ct_engine* e, int64_t row_begin, int64_t row_end, double* out, ct_stats* stats) {
+// Rows [row_begin, row_end) in chunks of about chunk_entries matrix entries: chunk c+1 is computed while chunk c leaves
+// the two-deep device ring -- to host memory `out` (may be NULL) over PCIe and, when `root` is given, into root's reserved
+// whole-matrix buffer at the rows' own place in the condensed vector (in place on root's own GPU, cudaMemcpyPeerAsync over
+// NVLink from the others).
+static int rows_stream(ct_engine* e, int64_t row_begin, int64_t row_end, double* out, ct_engine* root, ct_stats* stats) {
     int rc = check_rows(e, row_begin, row_end);
     if (rc) return rc;
     const int64_t n = ct_rows_pairs(e->M, row_begin, row_end);
-    if (n > 0 && !out) return fail(e, CT_ERR_ARG, "ct_rmsd_rows: out is NULL");
+    if (n > 0 && !out && !root) return fail(e, CT_ERR_ARG, "ct_rmsd_rows: out is NULL");
     CT_CUDA(e, cudaSetDevice(e->device));
-    // Row chunks of about chunk_entries matrix entries, aligned to the Gram block height so that no
-    // block of frame pairs is computed twice; chunk c+1 is computed while chunk c streams to the host.
+    double* root_dst = nullptr;
+    if (root) {
+        if (root->reserved_M != e->M || !root->d_slab)
+            return fail(e, CT_ERR_STATE, "ct_rmsd_rows_gather: call ct_matrix_reserve(root, M) with this trajectory's frame count first");
+        root_dst = root->d_slab + ct::condensed_row_base(e->M, row_begin);
+        if (root->device != e->device) {
+            int can = 0;
+            CT_CUDA(e, cudaDeviceCanAccessPeer(&can, e->device, root->device));
+            if (can) {   // direct NVLink path; without it cudaMemcpyPeerAsync still works, staged by the driver
+                const cudaError_t pe = cudaDeviceEnablePeerAccess(root->device, 0);
+                if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) CT_CUDA(e, pe);
+                cudaGetLastError();
+            }
+        }
+    }
+    // Row chunks aligned to the Gram block height so that no block of frame pairs is computed twice.
     const int align = e->use_i8 ? ct::oz_row_align() : (e->use_gram ? ct::gram_row_align(e->gram_variant) : 1);
     std::vector<int64_t> cuts;
     cuts.push_back(row_begin);
@@ -536,27 +570,48 @@ int ct_rmsd_rows(ct_engine* e, int64_t row_begin, int64_t row_end, double* out, 
     int64_t launches = 0;
     CT_CUDA(e, cudaEventRecord(e->ev_a, e->s_compute));
     int64_t written = 0;
+    bool used[2] = {false, false};
     for (size_t c = 0; c + 1 < cuts.size(); ++c) {
         const int b = (int)(c & 1);
         const int64_t cn = ct_rows_pairs(e->M, cuts[c], cuts[c + 1]);
         if (cn == 0) continue;
-        if (c >= 2) CT_CUDA(e, cudaStreamWaitEvent(e->s_compute, e->ev_copy_done[b], 0));
+        if (used[b]) {   // both consumers of this ring slot must be done with it
+            if (out) CT_CUDA(e, cudaStreamWaitEvent(e->s_compute, e->ev_copy_done[b], 0));
+            if (root) CT_CUDA(e, cudaStreamWaitEvent(e->s_compute, e->ev_peer_done[b], 0));
+        }
+        used[b] = true;
         rc = compute_rows_async(e, (int)cuts[c], (int)cuts[c + 1], e->d_chunk[b],
                                 ct::condensed_row_base(e->M, cuts[c]), cn, &launches);
         if (rc) return rc;
         CT_CUDA(e, cudaEventRecord(e->ev_chunk_done[b], e->s_compute));
-        CT_CUDA(e, cudaStreamWaitEvent(e->s_copy, e->ev_chunk_done[b], 0));
-        CT_CUDA(e, cudaMemcpyAsync(out + written, e->d_chunk[b], sizeof(double) * (size_t)cn, cudaMemcpyDeviceToHost,
-                                   e->s_copy));
-        CT_CUDA(e, cudaEventRecord(e->ev_copy_done[b], e->s_copy));
+        if (out) {
+            CT_CUDA(e, cudaStreamWaitEvent(e->s_copy, e->ev_chunk_done[b], 0));
+            CT_CUDA(e, cudaMemcpyAsync(out + written, e->d_chunk[b], sizeof(double) * (size_t)cn, cudaMemcpyDeviceToHost,
+                                       e->s_copy));
+            CT_CUDA(e, cudaEventRecord(e->ev_copy_done[b], e->s_copy));
+        }
+        if (root) {
+            CT_CUDA(e, cudaStreamWaitEvent(e->s_peer, e->ev_chunk_done[b], 0));
+            if (root->device == e->device)
+                CT_CUDA(e, cudaMemcpyAsync(root_dst + written, e->d_chunk[b], sizeof(double) * (size_t)cn, cudaMemcpyDeviceToDevice,
+                                           e->s_peer));
+            else
+                CT_CUDA(e, cudaMemcpyPeerAsync(root_dst + written, root->device, e->d_chunk[b], e->device,
+                                               sizeof(double) * (size_t)cn, e->s_peer));
+            CT_CUDA(e, cudaEventRecord(e->ev_peer_done[b], e->s_peer));
+        }
         written += cn;
     }
     CT_CUDA(e, cudaEventRecord(e->ev_b, e->s_compute));
-    CT_CUDA(e, cudaStreamWaitEvent(e->s_compute, e->ev_copy_done[0], 0));
-    CT_CUDA(e, cudaStreamWaitEvent(e->s_compute, e->ev_copy_done[1], 0));
+    for (int b = 0; b < 2; ++b) {
+        if (!used[b]) continue;
+        if (out) CT_CUDA(e, cudaStreamWaitEvent(e->s_compute, e->ev_copy_done[b], 0));
+        if (root) CT_CUDA(e, cudaStreamWaitEvent(e->s_compute, e->ev_peer_done[b], 0));
+    }
     CT_CUDA(e, cudaEventRecord(e->ev_c, e->s_compute));
     CT_CUDA(e, cudaStreamSynchronize(e->s_compute));
     CT_CUDA(e, cudaStreamSynchronize(e->s_copy));
+    CT_CUDA(e, cudaStreamSynchronize(e->s_peer));
     float ms = 0.f;
     CT_CUDA(e, cudaEventElapsedTime(&ms, e->ev_a, e->ev_b));
     e->stats.kernel_ms = ms;  // compute stream busy time (includes waits for buffer reuse)
@@ -566,6 +621,36 @@ int ct_rmsd_rows(ct_engine* e, int64_t row_begin, int64_t row_end, double* out, 
     e->stats.d2h_ms = ms;
     if ((rc = finish_stats(e, n, launches))) return rc;
     if (stats) *stats = e->stats;
+    return CT_OK;
+}
+
+int ct_rmsd_rows(ct_engine* e, int64_t row_begin, int64_t row_end, double* out, ct_stats* stats) {
+    return rows_stream(e, row_begin, row_end, out, nullptr, stats);
+}
+
+int ct_matrix_reserve(ct_engine* e, int64_t M) {
+    if (!e) return fail(nullptr, CT_ERR_ARG, "engine is NULL");
+    if (M < 2 || M > (int64_t)1 << 30) return fail(e, CT_ERR_ARG, "ct_matrix_reserve: need 2 <= M <= 2^30 frames");
+    CT_CUDA(e, cudaSetDevice(e->device));
+    e->slab_full_M = 0;
+    e->reserved_M = 0;
+    int rc = ensure(e, e->d_slab, e->slab_cap, (size_t)(M * (M - 1) / 2));
+    if (rc) return rc;
+    e->reserved_M = M;
+    return CT_OK;
+}
+
+int ct_rmsd_rows_gather(ct_engine* e, int64_t row_begin, int64_t row_end, double* out, ct_engine* root, ct_stats* stats) {
+    if (!root) return fail(e, CT_ERR_ARG, "ct_rmsd_rows_gather: root is NULL");
+    return rows_stream(e, row_begin, row_end, out, root, stats);
+}
+
+int ct_matrix_commit(ct_engine* e, int64_t M) {
+    if (!e) return fail(nullptr, CT_ERR_ARG, "engine is NULL");
+    if (e->reserved_M != M || M < 2) return fail(e, CT_ERR_STATE, "ct_matrix_commit: no matrix of M frames was reserved on this engine");
+    CT_CUDA(e, cudaSetDevice(e->device));
+    CT_CUDA(e, cudaDeviceSynchronize());   // peer copies were synchronised by their senders; this orders them before our streams
+    e->slab_full_M = M;
     return CT_OK;
 }
 
@@ -588,25 +673,27 @@ static int pair_values_impl(ct_engine* e, const int64_t* pairs, int64_t n_pairs,
     }
     if (n_pairs == 0) return CT_OK;
     CT_CUDA(e, cudaSetDevice(e->device));
-    long long* d_pairs = nullptr; double* d_vals = nullptr; int* d_perms = nullptr; double* d_xf = nullptr;
-    CT_CUDA(e, cudaMalloc(&d_pairs, sizeof(long long) * 2 * (size_t)n_pairs));
-    CT_CUDA(e, cudaMalloc(&d_vals, sizeof(double) * (size_t)n_pairs));
-    if (perms) CT_CUDA(e, cudaMalloc(&d_perms, sizeof(int) * (size_t)n_pairs * e->K));
-    if (transforms) CT_CUDA(e, cudaMalloc(&d_xf, sizeof(double) * 12 * (size_t)n_pairs));
-    CT_CUDA(e, cudaMemcpy(d_pairs, pairs, sizeof(long long) * 2 * (size_t)n_pairs, cudaMemcpyHostToDevice));
+    struct Scratch {   // freed on every return path
+        long long* pairs = nullptr; double* vals = nullptr; int* perms = nullptr; double* xf = nullptr;
+        ~Scratch() { cudaFree(pairs); cudaFree(vals); cudaFree(perms); cudaFree(xf); }
+    } d;
+    CT_CUDA(e, cudaMalloc(&d.pairs, sizeof(long long) * 2 * (size_t)n_pairs));
+    CT_CUDA(e, cudaMalloc(&d.vals, sizeof(double) * (size_t)n_pairs));
+    if (perms) CT_CUDA(e, cudaMalloc(&d.perms, sizeof(int) * (size_t)n_pairs * e->K));
+    if (transforms) CT_CUDA(e, cudaMalloc(&d.xf, sizeof(double) * 12 * (size_t)n_pairs));
+    CT_CUDA(e, cudaMemcpy(d.pairs, pairs, sizeof(long long) * 2 * (size_t)n_pairs, cudaMemcpyHostToDevice));
     CT_CUDA(e, cudaMemsetAsync(e->d_counters, 0, sizeof(unsigned long long) * 4, e->s_compute));
     CT_CUDA(e, cudaEventRecord(e->ev_a, e->s_compute));
-    CT_CUDA(e, ct::launch_pairs_list(e->plan, e->d_centred, (int)e->M, e->K, d_pairs, n_pairs, d_vals, d_perms,
-                                     e->d_counters, e->sm_count, e->s_compute, d_xf));
+    CT_CUDA(e, ct::launch_pairs_list(e->plan, e->d_centred, (int)e->M, e->K, d.pairs, n_pairs, d.vals, d.perms,
+                                     e->d_counters, e->sm_count, e->s_compute, d.xf));
     CT_CUDA(e, cudaEventRecord(e->ev_b, e->s_compute));
     CT_CUDA(e, cudaStreamSynchronize(e->s_compute));
     float ms = 0.f;
     CT_CUDA(e, cudaEventElapsedTime(&ms, e->ev_a, e->ev_b));
     e->stats.kernel_ms = ms; e->stats.pair_ms = ms; e->stats.gram_ms = 0.0; e->stats.total_ms = ms; e->stats.d2h_ms = 0.0;
-    CT_CUDA(e, cudaMemcpy(values, d_vals, sizeof(double) * (size_t)n_pairs, cudaMemcpyDeviceToHost));
-    if (perms) CT_CUDA(e, cudaMemcpy(perms, d_perms, sizeof(int) * (size_t)n_pairs * e->K, cudaMemcpyDeviceToHost));
-    if (transforms) CT_CUDA(e, cudaMemcpy(transforms, d_xf, sizeof(double) * 12 * (size_t)n_pairs, cudaMemcpyDeviceToHost));
-    cudaFree(d_pairs); cudaFree(d_vals); cudaFree(d_perms); cudaFree(d_xf);
+    CT_CUDA(e, cudaMemcpy(values, d.vals, sizeof(double) * (size_t)n_pairs, cudaMemcpyDeviceToHost));
+    if (perms) CT_CUDA(e, cudaMemcpy(perms, d.perms, sizeof(int) * (size_t)n_pairs * e->K, cudaMemcpyDeviceToHost));
+    if (transforms) CT_CUDA(e, cudaMemcpy(transforms, d.xf, sizeof(double) * 12 * (size_t)n_pairs, cudaMemcpyDeviceToHost));
     int rc = finish_stats(e, n_pairs, 1);
     if (rc) return rc;
     if (stats) *stats = e->stats;
@@ -639,6 +726,7 @@ int ct_matrix_consumers(ct_engine* e, const double* distmat, int64_t M, const in
     CT_CUDA(e, cudaEventRecord(e->ev_a, e->s_compute));
     if (distmat) {
         e->slab_full_M = 0;
+        e->reserved_M = 0;
         if ((rc = ensure(e, e->d_slab, e->slab_cap, (size_t)L))) return rc;
         CT_CUDA(e, cudaMemcpyAsync(e->d_slab, distmat, sizeof(double) * (size_t)L, cudaMemcpyHostToDevice, e->s_compute));
         e->slab_full_M = M;
@@ -688,6 +776,7 @@ int ct_linkage(ct_engine* e, const double* distmat, int64_t M, int32_t method, d
     CT_CUDA(e, cudaEventRecord(e->ev_a, e->s_compute));
     if (distmat) {
         e->slab_full_M = 0;
+        e->reserved_M = 0;
         if ((rc = ensure(e, e->d_slab, e->slab_cap, (size_t)L))) return rc;
         CT_CUDA(e, cudaMemcpyAsync(e->d_slab, distmat, sizeof(double) * (size_t)L, cudaMemcpyHostToDevice, e->s_compute));
         e->slab_full_M = M;

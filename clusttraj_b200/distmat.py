@@ -121,6 +121,16 @@ def condensed_matrix(atomic_nums, coords, opts, devices=None, out=None, return_s
     cuts = slab_bounds(M, len(devices))
     stats = [None] * len(devices)
     errors = []
+    # Several GPUs: the slabs also land in the first GPU's memory, chunk by chunk over NVLink while the next chunk is
+    # computed (ct_rmsd_rows_gather), so that the clustering and the matrix consumers that follow
+    # (clusttraj_b200.classify) find the whole matrix resident instead of uploading 8 L bytes again.  Only when it fits
+    # with room to spare for the clustering's working copy.
+    root = None
+    if len(devices) > 1 and os.environ.get("CLUSTTRAJ_B200_GATHER", "1") != "0":
+        cand = _engine_for(devices[0])
+        if 8 * total * 2.5 < cand.free_memory():
+            cand.matrix_reserve(M)
+            root = cand
 
     def work(k):
         try:
@@ -128,8 +138,11 @@ def condensed_matrix(atomic_nums, coords, opts, devices=None, out=None, return_s
             eng.load_frames(coords, atomic_nums, opts)
             lo = cuts[k] * M - cuts[k] * (cuts[k] + 1) // 2
             n = eng.rows_pairs(cuts[k], cuts[k + 1])
-            _, st = eng.rmsd_rows(cuts[k], cuts[k + 1], out[lo: lo + n])
-            stats[k] = dict(st, device=devices[k], rows=(cuts[k], cuts[k + 1]))
+            if root is not None:
+                _, st = eng.rmsd_rows_gather(cuts[k], cuts[k + 1], root, out[lo: lo + n])
+            else:
+                _, st = eng.rmsd_rows(cuts[k], cuts[k + 1], out[lo: lo + n])
+            stats[k] = dict(st, device=devices[k], rows=(cuts[k], cuts[k + 1]), gathered_on=devices[0] if root is not None else None)
         except Exception as exc:  # surfaced below, on the caller's thread
             errors.append(exc)
 
@@ -143,6 +156,8 @@ def condensed_matrix(atomic_nums, coords, opts, devices=None, out=None, return_s
             t.join()
     if errors:
         raise errors[0]
+    if root is not None:
+        root.matrix_commit(M, out)
     return (out, stats) if return_stats else out
 
 

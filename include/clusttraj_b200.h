@@ -100,6 +100,24 @@ int ct_rmsd_rows_device(ct_engine* e, int64_t row_begin, int64_t row_end, const 
 /* Copy entries [offset, offset+count) of the last device slab to host memory. */
 int ct_copy_slab(ct_engine* e, int64_t offset, int64_t count, double* out);
 
+/* Multi-GPU hand-off of the matrix to the consumers that stay on the GPU ("device-resident full
+ * matrix for GPU linkage"; consumers at clusttraj/classify.py:100,146-177).  The reference's Pool over rows
+ * (distmat.py:73-78) becomes one engine + one host thread per GPU, each owning a contiguous slab of rows; instead of
+ * sending every slab to the host and uploading the whole vector again for the clustering, the slabs also land, chunk by
+ * chunk while the next chunk is computed, in ONE GPU's memory:
+ *   ct_matrix_reserve(root, M)        room for the whole condensed matrix of M frames on root's GPU;
+ *   ct_rmsd_rows_gather(e, r0, r1, out, root, stats)
+ *                                     ct_rmsd_rows(e, r0, r1, out, stats) that additionally copies the rows into root's
+ *                                     matrix at their own place in the condensed vector: in place when e == root, else
+ *                                     GPU -> GPU with cudaMemcpyPeerAsync (NVLink when peer access is available).
+ *                                     `out` (host) may be NULL when only the device-resident matrix is wanted.  Engines
+ *                                     with disjoint row ranges may gather into the same root from different host threads;
+ *   ct_matrix_commit(root, M)         after every gathering call has returned: the matrix is complete, and
+ *                                     ct_linkage / ct_matrix_consumers(root, NULL, M, ...) run on it without an upload. */
+int ct_matrix_reserve(ct_engine* root, int64_t M);
+int ct_rmsd_rows_gather(ct_engine* e, int64_t row_begin, int64_t row_end, double* out, ct_engine* root, ct_stats* stats);
+int ct_matrix_commit(ct_engine* root, int64_t M);
+
 /* Whole matrix in one call = build_distance_matrix (distmat.py:44-78): load + all rows. */
 int ct_rmsd_condensed(ct_engine* e, const double* coords, const int32_t* atomic_nums, int64_t M, int32_t N,
                       const ct_opts* opts, double* out, ct_stats* stats);

@@ -909,3 +909,90 @@ def test_resident_matrix_is_reused_only_for_the_trusted_array():
     assert (classify.find_medoids_from_clusters(d, labels) == med).all()
     classify.trust_resident(None)
     assert classify.linkage(d, "average").tobytes() == Z0.tobytes()
+
+
+def test_gather_into_a_reserved_matrix_on_one_gpu():
+    """ct_matrix_reserve / ct_rmsd_rows_gather / ct_matrix_commit with two engines on the SAME GPU: each engine's row slab
+    lands at its own place of the root's whole-matrix buffer (device-to-device on one GPU; over NVLink between GPUs, see
+    the next test), the host copies are bit-identical to ct_rmsd_rows, and linkage / consumers then run on the gathered
+    matrix without an upload."""
+    import scipy.cluster.hierarchy as hcl
+
+    from clusttraj_b200 import _engine
+    from clusttraj_b200.distmat import slab_bounds
+    from clusttraj_b200.synth import make_trajectory
+
+    M = 1100
+    atoms, coords = make_trajectory(M, 30, seed=77, n_modes=6)
+    os.environ["CLUSTTRAJ_B200_CHUNK_ENTRIES"] = "50000"      # several chunks per slab
+    try:
+        root, other = _engine.Engine(0), _engine.Engine(0)
+    finally:
+        del os.environ["CLUSTTRAJ_B200_CHUNK_ENTRIES"]
+    for e in (root, other):
+        e.load_frames(coords, atoms, engine_opts())
+    want, _ = root.rmsd_rows(0, M)
+    want = want.copy()
+    cuts = slab_bounds(M, 2)
+    with pytest.raises(_engine.EngineError, match="ct_matrix_reserve"):
+        other.rmsd_rows_gather(cuts[1], cuts[2], root)
+    root.matrix_reserve(M)
+    with pytest.raises(_engine.EngineError, match="no whole matrix"):
+        root.linkage(M, "average")                             # reserved is not yet complete
+    n0 = root.rows_pairs(cuts[0], cuts[1])
+    a, st_a = root.rmsd_rows_gather(cuts[0], cuts[1], root)    # in place + host copy
+    _, st_b = other.rmsd_rows_gather(cuts[1], cuts[2], root, to_host=False)   # device only
+    assert st_a["launches"] > 2 and st_b["pairs"] == len(want) - n0
+    assert np.array_equal(a, want[:n0])
+    root.matrix_commit(M)
+    assert np.array_equal(root.copy_slab(0, len(want)), want)
+    Z, st = root.linkage(M, "average")
+    assert Z.tobytes() == hcl.linkage(want, "average").tobytes() and st["h2d_ms"] < 0.5
+    total, _, _ = root.matrix_consumers(M)
+    assert abs(total - want.sum()) <= 1e-12 * want.sum()
+    with pytest.raises(_engine.EngineError, match="reserved"):
+        other.matrix_commit(M)
+    root.close(); other.close()
+
+
+def test_in_process_multi_gpu_slabs():
+    """condensed_matrix(devices=[0, 1, ...]) — the in-process multi-GPU path the CLI uses (one engine + one host thread
+    per GPU, equal-area row slabs): bit-identical to one GPU, and the whole matrix is left resident on the first GPU
+    (gathered over NVLink) so that the clustering that follows uploads nothing.  With a single visible GPU the same code
+    runs with both slabs on device 0 through two passes."""
+    import scipy.cluster.hierarchy as hcl
+
+    from clusttraj_b200 import _engine, classify
+    from clusttraj_b200 import distmat as D
+    from clusttraj_b200.synth import make_trajectory
+
+    n = min(_engine.device_count(), 4)
+    if n < 2:
+        pytest.skip("needs two GPUs (the single-GPU gather test covers the same-device path)")
+    M = 3000
+    atoms, coords = make_trajectory(M, 40, seed=12, n_modes=6)
+    one = D.condensed_matrix(atoms, coords, engine_opts(), devices=[0]).copy()
+    many, stats = D.condensed_matrix(atoms, coords, engine_opts(), devices=list(range(n)), return_stats=True)
+    assert len(stats) == n and all(s["gathered_on"] == 0 for s in stats)
+    assert sum(s["pairs"] for s in stats) == M * (M - 1) // 2
+    assert np.array_equal(many, one)
+    root = D._engine_for(0)
+    assert np.array_equal(root.copy_slab(0, len(one)), one)            # gathered copy on GPU 0
+    classify.trust_resident(many)
+    Z = classify.linkage(many, "average")
+    assert root.stats()["h2d_ms"] < 0.5                                # no re-upload of the 36 MB matrix
+    assert Z.tobytes() == hcl.linkage(one, "average").tobytes()
+    classify.trust_resident(None)
+    # Hungarian mode through the per-pair kernel, and the streaming-only fall-back (gather switched off)
+    from clusttraj_b200.synth import make_solute_solvent
+
+    atoms, coords = make_solute_solvent(40, n_solute=12, n_solvent_mol=16, seed=2, box=7.0)
+    kw = dict(ns=12, reorder=True)
+    assert np.array_equal(D.condensed_matrix(atoms, coords, engine_opts(**kw), devices=list(range(n))),
+                          D.condensed_matrix(atoms, coords, engine_opts(**kw), devices=[0]))
+    os.environ["CLUSTTRAJ_B200_GATHER"] = "0"
+    try:
+        plain = D.condensed_matrix(atoms, coords, engine_opts(**kw), devices=list(range(n)))
+    finally:
+        del os.environ["CLUSTTRAJ_B200_GATHER"]
+    assert np.array_equal(plain, D.condensed_matrix(atoms, coords, engine_opts(**kw), devices=[0]))
