@@ -443,7 +443,7 @@ def measure(job, name, scaling, steps, warmup, sample_clocks=False, light_warmup
         "name": name, "scaling": scaling, "M": M, "N": int(N), "K": K, "kw": kw, "rows": (r0, r1), "my_pairs": my_pairs,
         "total_pairs": int(total_pairs), "value": value, "ms_per_step": dev_ms / steps, "steps": steps, "warmup": warmup,
         "e2e_value": e2e_value, "e2e_ms_per_step": e2e_total / steps, "h2d": int(coords.nbytes + atoms.nbytes),
-        "d2h": int(8 * my_pairs), "launches": launches, "clocks": clocks, "wall_ms": wall_ms, "flagged": flagged,
+        "d2h": int(8 * my_pairs), "launches": int(job.sum(float(launches))), "clocks": clocks, "wall_ms": wall_ms, "flagged": flagged,
         "checksum": checksum, "parity": parity,
         "roofline": roofline_of(name, kw, M, K, r0, r1, my_pairs, float(np.mean(gram_ms)), st),
         "_state": (eng, atoms, coords, pinned_in, opts),
@@ -530,6 +530,7 @@ def run_b200_arm(args, rank, world, local_rank, backend="nccl"):
             "cpu_baseline": cpu,
             "e2e": {"value": head["e2e_value"], "unit": "pairs/s", "h2d_bytes_per_step": head["h2d"],
                     "d2h_bytes_per_step": head["d2h"], "ms_per_step": head["e2e_ms_per_step"],
+                    "h2d_bytes_per_step_all_ranks": head["h2d"] * world, "d2h_bytes_per_step_all_ranks": 8 * head["total_pairs"],
                     "note": "ct_load_frames (pinned H2D + K1) + ct_rmsd_rows (K2, fix-up, chunked D2H into pinned "
                             "host memory, overlapped); bytes are per rank"},
             "parity": head["parity"],

@@ -4,9 +4,11 @@ The shared library is written next to this file (``_libclusttraj_b200.so``) so t
 GPU box with the repository snapshot.  There is no other backend: if the library is missing and cannot
 be built, importing the engine raises.
 """
+import fcntl
 import os
 import shutil
 import subprocess
+import tempfile
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
@@ -15,7 +17,7 @@ SOURCES = ["engine.cu", "pack.cu", "gram.cu", "ozaki.cu", "consumers.cu", "linka
 HEADERS = ["common.cuh", "solve3x3.cuh", os.path.join("..", "..", "include", "clusttraj_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared", "--use_fast_math=false",
+    "-Xcompiler", "-fPIC", "-shared",
 ]
 
 
@@ -35,18 +37,31 @@ def is_stale():
 
 
 def build(force=False, verbose=False):
-    """Compile every kernel for sm_100a into one shared library; returns its path."""
+    """Compile every kernel for sm_100a into one shared library; returns its path.  Safe under several processes
+    (torchrun ranks, pytest-xdist workers): one builds under a file lock into its own temporary file and publishes it
+    with an atomic rename, the others wait for the lock and find the library fresh."""
     if not force and not is_stale():
         return LIB
-    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
-    cmd = [_nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + \
-          [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB + ".tmp"]
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
-    os.replace(LIB + ".tmp", LIB)
-    if verbose:
-        print(proc.stderr)
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():   # another process built it while we waited
+                return LIB
+            fd, tmp = tempfile.mkstemp(prefix="_libclusttraj_b200.", suffix=".so.tmp", dir=HERE)
+            os.close(fd)
+            cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+                  [os.path.join(CSRC, s) for s in SOURCES] + ["-o", tmp]
+            proc = subprocess.run(cmd, capture_output=True, text=True)
+            if proc.returncode != 0:
+                if os.path.exists(tmp):
+                    os.unlink(tmp)
+                raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+            os.chmod(tmp, 0o755)
+            os.replace(tmp, LIB)
+            if verbose:
+                print(proc.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 

@@ -60,12 +60,21 @@ def load_library(build_if_missing=True):
         if build_if_missing and _build.is_stale():
             try:
                 _build.build()
-            except Exception as exc:  # a prebuilt .so that merely looks stale is still usable
+            except Exception as exc:
                 if not os.path.exists(path):
                     raise EngineError(f"clusttraj_b200: CUDA engine is not built and cannot be built: {exc}") from exc
+                # a prebuilt library older than its sources (e.g. a box without nvcc): usable only if it still exports
+                # the whole ABI, which is checked below; say so instead of running outdated kernels silently
+                import warnings
+                warnings.warn(f"clusttraj_b200: {path} is older than its sources and could not be rebuilt ({exc}); "
+                              "loading the existing library", RuntimeWarning)
         if not os.path.exists(path):
             raise EngineError("clusttraj_b200: CUDA engine library missing (run `python -m clusttraj_b200._build`)")
         lib = C.CDLL(path)
+        missing = [name for name in EXPORTS if not hasattr(lib, name)]
+        if missing:
+            raise EngineError(f"clusttraj_b200: {path} is out of date (missing C-ABI symbols {missing}); rebuild it with "
+                              "`python -m clusttraj_b200._build`")
         P = C.POINTER
         lib.ct_version.restype = C.c_char_p
         lib.ct_device_count.restype = C.c_int

@@ -47,6 +47,21 @@ def _n_frames(distmat):
 
 GPU_LINKAGE_METHODS = ("single", "complete", "average", "weighted", "ward")
 
+def _value_errors(call, *args, **kw):
+    """scipy.cluster.hierarchy.linkage raises ValueError on NaN / infinite distances (non-finite coordinates are a
+    supported input of the matrix kernels, so such a matrix can reach us).  The engine checks the matrix where it lies
+    (one pass over the resident copy, ct_linkage / ct_matrix_consumers; the medoid reduction also needs distances >= 0)
+    and reports SciPy's wording: surfaced here as the ValueError the reference's callers expect (main.py:53-66)."""
+    from ._engine import EngineError
+
+    try:
+        return call(*args, **kw)
+    except EngineError as exc:
+        msg = str(exc)
+        if "condensed distance matrix must" in msg:
+            raise ValueError(msg[msg.index("The condensed") if "The condensed" in msg else msg.index("the condensed"):]) from exc
+        raise
+
 
 def linkage(distmat, method="average", optimal_ordering=False):
     """scipy.cluster.hierarchy.linkage(distmat, method, optimal_ordering=...) with the clustering itself on the GPU:
@@ -59,7 +74,7 @@ def linkage(distmat, method="average", optimal_ordering=False):
         return hcl.linkage(distmat, method, optimal_ordering=bool(optimal_ordering))
     M = _n_frames(distmat)
     eng = _engine_for(visible_devices()[0])
-    Z, _ = eng.linkage(M, method, distmat=distmat, trusted=_trusted(distmat))
+    Z, _ = _value_errors(eng.linkage, M, method, distmat=distmat, trusted=_trusted(distmat))
     if optimal_ordering:
         Z = hcl.optimal_leaf_ordering(Z, distmat)
     return Z
@@ -132,7 +147,7 @@ def find_medoids_from_clusters(distmat, clusters):
     if clusters.shape != (M,):
         raise ValueError("clusters must hold one label per frame")
     eng = _engine_for(visible_devices()[0])
-    _, medoids, _ = eng.matrix_consumers(M, clusters=clusters, distmat=distmat, trusted=_trusted(distmat))
+    _, medoids, _ = _value_errors(eng.matrix_consumers, M, clusters=clusters, distmat=distmat, trusted=_trusted(distmat))
     return medoids.astype(int)
 
 

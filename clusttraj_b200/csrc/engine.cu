@@ -137,6 +137,39 @@ static int ensure(ct_engine* e, T*& ptr, size_t& cap, size_t need) {
     return CT_OK;
 }
 
+// scipy.cluster.hierarchy.linkage refuses NaN / infinite distances with a ValueError; the medoid reduction orders sums by
+// their bit patterns, which needs distances >= 0.  One pass over the resident matrix: flag[0] = entries that are not
+// finite, flag[1] = negative entries.
+__global__ void __launch_bounds__(256) matrix_check_kernel(const double* __restrict__ d, long long n, unsigned long long* flag) {
+    unsigned long long bad = 0, neg = 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        const double v = d[k];
+        bad += !(fabs(v) <= 1.7976931348623157e308);
+        neg += v < 0.0;
+    }
+    bad = __reduce_add_sync(0xffffffffu, (unsigned)bad);
+    neg = __reduce_add_sync(0xffffffffu, (unsigned)neg);
+    if ((threadIdx.x & 31) == 0) {
+        if (bad) atomicAdd(flag, bad);
+        if (neg) atomicAdd(flag + 1, neg);
+    }
+}
+
+// CT_ERR_ARG with SciPy's wording when the matrix resident in e->d_slab holds non-finite (or, for the medoids, negative) values
+static int check_matrix_values(ct_engine* e, long long L, bool refuse_negative, const char* who) {
+    CT_CUDA(e, cudaMemsetAsync(e->d_counters + 2, 0, sizeof(unsigned long long) * 2, e->s_compute));
+    matrix_check_kernel<<<e->sm_count * 8, 256, 0, e->s_compute>>>(e->d_slab, L, e->d_counters + 2);
+    CT_CUDA(e, cudaGetLastError());
+    unsigned long long c[2];
+    CT_CUDA(e, cudaMemcpyAsync(c, e->d_counters + 2, sizeof c, cudaMemcpyDeviceToHost, e->s_compute));
+    CT_CUDA(e, cudaStreamSynchronize(e->s_compute));
+    if (c[0]) return fail(e, CT_ERR_ARG, std::string(who) + ": The condensed distance matrix must contain only finite values.");
+    if (c[1] && refuse_negative)
+        return fail(e, CT_ERR_ARG, std::string(who) + ": the condensed distance matrix must not contain negative distances.");
+    return CT_OK;
+}
+
 extern "C" {
 
 const char* ct_version(void) { return "clusttraj_b200 0.1 (sm_100a)"; }
@@ -735,6 +768,7 @@ int ct_matrix_consumers(ct_engine* e, const double* distmat, int64_t M, const in
                                      "(pass distmat, or call ct_rmsd_rows_device(e, 0, M, ...) first)");
     }
     CT_CUDA(e, cudaEventRecord(e->ev_b, e->s_compute));
+    if (n_clusters > 0 && (rc = check_matrix_values(e, L, true, "ct_matrix_consumers"))) return rc;
     if ((rc = ensure(e, e->d_cons, e->cons_cap, (size_t)ct::consumers_scratch_doubles((int)M)))) return rc;
     if (n_clusters > 0) {
         if ((rc = ensure(e, e->d_labels, e->labels_cap, (size_t)M))) return rc;
@@ -785,6 +819,7 @@ int ct_linkage(ct_engine* e, const double* distmat, int64_t M, int32_t method, d
                                      "(pass distmat, or call ct_rmsd_rows_device(e, 0, M, ...) first)");
     }
     CT_CUDA(e, cudaEventRecord(e->ev_b, e->s_compute));
+    if ((rc = check_matrix_values(e, L, false, "ct_linkage"))) return rc;
     // scratch for the matrix the algorithm updates (the matrix itself stays intact, like SciPy's input): the square form
     // (M x M, persistent cluster kernel) when it fits, else a condensed copy (step-launch variant)
     {

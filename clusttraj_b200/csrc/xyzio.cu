@@ -237,11 +237,21 @@ static bool parse_pdb_frame(const Frames& f, size_t fr, double* xyz, int32_t* zs
             int z;
             if (n > 0) z = atomic_number(el, n);
             else {
-                char name[8];
-                int m = letters_of(p, eol, 12, 16, name);
-                if (m > 2) m = 2;                                              // [:2]
-                if (lookup_symbol(name, m) < 0) m = m > 1 ? 1 : m;              // not an element: its first letter
-                z = atomic_number(name, m);
+                // no element columns: the alignment convention of the atom-name field, clusttraj_b200/xyz.py:pdb_element_from_name
+                char name[5] = {' ', ' ', ' ', ' ', '\0'};
+                for (int t = 0; t < 4 && p + 12 + t < eol; ++t) name[t] = p[12 + t];
+                char sym[3] = {0, 0, 0};
+                int m = 0;
+                if (std::isalpha((unsigned char)name[0])) {
+                    const bool four = name[1] != ' ' && name[2] != ' ' && name[3] != ' ';
+                    sym[0] = name[0]; sym[1] = name[1];
+                    if (std::isalpha((unsigned char)name[1]) && lookup_symbol(sym, 2) >= 0 && !((name[0] == 'H' || name[0] == 'h') && four)) m = 2;
+                    else m = 1;
+                } else {
+                    for (int t = 1; t < 4 && !m; ++t)
+                        if (std::isalpha((unsigned char)name[t])) { sym[0] = name[t]; m = 1; }
+                }
+                z = m ? atomic_number(sym, m) : -1;
             }
             if (z < 0) { err = "frame " + std::to_string(fr) + ": unknown element"; return false; }
             if (!field_number(p, eol, 30, 38, xyz[3 * k]) || !field_number(p, eol, 38, 46, xyz[3 * k + 1]) ||

@@ -1,7 +1,9 @@
 """Option carrier, logger and command-line parsing with the reference's names and semantics
 (clusttraj/io.py:42-579), re-hosted without its hard imports of ``rmsd`` / ``openbabel`` (neither is
-needed: reordering runs inside the CUDA engine and XYZ is read natively).  Structure writers
-(io.py:582-1015) are outside the accelerated path and not provided."""
+needed: reordering runs inside the CUDA engine and XYZ / PDB / GRO are read natively), and the structure writers
+(io.py:582-1015: align_mol, save_clusters_config, save_medoids_config) with their arithmetic on the GPU
+(ct_pair_transforms) and the .xyz text written natively (ct_format_xyz); other output formats need OpenBabel and are
+refused loudly, as are the matplotlib plots (-p)."""
 import argparse
 import logging
 import os
@@ -15,6 +17,8 @@ from . import reorder as _reorder
 
 LINKAGE_METHODS = ("single", "complete", "average", "weighted", "centroid", "median", "ward")
 REORDER_ALGS = ("inertia-hungarian", "hungarian", "brute", "distance", "qml")  # names the reference accepts
+NATIVE_INPUT_FORMATS = ("xyz", "pdb", "ent", "gro")   # read by clusttraj_b200/xyz.py (ct_read_xyz / _pdb / _gro), case-insensitive
+NATIVE_OUTPUT_FORMATS = ("xyz",)                      # written by ct_format_xyz
 
 header_string = """
 clusttraj (B200 engine) - a solvent-informed tool for clustering trajectories.
@@ -149,7 +153,7 @@ def _parser() -> argparse.ArgumentParser:
     p = argparse.ArgumentParser(
         prog="clusttraj_b200",
         description="Hierarchical clustering of a trajectory on the minimum-RMSD matrix (computed on B200 GPUs).")
-    p.add_argument("trajectory_file", type=extant_file, help="trajectory file (.xyz natively)")
+    p.add_argument("trajectory_file", type=extant_file, help="trajectory file (.xyz, .pdb / .ent, .gro natively)")
     p.add_argument("-f", "--force-overwrite", dest="force", action="store_true")
     p.add_argument("-np", "--nprocesses", type=check_positive, default=4,
                    help="kept for compatibility; the engine uses GPUs, not worker processes")
@@ -185,8 +189,9 @@ def configure_runtime(args_in) -> ClustOptions:
     parser = _parser()
     args = parser.parse_args(args_in)
     Logger.setup(args.log)
-    ext = os.path.splitext(args.trajectory_file)[1][1:].lower()
-    if ext != "xyz":
+    ext = os.path.splitext(args.trajectory_file)[1][1:]
+    if ext.lower() not in NATIVE_INPUT_FORMATS:
+        # formats without a native reader go through OpenBabel when it is installed (the reference's check, io.py:424-427)
         try:
             from openbabel import pybel
             ok = ext in pybel.informats
@@ -200,8 +205,14 @@ def configure_runtime(args_in) -> ClustOptions:
         parser.error(f"The reorder method you selected with --reorder-method ({args.reorder_alg}) is not valid.")
     if args.reorder and args.reorder_alg in ("brute", "qml"):
         parser.error(f"--reorder-alg {args.reorder_alg} is not implemented by the B200 engine (use hungarian or distance).")
-    if args.clusters_configurations or args.medoids_configurations or args.plot:
-        parser.error("-cc / -mc / -p need OpenBabel writers and matplotlib, which are outside the B200 engine.")
+    if args.clusters_configurations and args.clusters_configurations not in NATIVE_OUTPUT_FORMATS:
+        parser.error("The format you selected to save the clustered superposed configurations "
+                     f"({args.clusters_configurations}) is not valid: clusttraj_b200 writes xyz (other formats need OpenBabel).")
+    if args.medoids_configurations and args.medoids_configurations not in NATIVE_OUTPUT_FORMATS:
+        parser.error(f"The format you selected to save the superposed medoids ({args.medoids_configurations}) is not valid: "
+                     "clusttraj_b200 writes xyz (other formats need OpenBabel).")
+    if args.plot:
+        parser.error("-p needs matplotlib plots, which are outside the B200 engine (SURVEY.md: out of scope).")
     if args.reorder_exclusions and args.no_hydrogen:
         parser.error("You cannot use --no-hydrogen and reorder exclusions with -eex at the same time")
     if not args.reorder and args.reorder_exclusions:

@@ -62,7 +62,7 @@ def read_xyz(path):
     try:
         from . import _engine
         native = _engine.read_xyz_native(path)
-    except (ImportError, OSError, _engine.EngineError):
+    except Exception:   # library missing / cannot be built (EngineError), dlopen failure: the readers below need no library
         native = None
     if native is not None:
         return native
@@ -99,9 +99,31 @@ def _native(path, fmt):
         return None
 
 
+def pdb_element_from_name(field):
+    """Element symbol for an ATOM/HETATM record WITHOUT element columns, from the atom-name field (columns 13-16) by the
+    alignment convention of the PDB format (wwPDB format guide, ATOM record: "Alignment of one-letter atom name such as C
+    starts at column 14, while two-letter atom name such as FE starts at column 13"):
+      * column 13 blank or a digit -> the first letter that follows is a one-letter element (" CA " alpha carbon -> C,
+        "1HG2" -> H, " OW " -> O);
+      * column 13 a letter -> the two-letter symbol in columns 13-14 when that is an element ("FE  ", "CL  ", "CA  " =
+        calcium, "ZN  "), except the four-character hydrogen names that have to start in column 13 ("HG12", "HD21": H);
+        otherwise the letter in column 13 ("C12 " from a writer that left-justifies -> C)."""
+    name = (field + "    ")[:4]
+    if name[0].isalpha():
+        two = name[:2]
+        if name[1].isalpha() and two.lower() in Z_OF and not (name[0] in "Hh" and " " not in name):
+            return two
+        return name[0]
+    for ch in name[1:]:
+        if ch.isalpha():
+            return ch
+    return name.strip()[:1]
+
+
 def read_pdb(path, native=True):
     """MODEL/ENDMDL frames of a PDB file (or a single frame without MODEL records): ATOM/HETATM records, element
-    from columns 77-78 when present, else from the atom name (columns 13-16) the way OpenBabel guesses it.  Parsed by the
+    from columns 77-78 when present, else from the atom name (columns 13-16) by the format's alignment convention
+    (pdb_element_from_name).  Parsed by the
     engine library's parallel reader (ct_read_pdb) when it accepts the file, else by the line loop below."""
     got = _native(path, "pdb") if native else None
     if got is not None:
@@ -119,11 +141,7 @@ def read_pdb(path, native=True):
         for line in fh:
             rec = line[:6]
             if rec in ("ATOM  ", "HETATM"):
-                el = line[76:78].strip()
-                if not el:
-                    el = "".join(ch for ch in line[12:16] if ch.isalpha())[:2].strip()
-                    if el.lower() not in Z_OF:
-                        el = el[:1]
+                el = line[76:78].strip() or pdb_element_from_name(line[12:16])
                 z.append(_atomic_number(el))
                 x.append((float(line[30:38]), float(line[38:46]), float(line[46:54])))
             elif rec.startswith("ENDMDL") or rec.startswith("END"):

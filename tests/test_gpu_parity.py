@@ -490,6 +490,46 @@ def test_int8_kernel_error_is_a_rigid_input_perturbation():
     e.close()
 
 
+@pytest.mark.parametrize("K", [100, 300])
+def test_int8_kernel_accuracy_at_the_edge_of_its_acceptance_window(K):
+    """The edge of the automatic int8 choice: coordinates just under 256 A from the centroid (the coarsest quantum the engine
+    accepts, 2^-22 A = 2.4e-7 A) and near-duplicate frames whose cancelling E = G_i + G_j - 2 lambda straddles the flag
+    threshold 1e-9 (G_i + G_j): pairs just above it are NOT re-done by the FP64 fix-up and carry the whole quantisation
+    error amplified by 1 / (2 K RMSD).  Every pair (exact duplicates included) must still be within the north star's
+    1e-6 A of the oracle's value for the UNROUNDED coordinates."""
+    from clusttraj_b200.synth import _random_rotations
+
+    rng = np.random.default_rng(300 + K)
+    M = 56
+    base = rng.normal(size=(K, 3))
+    base *= (250.0 * rng.uniform(0.0, 1.0, size=(K, 1)) ** (1.0 / 3.0)) / np.linalg.norm(base, axis=1, keepdims=True)   # ball
+    base -= base.mean(axis=0)
+    base *= 254.0 / np.linalg.norm(base, axis=1).max()      # the farthest atom 254 A from the centroid, whatever the rotation
+    g_half = 0.5 * (base ** 2).sum()
+    # noise per frame such that pair RMSDs run from 0.4x to 2.5x the threshold RMSD sqrt(1e-9 * 2 (G_i + G_j) / 2 / K)
+    thr = np.sqrt(1e-9 * 4.0 * g_half / K)
+    sig = thr * np.linspace(0.25, 1.6, M) / np.sqrt(3.0)
+    frames = base[None] + rng.normal(size=(M, K, 3)) * sig[:, None, None]
+    frames[1] = frames[0]                      # exact duplicates (one left unrotated)
+    frames[2] = frames[0]
+    R = _random_rotations(rng, M)
+    R[1] = np.eye(3)
+    frames = np.einsum("mnk,mjk->mnj", frames, R)
+    atoms = np.full(K, 6, dtype=np.int32)
+    e = _engine_with(None)
+    got, st = _full(e, atoms, frames)
+    assert st["gram_path"] == 2 and st["quant_step"] == 2.0 ** -22, st      # int8 kernel at its coarsest accepted quantum
+    want = oracle_rows(atoms, frames, range(M), n_workers=4)
+    ratio = (want ** 2) * K / (4.0 * g_half) / 1e-9                          # E / (1e-9 (G_i + G_j)) per pair
+    just_above = (ratio > 1.0) & (ratio < 1.5)
+    assert just_above.sum() >= 50 and (ratio < 1.0).sum() >= 50, (just_above.sum(), (ratio < 1.0).sum())
+    assert 0 < st["flagged"] < len(want)                                    # both sides of the threshold were exercised
+    err = np.abs(got - want)
+    assert err.max() <= 1e-6, (err.max(), err.max() / st["quant_step"])
+    assert err[just_above].max() <= 1e-6 and got[0] <= 1e-6 and got[1] <= 1e-6   # (0,1), (0,2): duplicates
+    e.close()
+
+
 # ---- consumers of the matrix: sum_distmat / find_medoids_from_clusters (clusttraj/classify.py:146-177) -----------------
 
 def _consumer_cases(golden_dir):
@@ -598,7 +638,51 @@ def test_cli_config1_end_to_end(golden_dir, tmp_path):
     assert (np.loadtxt(tmp_path / "clusters.dat", dtype=int) == [1, 2, 3]).all()
     text = open(tmp_path / "clusters.out").read()
     assert "3 cluster(s)" in text and "The total sum of the RMSD matrix is 12.2554" in text
-    assert "1\t1\t0" in text and "3\t1\t2" in text   # every frame is the medoid of its own cluster
+    # the reference's summary text (main.py:107-135): every frame is the medoid of its own cluster
+    assert "The index for the medoids are:\n0 1 2 \n\nThe cluster sizes are:\nCluster\tSize\n1\t1\n2\t1\n3\t1\n" in text
+
+
+def test_cli_structure_output_native_formats_and_clean_errors(golden_dir, tmp_path):
+    """ADVICE round 1 through the CLI: -cc xyz -mc xyz write the superposed structures (native writers); .pdb and .gro
+    trajectories run without OpenBabel; -nc beyond the number of snapshots and a matrix with NaNs (-i) end in the
+    reference's clean SystemExit (main.py:53-66; SciPy's ValueError for non-finite distances) instead of a traceback."""
+    import shutil
+
+    from clusttraj_b200.main import main
+
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        traj = str(tmp_path / "testtraj.xyz")
+        shutil.copy(os.path.join(golden_dir, "ref_testtraj.xyz"), traj)
+        assert main([traj, "-rmsd", "4.4", "-m", "average", "-f", "-cc", "xyz", "-mc", "xyz", "-v"]) == 0
+        clusters = np.loadtxt(tmp_path / "clusters.dat", dtype=int)
+        assert list(clusters) == [1, 1, 2]        # Z = [[0,1,3.416..],[2,3,4.4197..]] (SURVEY 8c(3)) cut at 4.4
+        from clusttraj_b200.xyz import read_xyz
+
+        a1, c1 = read_xyz(str(tmp_path / "clusters_confs_1.xyz"))
+        a2, c2 = read_xyz(str(tmp_path / "clusters_confs_2.xyz"))
+        am, cm = read_xyz(str(tmp_path / "clusters_medoids.xyz"))
+        assert c1.shape == (2, 41, 3) and c2.shape == (1, 41, 3) and cm.shape == (2, 41, 3)
+        # the members of cluster 1 are superposed on its medoid: their plain Kabsch RMSD is the matrix entry (0, 1)
+        d = np.load(tmp_path / "distmat.npy")
+        assert abs(np.sqrt(((c1[0] - c1[1]) ** 2).sum() / 41) - d[0]) < 2e-5    # files hold 5 decimals
+        with pytest.raises(SystemExit, match="Cannot request 5 clusters from 3 snapshots"):
+            main([traj, "-nc", "5", "-f"])
+        bad = d.copy()
+        bad[1] = np.nan
+        np.save(tmp_path / "bad.npy", bad)
+        with pytest.raises(SystemExit, match="must contain only finite values"):
+            main([traj, "-rmsd", "1.0", "-f", "-i", str(tmp_path / "bad.npy")])
+        for name, n_frames in (("hand_elements.pdb", 2), ("hand_noelements.pdb", 2), ("hand_water.gro", 2)):
+            src = str(tmp_path / name)
+            shutil.copy(os.path.join(golden_dir, name), src)
+            assert main([src, "-rmsd", "0.01", "-f", "-od", str(tmp_path / (name + ".npy"))]) == 0
+            dd = np.load(tmp_path / (name + ".npy"))
+            assert dd.shape == (n_frames * (n_frames - 1) // 2,) and 0.0 < dd[0] < 1.0
+            assert list(np.loadtxt(tmp_path / "clusters.dat", dtype=int)) == [1, 2]
+    finally:
+        os.chdir(cwd)
 
 
 def test_non_finite_coordinates_take_the_fp64_kernel():

@@ -488,3 +488,80 @@ def test_native_pdb_and_gro_parsers_match_the_python_readers(tmp_path):
     assert _engine.read_xyz_native(str(badg), fmt="gro") is None
     with pytest.raises(ValueError):
         xyz.read_gro(str(badg))
+
+
+def test_hand_made_pdb_and_gro_fixtures(golden_dir):
+    """SURVEY 8f-3 pinned from OUTSIDE the repo's readers: three small files laid out by hand after the format definitions
+    (tests/golden/hand_elements.pdb, hand_noelements.pdb, hand_water.gro) with the expected atomic numbers and Angstrom
+    coordinates typed here as literals.  Both the Python line readers and the native parallel readers (ct_read_pdb /
+    ct_read_gro) must return exactly these."""
+    from clusttraj_b200 import _engine, xyz
+
+    # 1. element columns present (77-78), two MODELs, ATOM + HETATM, REMARK / CRYST1 / TER / ENDMDL / END records
+    z_want = [7, 6, 6, 8, 1, 30, 8]
+    x_want = np.array([
+        [[-1.195, 0.201, 5.124], [0.234, 0.407, 4.870], [0.986, -0.873, 4.563], [0.407, -1.952, 4.441],
+         [0.657, 0.890, 5.752], [12.500, -10.250, 100.125], [-5.000, 3.250, -7.875]],
+        [[-1.000, 0.250, 5.000], [0.250, 0.500, 4.750], [1.000, -0.750, 4.500], [0.500, -2.000, 4.250],
+         [0.750, 1.000, 5.750], [12.625, -10.125, 99.875], [-4.500, 3.125, -8.000]]])
+    path = os.path.join(golden_dir, "hand_elements.pdb")
+    for atoms, coords in (xyz.read_pdb(path, native=False), _engine.read_xyz_native(path, fmt="pdb"), xyz.read_trajectory(path)):
+        assert atoms.shape == (2, 7) and atoms.dtype == np.int32 and (atoms == z_want).all()
+        assert coords.shape == (2, 7, 3) and coords.dtype == np.float64 and np.array_equal(coords, x_want)
+    # 2. NO element columns: the alignment of the atom name decides (column 14 = one-letter element, column 13 = two letters,
+    #    four-character hydrogen names): N, C-alpha (not calcium), C, H (HG12), H (1HG2), Ca ion, Fe, Cl, O
+    z_want = [7, 6, 6, 1, 1, 20, 26, 17, 8]
+    first = np.array([[1.000, 2.000, 3.000], [2.458, 2.000, 3.000], [3.000, 3.400, 3.100], [3.500, 3.900, 4.000],
+                      [2.200, 4.100, 2.600], [10.000, -20.000, 30.000], [-1.500, 0.000, 0.500], [7.250, 7.500, 7.750],
+                      [-9.999, 99.999, -100.001]])
+    second = first.copy()
+    second[0] = [1.125, 2.250, 3.375]
+    second[8] = [-9.500, 99.500, -99.500]
+    path = os.path.join(golden_dir, "hand_noelements.pdb")
+    for atoms, coords in (xyz.read_pdb(path, native=False), _engine.read_xyz_native(path, fmt="pdb")):
+        assert atoms.shape == (2, 9) and (atoms == z_want).all()
+        assert np.array_equal(coords, np.stack([first, second]))
+    for field, want in ((" CA ", "C"), ("CA  ", "CA"), ("HG12", "H"), ("1HG2", "H"), (" OW ", "O"), ("FE  ", "FE"), ("C12 ", "C"),
+                        ("ZN", "ZN"), (" N", "N"), ("HE  ", "HE")):
+        assert xyz.pdb_element_from_name(field) == want, field
+    # 3. GROMACS .gro: positions in nm -> Angstrom, element from the atom name (OW, HW1, HW2, C1)
+    z_want = [8, 1, 1, 8, 1, 1, 6]
+    nm = np.array([
+        [[0.126, 1.624, 1.679], [0.190, 1.661, 1.747], [0.177, 1.568, 1.613], [1.275, 0.053, 0.622],
+         [1.337, 0.002, 0.680], [1.326, 0.120, 0.568], [-0.250, 2.500, 0.001]],
+        [[0.130, 1.620, 1.680], [0.195, 1.655, 1.750], [0.180, 1.565, 1.610], [1.270, 0.050, 0.625],
+         [1.335, 0.005, 0.685], [1.325, 0.125, 0.565], [-0.255, 2.505, 0.000]]])
+    path = os.path.join(golden_dir, "hand_water.gro")
+    for atoms, coords in (xyz.read_gro(path, native=False), _engine.read_xyz_native(path, fmt="gro"), xyz.read_trajectory(path)):
+        assert atoms.shape == (2, 7) and (atoms == z_want).all()
+        assert coords.shape == (2, 7, 3) and np.abs(coords - 10.0 * nm).max() < 1e-12
+    assert abs(coords[0, 0, 0] - 1.26) < 1e-12 and abs(coords[1, 6, 1] - 25.05) < 1e-12
+
+
+def test_cli_accepts_native_formats_and_xyz_structure_output(tmp_path, golden_dir):
+    """-cc xyz / -mc xyz reach the native writers, .pdb / .ent / .gro trajectories are accepted without
+    OpenBabel (case-insensitively), other output formats and -p are refused with argparse's exit."""
+    import shutil
+
+    from clusttraj_b200.io import configure_runtime
+
+    common = ["--log", str(tmp_path / "c.log"), "-oc", str(tmp_path / "clusters.dat"), "-od", str(tmp_path / "d.npy")]
+    traj = os.path.join(golden_dir, "ref_testtraj.xyz")
+    opt = configure_runtime([traj, "-rmsd", "1.0", "-cc", "xyz", "-mc", "xyz"] + common)
+    assert opt.save_confs and opt.save_medoids and opt.out_conf_fmt == "xyz" and opt.out_medoids_fmt == "xyz"
+    assert opt.out_conf_name == str(tmp_path / "clusters_confs") and opt.out_medoids_name == str(tmp_path / "clusters_medoids")
+    for bad in (["-cc", "pdb"], ["-mc", "mol2"], ["-p"]):
+        with pytest.raises(SystemExit):
+            configure_runtime([traj, "-rmsd", "1.0"] + bad + common)
+    for name in ("hand_elements.pdb", "hand_water.gro"):
+        assert configure_runtime([os.path.join(golden_dir, name), "-rmsd", "1.0"] + common).trajfile.endswith(name)
+    upper = tmp_path / "UPPER.PDB"
+    shutil.copy(os.path.join(golden_dir, "hand_elements.pdb"), upper)
+    ent = tmp_path / "pdb1abc.ent"
+    shutil.copy(os.path.join(golden_dir, "hand_elements.pdb"), ent)
+    for p in (upper, ent):
+        configure_runtime([str(p), "-rmsd", "1.0"] + common)
+    weird = tmp_path / "traj.mol2"
+    weird.write_text("x\n")
+    with pytest.raises(SystemExit):
+        configure_runtime([str(weird), "-rmsd", "1.0"] + common)
