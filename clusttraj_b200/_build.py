@@ -12,7 +12,8 @@ import tempfile
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "_libclusttraj_b200.so")
+# CLUSTTRAJ_B200_LIB / CLUSTTRAJ_B200_NVCC_FLAGS: development hooks (tools/ab_variants.sh builds kernel variants side by side)
+LIB = os.environ.get("CLUSTTRAJ_B200_LIB") or os.path.join(HERE, "_libclusttraj_b200.so")
 SOURCES = ["engine.cu", "pack.cu", "gram.cu", "ozaki.cu", "consumers.cu", "linkage.cu", "xyzio.cu", "pair.cu", "stepwise.cu"]
 HEADERS = ["common.cuh", "solve3x3.cuh", os.path.join("..", "..", "include", "clusttraj_b200.h")]
 NVCC_FLAGS = [
@@ -49,7 +50,7 @@ def build(force=False, verbose=False):
                 return LIB
             fd, tmp = tempfile.mkstemp(prefix="_libclusttraj_b200.", suffix=".so.tmp", dir=HERE)
             os.close(fd)
-            cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+            cmd = [_nvcc()] + NVCC_FLAGS + os.environ.get("CLUSTTRAJ_B200_NVCC_FLAGS", "").split() + (["-Xptxas", "-v"] if verbose else []) + \
                   [os.path.join(CSRC, s) for s in SOURCES] + ["-o", tmp]
             proc = subprocess.run(cmd, capture_output=True, text=True)
             if proc.returncode != 0:

@@ -426,10 +426,15 @@ struct TsCfg {
     static constexpr int ACOL = 4 * N;                 // first TMEM column of the A operand (after two level-pair buffers)
     static constexpr int B_STAGE = OZ_SLICES * N * KP_MAX;
     static constexpr int SCRATCH = NWG * OZ_FI * 73 * 8;
-    static constexpr int SMEM = 2 * B_STAGE + SCRATCH + 256;
+    static constexpr int TABLES = NWG * 2 * OZ_FI * 8;  // per warpgroup: output offset and G of the 40 rows of the block row
+    static constexpr int SMEM = 2 * B_STAGE + SCRATCH + 256 + TABLES;
     static constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(OZ_M >> 4) << 24);
     static_assert(ACOL + KP_MAX <= OZ_TMEM_COLS, "accumulators and the A operand must fit the 512 TMEM columns");
 };
+#ifndef TS_CTRL_REGS
+#define TS_CTRL_REGS 32    // registers the four control warps of gram_i8_ts_kernel<4> keep (96 x 640 are the CTA's allocation) ...
+#define TS_EPI_REGS 112    // ... and what that leaves for each of the 512 epilogue threads: (61440 - 128 x 32) / 512
+#endif
 constexpr int TS_WG_PITCH = 73;                       // doubles per frame row of a warpgroup's hand-off region: 8 pairs x 9,
                                                       // padded to 9 (mod 16) 8-byte bank units: conflict-free both ways
 
@@ -495,7 +500,8 @@ __global__ void __launch_bounds__(TsCfg<NWG>::THREADS, 1) gram_i8_ts_kernel(cons
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // provably warp-uniform
 
     if (warp < 4) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+        if constexpr (NWG == 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TS_CTRL_REGS));
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
         if (warp == 0 && lane == 0) {
             // ---- producer: the B tile of every block, four slices ------------------------------------------------
             TsWalker<FJ> w;
@@ -539,7 +545,10 @@ __global__ void __launch_bounds__(TsCfg<NWG>::THREADS, 1) gram_i8_ts_kernel(cons
                     if (elect_one()) {
 #pragma unroll
                         for (int lv = 0; lv < 2; ++lv) {
-                            const int q = 2 * pr + lv;   // level pairs from the most significant down: (0,1), (2,3), (4,5)
+                            // Level pairs in the order (2,3), (4,5), (0,1) = 28, 20 and 12 MMAs per 128 atoms: the pair that can only
+                            // be issued once the epilogue has drained the first one (two TMEM buffers) is the cheapest, so the
+                            // epilogue, which needs it 1-2 conversions later, does not wait for the tensor pipe
+                            const int q = 2 * ((pr + 1) % OZ_NPAIR) + lv;
                             const uint32_t d = tmem_base + (uint32_t)(tb * 2 * N + lv * N);
                             const int s_lo = q > 3 ? q - 3 : 0, s_hi = q < 3 ? q : 3;
 #pragma unroll
@@ -566,7 +575,8 @@ __global__ void __launch_bounds__(TsCfg<NWG>::THREADS, 1) gram_i8_ts_kernel(cons
         }
     } else {
         // ---- epilogue warps (4 warpgroups): warpgroup wg owns accumulator columns 24 wg .. 24 wg + 23 = 8 column frames ----
-        if constexpr (NWG == 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        // 96 registers x 640 threads are the CTA's allocation: the control warps keep 32, which leaves 112 for each epilogue thread
+        if constexpr (NWG == 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TS_EPI_REGS));
         else asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
         const int quarter = warp & 3;                 // TMEM lanes 32 * quarter .. + 31
         const int wg = (warp - 4) >> 2;               // 0..NWG-1
@@ -575,25 +585,50 @@ __global__ void __launch_bounds__(TsCfg<NWG>::THREADS, 1) gram_i8_ts_kernel(cons
         const bool row_ok = lane < 30;
         const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
         const double s2 = p.qinfo[0];
-        const double sc[OZ_NPAIR] = {s2 * 1099511627776.0, s2 * 16777216.0, s2 * 256.0};   // 2^40, 2^24, 2^8 (issue order)
+        // weights of the level pairs in ISSUE order (2,3), (4,5), (0,1): 2^24, 2^8, 2^40 (times 2^-2f)
+        const double s_mid = s2 * 16777216.0, s_lo = s2 * 256.0, s_hi = s2 * 1099511627776.0;
         // The int32 level sums enter the FP64 recombination still carrying the bias of the integer -> double trick
         // (xm = MAGIC + v, exact); the bias is taken out inside the FMAs instead of by a subtraction per value:
-        //   acc = fma(xm_hi, s_hi, -MAGIC (s_hi + s_mid))   = v_hi s_hi - MAGIC s_mid          (exact: 37 significant bits)
-        //   acc = fma(xm_mid, s_mid, acc)                    = v_hi s_hi + v_mid s_mid          (exact: < 2^51 units of s_mid)
-        //   acc = fma(xm_lo, s_lo, acc - MAGIC s_lo)         = the whole element, rounded ONCE  (the subtraction is exact)
+        //   acc = fma(xm_mid, s_mid, -MAGIC (s_mid + s_lo))  = v_mid s_mid - MAGIC s_lo            (exact: integers < 2^53 in units of s_lo)
+        //   acc = fma(xm_lo, s_lo, acc)                       = v_mid s_mid + v_lo s_lo             (exact: < 2^51 units of s_lo)
+        //   acc = acc + fma(xm_hi, s_hi, -MAGIC s_hi)         = the whole element, rounded ONCE     (the fma is exact: v_hi s_hi)
         // (scales are powers of two 2^16 apart, |v| < 2^34.)  4 FP64 operations per value instead of 6, on the pipe the
         // epilogue is throttled by, and a correctly rounded sum.
         constexpr double MAGIC = NWG == 4 ? 4503601774854144.0 : 6755399441055744.0;   // 2^52 + 2^31 | 2^52 + 2^51
-        const double kfold0 = -MAGIC * (sc[0] + sc[1]), kfold2 = -MAGIC * sc[2];
+        const double kfold_mid = -MAGIC * (s_mid + s_lo), kfold_hi = -MAGIC * s_hi;
         double* wg_scratch = scratch + wg * (OZ_FI * TS_WG_PITCH);
-        double* my_row = wg_scratch + (quarter * 10 + g) * TS_WG_PITCH + 3 * a;
+        // per-warpgroup tables of the current block row, refreshed when the row changes: element offset of every row's
+        // start in the output slab (shifted so that column j indexes it directly) and G of the row's frame
+        long long* row_off_s = reinterpret_cast<long long*>(smem + 2 * Cfg::B_STAGE + Cfg::SCRATCH + 256) + wg * (2 * OZ_FI);
+        double* row_g_s = reinterpret_cast<double*>(row_off_s + OZ_FI);
+        // Thread-invariant shared-memory addresses, made opaque so that the compiler keeps them in registers instead of
+        // re-deriving them from the thread index in every block (~75 instructions per block otherwise)
+        uint32_t my_row_s = smem_u32(wg_scratch + (quarter * 10 + g) * TS_WG_PITCH + 3 * a);
+        uint32_t rd_s[3], tab_s[3];
+        int il_r[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int pass = (wt >> 5) + 4 * r;
+            const int slot = 4 * pass + (lane >> 3);          // 0..39 (valid) .. 47
+            const int il = slot < OZ_FI ? (slot / 5) + 8 * (slot % 5) : 0;
+            il_r[r] = slot < OZ_FI ? il : -1;
+            rd_s[r] = smem_u32(wg_scratch + il * TS_WG_PITCH + (lane & 7) * 9);
+            tab_s[r] = smem_u32(row_off_s + il);
+            asm volatile("" : "+r"(rd_s[r]), "+r"(tab_s[r]), "+r"(il_r[r]));
+        }
+        asm volatile("" : "+r"(my_row_s));
         const int last_row = min(p.row_end, p.M - 1);
         TsWalker<FJ> w;
         w.init(ti_begin, ntj, blk_start, blk_count);
         int tb = 0; uint32_t tphase = 0;
         int cur_ti = -1; uint32_t afree_phase = 0;
+        // register pairs that hold the high word of the magic constant for good: a conversion only replaces the low word
+        double magic_pair[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) magic_pair[k] = __hiloint2double(0x43300000, k);
         for (; w.valid(); w.next()) {
-            if (wg == 0 && w.ti != cur_ti) {
+            const bool new_row = w.ti != cur_ti;
+            if (wg == 0 && new_row) {
                 // this warp's 32 A rows of the new block row: global -> registers -> TMEM
                 if (cur_ti >= 0) { mbar_wait(a_free, afree_phase); afree_phase ^= 1; tc_fence_after(); }
                 const uint4* src = reinterpret_cast<const uint4*>(p.packT + ((size_t)w.ti * OZ_M + quarter * 32 + lane) * (size_t)(OZ_SLICES * kp));
@@ -609,19 +644,11 @@ __global__ void __launch_bounds__(TsCfg<NWG>::THREADS, 1) gram_i8_ts_kernel(cons
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(a_ready);
-                cur_ti = w.ti;
             }
-            // G of this thread's pairs (the pass/slot mapping below): fetched now, used after the accumulate phase
+            cur_ti = w.ti;
+            // G of this thread's column frame: fetched now, used after the accumulate phase
             const double gj = p.Gq[w.tj * FJ + wg * 8 + (lane & 7)];
-            double gi[3];
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                const int slot = 4 * ((wt >> 5) + 4 * r) + (lane >> 3);
-                gi[r] = p.Gq[w.ti * OZ_FI + (slot / 5) + 8 * (slot % 5)];
-            }
             double acc[24];
-#pragma unroll
-            for (int n = 0; n < 24; ++n) acc[n] = 0.0;
 #pragma unroll
             for (int pr = 0; pr < OZ_NPAIR; ++pr) {
                 mbar_wait(&tfull[tb], tphase);
@@ -634,15 +661,22 @@ __global__ void __launch_bounds__(TsCfg<NWG>::THREADS, 1) gram_i8_ts_kernel(cons
                     tmem_ld8(t0 + 16, ev2);
                     tmem_ld8(t0 + N + 16, od2);
                     tmem_wait_ld();
+                    const double sc = pr == 0 ? s_mid : (pr == 1 ? s_lo : s_hi);
 #pragma unroll
-                    for (int n = 0; n < 16; ++n) {
-                        const double xm = NWG == 4 ? level_pair32_biased((int)ev[n], (int)od[n]) : level_pair_biased((int)ev[n], (int)od[n]);
-                        acc[n] = fma(xm, sc[pr], pr == 0 ? kfold0 : (pr == 1 ? acc[n] : acc[n] + kfold2));
-                    }
-#pragma unroll
-                    for (int n = 0; n < 8; ++n) {
-                        const double xm = NWG == 4 ? level_pair32_biased((int)ev2[n], (int)od2[n]) : level_pair_biased((int)ev2[n], (int)od2[n]);
-                        acc[16 + n] = fma(xm, sc[pr], pr == 0 ? kfold0 : (pr == 1 ? acc[16 + n] : acc[16 + n] + kfold2));
+                    for (int n = 0; n < 24; ++n) {
+                        const int e = (int)(n < 16 ? ev[n] : ev2[n - 16]), o = (int)(n < 16 ? od[n] : od2[n - 16]);
+                        double xm;
+                        if constexpr (NWG == 4) {
+                            // 2^52 + 2^31 + v: only the low word of a resident register pair changes (no move of the high word)
+                            const int lo = (e * 256 + o) ^ (int)0x80000000;
+                            asm("{\n.reg .b32 l, h;\nmov.b64 {l, h}, %0;\nmov.b64 %0, {%1, h};\n}" : "+d"(magic_pair[n & 7]) : "r"(lo));
+                            xm = magic_pair[n & 7];
+                        } else {
+                            xm = level_pair_biased(e, o);
+                        }
+                        if (pr == 0) acc[n] = fma(xm, sc, kfold_mid);
+                        else if (pr == 1) acc[n] = fma(xm, sc, acc[n]);
+                        else acc[n] += fma(xm, sc, kfold_hi);
                     }
                 }
                 tc_fence_before();
@@ -651,14 +685,19 @@ __global__ void __launch_bounds__(TsCfg<NWG>::THREADS, 1) gram_i8_ts_kernel(cons
                 tb ^= 1; if (tb == 0) tphase ^= 1;
             }
             // ---- transposition through shared memory: rows (frame i, coordinate a) in, whole 3x3 of one pair out ----
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");   // everyone has read the previous block
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");   // everyone has read the previous block (and its tables)
             if (row_ok) {
 #pragma unroll
                 for (int jj = 0; jj < 8; ++jj) {
-                    my_row[jj * 9 + 0] = acc[3 * jj + 0];
-                    my_row[jj * 9 + 1] = acc[3 * jj + 1];
-                    my_row[jj * 9 + 2] = acc[3 * jj + 2];
+                    asm volatile("st.shared.f64 [%0], %1;" ::"r"(my_row_s + (uint32_t)(jj * 72)), "d"(acc[3 * jj + 0]) : "memory");
+                    asm volatile("st.shared.f64 [%0], %1;" ::"r"(my_row_s + (uint32_t)(jj * 72 + 8)), "d"(acc[3 * jj + 1]) : "memory");
+                    asm volatile("st.shared.f64 [%0], %1;" ::"r"(my_row_s + (uint32_t)(jj * 72 + 16)), "d"(acc[3 * jj + 2]) : "memory");
                 }
+            }
+            if (new_row && wt < OZ_FI) {
+                const int i = w.ti * OZ_FI + wt;
+                row_off_s[wt] = condensed_row_base(p.M, i) - p.idx_base - i - 1;
+                row_g_s[wt] = p.Gq[i];
             }
             asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
             // Pairs of this warpgroup: 40 rows x 8 columns.  A warp pass takes four 8-row-apart rows (lane = 8 * sub + jl),
@@ -666,58 +705,54 @@ __global__ void __launch_bounds__(TsCfg<NWG>::THREADS, 1) gram_i8_ts_kernel(cons
             // mod 16) and every row's 8 results are one 64-byte run of the condensed vector.  40 (row class, sub) slots,
             // four per warp pass: passes 0-9, warp ww of the warpgroup does passes ww, ww + 4, ww + 8.
             double qa[3], qb[3], qd[3], hg[3], lam[3];
-            int pi[3], pj[3];
-            bool plive[3];
-            double* out_row[3];   // start of condensed row i, shifted so that column j indexes it directly
+            long long out_off[3];   // offset of the pair's entry in the output slab
+            bool pmine[3];
+            const int j = w.tj * FJ + wg * 8 + (lane & 7);
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
-                const int pass = (wt >> 5) + 4 * r;
-                const int slot = 4 * pass + (lane >> 3);          // 0..39 (valid) .. 47
-                const int il = (slot / 5) + 8 * (slot % 5), jl = lane & 7;
-                const int i = w.ti * OZ_FI + il, j = w.tj * FJ + wg * 8 + jl;
-                pi[r] = i; pj[r] = j;
-                out_row[r] = p.out + (condensed_row_base(p.M, i) - p.idx_base - i - 1);
-                const bool live = slot < OZ_FI && i < j && j < p.M;
-                plive[r] = live;
+                const int i = w.ti * OZ_FI + il_r[r];
+                const bool live = il_r[r] >= 0 && i < j && j < p.M;
+                pmine[r] = live && i >= p.row_begin && i < last_row;
                 double s9[9];
                 if (live) {
-                    const double* src = wg_scratch + il * TS_WG_PITCH + jl * 9;
 #pragma unroll
-                    for (int k = 0; k < 9; ++k) s9[k] = src[k];
-                    hg[r] = gi[r] + gj;
+                    for (int k = 0; k < 9; ++k) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(s9[k]) : "r"(rd_s[r] + (uint32_t)(8 * k)) : "memory");
+                    double gi;
+                    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(out_off[r]) : "r"(tab_s[r]) : "memory");
+                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(gi) : "r"(tab_s[r] + (uint32_t)(8 * OZ_FI)) : "memory");
+                    hg[r] = gi + gj;
                 } else {
                     // lower triangle / padding: a well-conditioned stand-in (identity) so that no lane drags its warp
                     // through the solver's slow path; the result is never stored
 #pragma unroll
                     for (int k = 0; k < 9; ++k) s9[k] = (k % 4 == 0) ? 1.0 : 0.0;
                     hg[r] = 3.0;
+                    out_off[r] = 0;
                 }
                 quartic_invariants(s9, qa[r], qb[r], qd[r]);
             }
             unsigned okmask;
             if ((wt >> 5) < 2) {
-                okmask = largest_root_f64<3>(qa, qb, qd, hg, lam);
+                okmask = largest_root_fast<3>(qa, qb, qd, hg, lam);
             } else {  // passes 10 and 11 do not exist: warps 2 and 3 of the warpgroup have two passes
                 double a2[2] = {qa[0], qa[1]}, b2[2] = {qb[0], qb[1]}, d2[2] = {qd[0], qd[1]}, h2[2] = {hg[0], hg[1]}, l2[2];
-                okmask = largest_root_f64<2>(a2, b2, d2, h2, l2);
+                okmask = largest_root_fast<2>(a2, b2, d2, h2, l2);
                 lam[0] = l2[0]; lam[1] = l2[1]; lam[2] = 0.0;
             }
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
-                const int i = pi[r], j = pj[r];
                 const double eh = hg[r] - lam[r];
                 const double v = (eh > 0.0 ? eh : 0.0) * p.inv_k2;
                 const double y = rsqrt_approx_f64(v + 1e-300);        // sqrt(v) = v / sqrt(v), one Newton step
                 double rm = v * y;
                 rm = fma(fma(-rm, rm, v), 0.5 * y, rm);
                 const bool ok = (okmask >> r) & 1u;
-                const bool mine = plive[r] && i >= p.row_begin && i < last_row;
-                if ((!ok || eh < p.flag_rel * hg[r]) && mine) {
+                if ((!ok || eh < p.flag_rel * hg[r]) && pmine[r]) {
                     const unsigned int t = atomicAdd(p.fix.count, 1u);
-                    if (t < p.fix.capacity) p.fix.pairs[t] = make_int2(i, j);
+                    if (t < p.fix.capacity) p.fix.pairs[t] = make_int2(w.ti * OZ_FI + il_r[r], j);
                     else rm = -1.0;
                 }
-                if (mine) __stcs(out_row[r] + j, rm);   // streaming store: the output must not evict the operand tiles from L2
+                if (pmine[r]) __stcs(p.out + out_off[r] + j, rm);   // streaming store: the output must not evict the operand tiles from L2
             }
         }
     }

@@ -229,6 +229,93 @@ __device__ __forceinline__ unsigned largest_root_f64(const double (&a)[NP], cons
     return ok;
 }
 
+// Fixed-trip variant for the epilogues that are bound by instruction issue (ozaki.cu): FOUR Newton steps from the same
+// upper bound with no test inside the iteration (7 instructions per step and pair instead of ~25: the acceptance test of
+// largest_root_f64 is a dozen integer operations per step), then ONE acceptance test per pair:
+//   * the fourth step is below 2^-30 of the root (typical trajectories start within a per cent of it and reach round-off
+//     in three steps), AND
+//   * the root is well separated: f'(x) / 4 >= 2^-10 x^3.  f' = 8 (s2+s3)(s1+s3)(s1+s2) at the largest root, so this
+//     refuses exactly the ill-conditioned cases -- near-collinear structures, mirror images of near-symmetric ones --
+//     where Newton converges only linearly and a small step does not mean a small error.  With the separation bound the
+//     error recurrence is e' <= 1250 e^2 / x, i.e. a step below 2^-30 x leaves an error below 1e-15 x.
+// Pairs that fail the test continue in the tested loop of largest_root_f64 (same state); what that loop cannot settle is
+// reported through ok_mask and re-done by the explicit-rotation fix-up path, as before.
+template <int NP>
+__device__ __forceinline__ unsigned largest_root_fast(const double (&a)[NP], const double (&b)[NP], const double (&d)[NP],
+                                                      const double (&half_g)[NP], double (&lam)[NP]) {
+    double x[NP], m8d[NP], m4b[NP], d2[NP], step[NP], fq[NP];
+    constexpr unsigned ALL = (1u << NP) - 1u;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        const double a3 = 3.0 * a[p];
+        const double s = a3 * rsqrt_approx_f64(a3 + 1e-300) * 1.000001;   // >= sqrt(3a)
+        const double x0 = half_g[p] < s ? half_g[p] : s;
+        x[p] = x0 > 0.0 ? x0 : 0.0;
+        m8d[p] = -8.0 * d[p];
+        m4b[p] = -4.0 * b[p];
+        d2[p] = 2.0 * d[p];
+    }
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            const double t = fma(x[p], x[p], -a[p]);
+            const double f = fma(t, t, fma(m8d[p], x[p], m4b[p]));
+            fq[p] = fma(x[p], t, -d2[p]);                                 // f' / 4
+            const double q = 0.25 * rcp_approx_f64(fq[p]);
+            if (it == 3) step[p] = f * q;
+            x[p] = fma(-f, q, x[p]);
+        }
+    }
+    unsigned ok = 0;
+    int e_last[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        const int e_s = (__double2hiint(step[p]) >> 20) & 0x7ff, e_x = (__double2hiint(x[p]) >> 20) & 0x7ff;
+        const double x3 = x[p] * x[p] * x[p];
+        // (x = NaN or infinity -- S == 0 makes the very first quotient 0 / 0 -- has exponent 0x7ff and fails the first test)
+        if (e_s + 30 <= e_x && e_x != 0x7ff && fq[p] >= 0.0009765625 * x3) ok |= 1u << p;
+        e_last[p] = e_s;
+        if (a[p] == 0.0) { x[p] = 0.0; ok |= 1u << p; }                   // zero covariance (1-atom frames): every root is 0
+    }
+    if (ok != ALL) {
+        // the tested iteration of largest_root_f64, continued from where the four steps ended
+        unsigned bad = 0;
+#pragma unroll
+        for (int p = 0; p < NP; ++p)
+            if (!(x[p] == x[p]) || !(x[p] <= 1.7976931348623157e308)) {     // restart a pair that blew up from its upper bound
+                const double a3 = 3.0 * a[p];
+                const double s = a3 * rsqrt_approx_f64(a3 + 1e-300) * 1.000001;
+                const double x0 = half_g[p] < s ? half_g[p] : s;
+                x[p] = x0 > 0.0 ? x0 : 0.0;
+                e_last[p] = ((__double2hiint(x[p]) >> 20) & 0x7ff) - 22;
+                bad |= 1u << p;
+            }
+        (void)bad;
+#pragma unroll 1
+        for (int it = 0; it < 20 && ok != ALL; ++it) {
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                const double t = fma(x[p], x[p], -a[p]);
+                const double f = fma(t, t, fma(m8d[p], x[p], m4b[p]));
+                const double fq2 = fma(x[p], t, -d2[p]);
+                const bool up = fq2 > 0.0;
+                const double st = (up && !((ok >> p) & 1u)) ? f * (0.25 * rcp_approx_f64(fq2)) : 0.0;   // accepted pairs stay put
+                x[p] -= st;
+                const int e_as = (__double2hiint(st) >> 20) & 0x7ff, e_x = (__double2hiint(x[p]) >> 20) & 0x7ff;
+                if (up && e_as + 23 <= e_x && e_as + e_x <= 2 * e_last[p] + 4) ok |= 1u << p;
+                e_last[p] = e_as;
+            }
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        lam[p] = x[p];
+        if (!(x[p] == x[p])) ok &= ~(1u << p);
+    }
+    return ok;
+}
+
 // Cyclic Jacobi on a symmetric 4x4 matrix (in registers, fully unrolled indices).  On return A holds the
 // eigenvalues on its diagonal and the columns of V the eigenvectors.
 __device__ __forceinline__ void jacobi4(double (&A)[4][4], double (&V)[4][4]) {
