@@ -72,7 +72,7 @@ struct ct_engine {
     uint8_t* d_packB = nullptr; size_t packB_cap = 0;
     uint8_t* d_packT = nullptr; size_t packT_cap = 0;
     double* d_Gq = nullptr; size_t gq_cap = 0;
-    double* d_qinfo = nullptr;               // [0] 2^-2f, [1] f, [2] max |x|
+    double* d_qinfo = nullptr;               // [0] 2^-2f, [1] f, [2] max |x|, [4..11] the magic constant of the int -> double trick
     unsigned long long* d_maxbits = nullptr;
     double quant_f = 0.0;
     ct::PairPlanHost* plan = nullptr;
@@ -204,7 +204,7 @@ static int engine_init(ct_engine* e, int device) {
     CT_CUDA(e, cudaMalloc(&e->d_fix_pairs, sizeof(int2) * e->fix_cap));
     CT_CUDA(e, cudaMalloc(&e->d_fix_count, sizeof(unsigned int)));
     CT_CUDA(e, cudaMalloc(&e->d_counters, sizeof(unsigned long long) * 4));
-    CT_CUDA(e, cudaMalloc(&e->d_qinfo, sizeof(double) * 4));
+    CT_CUDA(e, cudaMalloc(&e->d_qinfo, sizeof(double) * 16));
     CT_CUDA(e, cudaMalloc(&e->d_maxbits, sizeof(unsigned long long)));
     return CT_OK;
 }

@@ -608,7 +608,9 @@ __global__ void __launch_bounds__(TsCfg<NWG>::THREADS, 1) gram_i8_ts_kernel(cons
         int il_r[3];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-            const int pass = (wt >> 5) + 4 * r;
+            // warp ww of the warpgroup takes the passes with (pass + wg) % 4 == ww: the two warps with three passes sit on
+            // different schedulers in different warpgroups (warp ww of every warpgroup shares scheduler ww)
+            const int pass = (((wt >> 5) - wg) & 3) + 4 * r;
             const int slot = 4 * pass + (lane >> 3);          // 0..39 (valid) .. 47
             const int il = slot < OZ_FI ? (slot / 5) + 8 * (slot % 5) : 0;
             il_r[r] = slot < OZ_FI ? il : -1;
@@ -625,7 +627,7 @@ __global__ void __launch_bounds__(TsCfg<NWG>::THREADS, 1) gram_i8_ts_kernel(cons
         // register pairs that hold the high word of the magic constant for good: a conversion only replaces the low word
         double magic_pair[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) magic_pair[k] = __hiloint2double(0x43300000, k);
+        for (int k = 0; k < 8; ++k) magic_pair[k] = p.qinfo[4 + k];   // 2^52 + 2^31, opaque to the compiler (see quant_info_kernel)
         for (; w.valid(); w.next()) {
             const bool new_row = w.ti != cur_ti;
             if (wg == 0 && new_row) {
@@ -648,41 +650,56 @@ __global__ void __launch_bounds__(TsCfg<NWG>::THREADS, 1) gram_i8_ts_kernel(cons
             cur_ti = w.ti;
             // G of this thread's column frame: fetched now, used after the accumulate phase
             const double gj = p.Gq[w.tj * FJ + wg * 8 + (lane & 7)];
+            // Level pairs -> FP64 covariance rows, software-pipelined against the TMEM loads: a pair's 24 columns come as
+            // 16 + 8 (tcgen05.wait::ld waits for ALL outstanding loads, so the 8 are requested once the 16 have landed and
+            // arrive while those are converted; the next pair's 16 are requested before the 8 are converted).  The pair's
+            // TMEM buffer is handed back to the MMA warp as soon as its last load has landed, before the conversion.
             double acc[24];
+            uint32_t ev[16], od[16], ev2[8], od2[8];
+            auto convert = [&](int pr, int n, uint32_t e_raw, uint32_t o_raw) {
+                const int e = (int)e_raw, o = (int)o_raw;
+                double xm;
+                if constexpr (NWG == 4) {
+                    // 2^52 + 2^31 + v: only the low word of a resident register pair changes
+                    const int lo = (e * 256 + o) ^ (int)0x80000000;
+                    asm("{\n.reg .b32 l, h;\nmov.b64 {l, h}, %0;\nmov.b64 %0, {%1, h};\n}" : "+d"(magic_pair[n & 7]) : "r"(lo));
+                    xm = magic_pair[n & 7];
+                } else {
+                    xm = level_pair_biased(e, o);
+                }
+                if (pr == 0) acc[n] = fma(xm, s_mid, kfold_mid);
+                else if (pr == 1) acc[n] = fma(xm, s_lo, acc[n]);
+                else acc[n] += fma(xm, s_hi, kfold_hi);
+            };
+            mbar_wait(&tfull[tb], tphase);
+            tc_fence_after();
+            {
+                const uint32_t t0 = tlane + (uint32_t)(tb * 2 * N + wg * 24);
+                tmem_ld16(t0, ev);
+                tmem_ld16(t0 + N, od);
+            }
 #pragma unroll
             for (int pr = 0; pr < OZ_NPAIR; ++pr) {
-                mbar_wait(&tfull[tb], tphase);
-                tc_fence_after();
                 const uint32_t t0 = tlane + (uint32_t)(tb * 2 * N + wg * 24);
-                {   // 16 + 8 columns: two TMEM round trips per level pair instead of three
-                    uint32_t ev[16], od[16], ev2[8], od2[8];
-                    tmem_ld16(t0, ev);
-                    tmem_ld16(t0 + N, od);
-                    tmem_ld8(t0 + 16, ev2);
-                    tmem_ld8(t0 + N + 16, od2);
-                    tmem_wait_ld();
-                    const double sc = pr == 0 ? s_mid : (pr == 1 ? s_lo : s_hi);
+                tmem_wait_ld();
+                tmem_ld8(t0 + 16, ev2);
+                tmem_ld8(t0 + N + 16, od2);
 #pragma unroll
-                    for (int n = 0; n < 24; ++n) {
-                        const int e = (int)(n < 16 ? ev[n] : ev2[n - 16]), o = (int)(n < 16 ? od[n] : od2[n - 16]);
-                        double xm;
-                        if constexpr (NWG == 4) {
-                            // 2^52 + 2^31 + v: only the low word of a resident register pair changes (no move of the high word)
-                            const int lo = (e * 256 + o) ^ (int)0x80000000;
-                            asm("{\n.reg .b32 l, h;\nmov.b64 {l, h}, %0;\nmov.b64 %0, {%1, h};\n}" : "+d"(magic_pair[n & 7]) : "r"(lo));
-                            xm = magic_pair[n & 7];
-                        } else {
-                            xm = level_pair_biased(e, o);
-                        }
-                        if (pr == 0) acc[n] = fma(xm, sc, kfold_mid);
-                        else if (pr == 1) acc[n] = fma(xm, sc, acc[n]);
-                        else acc[n] += fma(xm, sc, kfold_hi);
-                    }
-                }
+                for (int n = 0; n < 16; ++n) convert(pr, n, ev[n], od[n]);
+                tmem_wait_ld();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[tb]);
                 tb ^= 1; if (tb == 0) tphase ^= 1;
+                if (pr + 1 < OZ_NPAIR) {
+                    mbar_wait(&tfull[tb], tphase);
+                    tc_fence_after();
+                    const uint32_t t1 = tlane + (uint32_t)(tb * 2 * N + wg * 24);
+                    tmem_ld16(t1, ev);
+                    tmem_ld16(t1 + N, od);
+                }
+#pragma unroll
+                for (int n = 0; n < 8; ++n) convert(pr, 16 + n, ev2[n], od2[n]);
             }
             // ---- transposition through shared memory: rows (frame i, coordinate a) in, whole 3x3 of one pair out ----
             asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");   // everyone has read the previous block (and its tables)
@@ -703,7 +720,7 @@ __global__ void __launch_bounds__(TsCfg<NWG>::THREADS, 1) gram_i8_ts_kernel(cons
             // Pairs of this warpgroup: 40 rows x 8 columns.  A warp pass takes four 8-row-apart rows (lane = 8 * sub + jl),
             // so that the 16 lanes of a shared-memory wavefront read 16 different 8-byte bank units (il + jl all different
             // mod 16) and every row's 8 results are one 64-byte run of the condensed vector.  40 (row class, sub) slots,
-            // four per warp pass: passes 0-9, warp ww of the warpgroup does passes ww, ww + 4, ww + 8.
+            // four per warp pass: passes 0-9, a warp does passes q, q + 4, q + 8 with q = (ww - wg) mod 4.
             double qa[3], qb[3], qd[3], hg[3], lam[3];
             long long out_off[3];   // offset of the pair's entry in the output slab
             bool pmine[3];
@@ -732,7 +749,7 @@ __global__ void __launch_bounds__(TsCfg<NWG>::THREADS, 1) gram_i8_ts_kernel(cons
                 quartic_invariants(s9, qa[r], qb[r], qd[r]);
             }
             unsigned okmask;
-            if ((wt >> 5) < 2) {
+            if ((((wt >> 5) - wg) & 3) < 2) {
                 okmask = largest_root_fast<3>(qa, qb, qd, hg, lam);
             } else {  // passes 10 and 11 do not exist: warps 2 and 3 of the warpgroup have two passes
                 double a2[2] = {qa[0], qa[1]}, b2[2] = {qb[0], qb[1]}, d2[2] = {qd[0], qd[1]}, h2[2] = {hg[0], hg[1]}, l2[2];
@@ -792,6 +809,9 @@ __global__ void quant_info_kernel(const unsigned long long* maxbits, double* qin
     qinfo[0] = ldexp(1.0, -2 * f);
     qinfo[1] = (double)f;
     qinfo[2] = __longlong_as_double((long long)*maxbits);
+    // 2^52 + 2^31: the epilogue of gram_i8_ts_kernel<4> reads these eight copies at run time so that the compiler sees eight
+    // unrelated values and keeps each in its own register pair, of which a conversion only replaces the low word
+    for (int k = 0; k < 8; ++k) qinfo[4 + k] = 4503601774854144.0;
 }
 
 // Which tcgen05 kernel serves K kept atoms, and the operand layouts it reads.
