@@ -650,12 +650,11 @@ __global__ void __launch_bounds__(TsCfg<NWG>::THREADS, 1) gram_i8_ts_kernel(cons
             cur_ti = w.ti;
             // G of this thread's column frame: fetched now, used after the accumulate phase
             const double gj = p.Gq[w.tj * FJ + wg * 8 + (lane & 7)];
-            // Level pairs -> FP64 covariance rows, software-pipelined against the TMEM loads: a pair's 24 columns come as
-            // 16 + 8 (tcgen05.wait::ld waits for ALL outstanding loads, so the 8 are requested once the 16 have landed and
-            // arrive while those are converted; the next pair's 16 are requested before the 8 are converted).  The pair's
-            // TMEM buffer is handed back to the MMA warp as soon as its last load has landed, before the conversion.
+            // Level pairs -> FP64 covariance rows.  A pair's TMEM buffer goes back to the MMA warp the moment its 24 columns are
+            // in registers, BEFORE they are converted: the third pair of a block can only be issued into the buffer of the
+            // first (two buffers), and every cycle between that release and the point where the epilogue needs the third pair
+            // is one it does not wait for the tensor pipe.
             double acc[24];
-            uint32_t ev[16], od[16], ev2[8], od2[8];
             auto convert = [&](int pr, int n, uint32_t e_raw, uint32_t o_raw) {
                 const int e = (int)e_raw, o = (int)o_raw;
                 double xm;
@@ -671,33 +670,23 @@ __global__ void __launch_bounds__(TsCfg<NWG>::THREADS, 1) gram_i8_ts_kernel(cons
                 else if (pr == 1) acc[n] = fma(xm, s_lo, acc[n]);
                 else acc[n] += fma(xm, s_hi, kfold_hi);
             };
-            mbar_wait(&tfull[tb], tphase);
-            tc_fence_after();
-            {
-                const uint32_t t0 = tlane + (uint32_t)(tb * 2 * N + wg * 24);
-                tmem_ld16(t0, ev);
-                tmem_ld16(t0 + N, od);
-            }
 #pragma unroll
             for (int pr = 0; pr < OZ_NPAIR; ++pr) {
+                mbar_wait(&tfull[tb], tphase);
+                tc_fence_after();
                 const uint32_t t0 = tlane + (uint32_t)(tb * 2 * N + wg * 24);
-                tmem_wait_ld();
+                uint32_t ev[16], od[16], ev2[8], od2[8];
+                tmem_ld16(t0, ev);
+                tmem_ld16(t0 + N, od);
                 tmem_ld8(t0 + 16, ev2);
                 tmem_ld8(t0 + N + 16, od2);
-#pragma unroll
-                for (int n = 0; n < 16; ++n) convert(pr, n, ev[n], od[n]);
                 tmem_wait_ld();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[tb]);
                 tb ^= 1; if (tb == 0) tphase ^= 1;
-                if (pr + 1 < OZ_NPAIR) {
-                    mbar_wait(&tfull[tb], tphase);
-                    tc_fence_after();
-                    const uint32_t t1 = tlane + (uint32_t)(tb * 2 * N + wg * 24);
-                    tmem_ld16(t1, ev);
-                    tmem_ld16(t1 + N, od);
-                }
+#pragma unroll
+                for (int n = 0; n < 16; ++n) convert(pr, n, ev[n], od[n]);
 #pragma unroll
                 for (int n = 0; n < 8; ++n) convert(pr, 16 + n, ev2[n], od2[n]);
             }
