@@ -337,7 +337,7 @@ def roofline_of(name, kw, M, K, r0, r1, my_pairs, mean_gram_ms, st):
         out = {"bound": "tensor", "achieved": i8_tops, "peak": i8_peak, "unit": "TFLOP/s", "frac": i8_tops / i8_peak,
                "traffic": None, "pairs_per_launch": my_pairs, "launch_ms": mean_gram_ms,
                "ops_per_pair": 15 * 18 * K, "peak_source": i8_src,
-               "kernel": "gram_i8_ts_kernel<4>" if chunks <= 4 else ("gram_i8_ts_kernel<2>" if chunks <= 10 else "gram_i8_kernel"),
+               "kernel": "gram_i8_ts_kernel<8>" if chunks <= 4 else ("gram_i8_ts_kernel<4>" if chunks <= 10 else "gram_i8_kernel"),
                "pipe": f"int8 tcgen05.mma (SASS UTCIMMA), M128 N{n_mma} K32; unit = 1e12 int8 multiply-add operations x 2 per s",
                "issued_tops": issued, "issued_frac": issued / i8_peak,
                "fp64_equiv": fp64_equiv, "quant_step_angstrom": float(st["quant_step"]),

@@ -22,8 +22,8 @@
 // 1-D cp.async.bulk copies and the shared-memory descriptors need no swizzle.
 //
 // Three kernels (launch_gram_i8 picks by the padded atom count kp):
-//   gram_i8_ts_kernel<4>  kp <= 128: A tile resident in TMEM (".ts" MMA), B streams, N = 96, 16 epilogue warps;
-//   gram_i8_ts_kernel<2>  kp <= 320: the same with N = 48 (A takes 320 of the 512 TMEM columns), 8 epilogue warps;
+//   gram_i8_ts_kernel<8>  kp <= 128: A tile resident in TMEM (".ts" MMA), B streams, N = 96, 16 epilogue warps;
+//   gram_i8_ts_kernel<4>  kp <= 320: the same with N = 48 (A takes up to 320 of the 512 TMEM columns), 16 epilogue warps;
 //   gram_i8_kernel        larger kp: A and B both stream through shared memory in K-blocks of 128 atoms; N = 80 so that ALL
 //                         six level accumulators (480 TMEM columns) stay resident over the K-blocks of a block and are
 //                         converted once; 8 epilogue warps that transpose with shuffles (shared memory is full).  Bound
@@ -404,39 +404,46 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) gram_i8_kernel(const OzParams p
 }
 
 
-// ---- K <= 128 atoms: A operand resident in TMEM, dedicated solver warps -------------------------------------
-// With the whole contraction in one K-block the A tile (40 frames x 4 slices x 128 B = 64 KiB) is exactly 128 TMEM
-// columns, next to the 384 accumulator columns.  It is written there once per row of blocks (tcgen05.st, straight
-// from global memory, by the warps that own the TMEM lanes) and every MMA takes it from TMEM (".ts"), so shared
-// memory only carries the streaming B tiles: the MMA no longer reads more than the 128 B/clk shared memory can
-// deliver, and the freed 130 KiB hold a hand-off buffer between the warps that turn integer levels into FP64
-// covariances and four solver warps.  The hand-off is also the transposition the row-per-lane accumulator layout
-// needs: accumulate warps write (frame i, coordinate a) rows, a solver lane reads the whole 3x3 of one pair, lanes
-// run along j, so the RMSD stores are 256-byte contiguous runs of the condensed vector.
+// ---- K <= 320 atoms: A operand resident in TMEM, sixteen epilogue warps -------------------------------------------
+// With the whole contraction in one K-block the A tile (40 frames x 4 slices x kp bytes) is kp TMEM columns next to the
+// accumulators.  It is written there once per row of blocks (tcgen05.st, straight from global memory, by the warps that
+// own the TMEM lanes) and every MMA takes it from TMEM (".ts"), so shared memory only carries the streaming B tiles: the
+// MMA no longer reads more than the 128 B/clk shared memory can deliver, and the freed shared memory holds the hand-off
+// buffer in which the row-per-lane accumulator layout is transposed: a lane writes its (frame i, coordinate a) row, and
+// reads back the whole 3x3 of one pair, lanes running along j so that the RMSD stores are contiguous runs.
 // Two shapes, chosen by the padded atom count kp (a multiple of 32, all of the contraction in ONE shared-memory stage):
-//   NWG = 4: column tiles of 32 frames (N = 96), accumulators 384 TMEM columns, A up to 128 columns  -> kp <= 128
-//   NWG = 2: column tiles of 16 frames (N = 48), accumulators 192 TMEM columns, A up to 320 columns  -> kp <= 320
-// NWG is also the number of epilogue warpgroups: each owns 24 accumulator columns = 8 column frames.
-template <int NWG>
+//   PW = 8: column tiles of 32 frames (N = 96), two level-pair buffers (384 TMEM columns), A up to 128 columns -> kp <= 128
+//   PW = 4: column tiles of 16 frames (N = 48), A up to 320 columns -> kp <= 320; THREE level-pair buffers (288 columns) while
+//           kp <= 224, so that the MMA warp runs a whole block ahead of the epilogue, else two
+// Both have FOUR epilogue warpgroups (16 warps, 4 per scheduler): warpgroup wg owns 3 PW accumulator columns = PW column
+// frames of every row.  (The N = 48 shape used to run with two warpgroups of 24 columns: two warps per scheduler left its
+// epilogue latency-bound at 30 % issue utilisation.)
+template <int PW>
 struct TsCfg {
-    static constexpr int FJ = 8 * NWG;                 // frames per column tile
+    static constexpr int WGS = 4;                      // epilogue warpgroups
+    static constexpr int FJ = WGS * PW;                // frames per column tile
     static constexpr int N = 3 * FJ;                   // MMA N
-    static constexpr int THREADS = 128 + 128 * NWG;    // 4 control warps + 4 NWG epilogue warps
-    static constexpr int KP_MAX = NWG == 4 ? 128 : 320;
-    static constexpr int ACOL = 4 * N;                 // first TMEM column of the A operand (after two level-pair buffers)
+    static constexpr int CW = 3 * PW;                  // accumulator columns per warpgroup
+    static constexpr int THREADS = 128 + 128 * WGS;    // 4 control warps + 16 epilogue warps
+    static constexpr int KP_MAX = PW == 8 ? 128 : 320;
+    static constexpr int PITCH = PW == 8 ? 73 : 41;    // doubles per frame row of a warpgroup's hand-off region: 9 PW padded to
+                                                       // 9 (mod 16) 8-byte bank units
+    static constexpr int NR = PW == 8 ? 3 : 2;         // solve passes of the busiest warps of a warpgroup (the others: NR - 1)
     static constexpr int B_STAGE = OZ_SLICES * N * KP_MAX;
-    static constexpr int SCRATCH = NWG * OZ_FI * 73 * 8;
-    static constexpr int TABLES = NWG * 2 * OZ_FI * 8;  // per warpgroup: output offset and G of the 40 rows of the block row
+    static constexpr int SCRATCH = WGS * OZ_FI * PITCH * 8;
+    static constexpr int TABLES = WGS * 2 * OZ_FI * 8; // per warpgroup: output offset and G of the 40 rows of the block row
     static constexpr int SMEM = 2 * B_STAGE + SCRATCH + 256 + TABLES;
     static constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(OZ_M >> 4) << 24);
-    static_assert(ACOL + KP_MAX <= OZ_TMEM_COLS, "accumulators and the A operand must fit the 512 TMEM columns");
+    // TMEM: nbuf level-pair buffers of 2 N columns, then the A operand (kp columns)
+    __host__ __device__ static int nbuf(int kp) { return (OZ_TMEM_COLS - kp) / (2 * N) >= 3 ? 3 : 2; }
+    static_assert(4 * N + KP_MAX <= OZ_TMEM_COLS, "two level-pair buffers and the A operand must fit the 512 TMEM columns");
 };
 #ifndef TS_CTRL_REGS
-#define TS_CTRL_REGS 32    // registers the four control warps of gram_i8_ts_kernel<4> keep (96 x 640 are the CTA's allocation) ...
+#define TS_CTRL_REGS 32    // PW = 8: registers the four control warps keep (96 x 640 are the CTA's allocation) ...
 #define TS_EPI_REGS 112    // ... and what that leaves for each of the 512 epilogue threads: (61440 - 128 x 32) / 512
+#define TS_CTRL_REGS_N48 48   // PW = 4: the unrolled MMA issue wants more uniform-register feeding, the epilogue (12 accumulator
+#define TS_EPI_REGS_N48 104   // columns, two solve passes) less
 #endif
-constexpr int TS_WG_PITCH = 73;                       // doubles per frame row of a warpgroup's hand-off region: 8 pairs x 9,
-                                                      // padded to 9 (mod 16) 8-byte bank units: conflict-free both ways
 
 // upper-triangle block walk for column tiles of FJ frames (see OzWalker)
 template <int FJ>
@@ -461,20 +468,80 @@ struct TsWalker {
     }
 };
 
-template <int NWG>
-__global__ void __launch_bounds__(TsCfg<NWG>::THREADS, 1) gram_i8_ts_kernel(const OzParams p) {
-    using Cfg = TsCfg<NWG>;
-    constexpr int FJ = Cfg::FJ, N = Cfg::N, ACOL = Cfg::ACOL;
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+                 : "r"(taddr)
+                 : "memory");
+}
+// L2 eviction priorities: the B tiles are re-read by every CTA of the grid (keep), an A tile by one CTA once (do not keep)
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
+}
+// 32 bytes (one 32-atom chunk of one A row) in one 256-bit load that is not kept in L1 and leaves L2 first
+__device__ __forceinline__ void ldg256_evict_first(const void* ptr, uint32_t (&v)[8]) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "l"(ptr));
+}
+
+// The MMAs of one level pair of one block (issued by one elected thread): levels q = 2 ((pr + 1) % 3) + lv, lv = 0, 1, each the sum
+// over the digit-slice pairs (s, q - s) and over the 32-atom chunks kc of  A[slice s, chunk kc] (TMEM) x B[slice q - s, chunk kc]
+// (shared memory).  NCH > 0: chunk count known at compile time, every operand address is the base plus an immediate;
+// NCH = 0: run-time chunk count `nch`.
+template <int N, int NCH>
+__device__ __forceinline__ void ts_issue_pair(int pr, uint32_t d0, uint32_t a0, uint32_t b_lo, int nch = NCH) {
+    constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);   // SBO = 128 B, descriptor version of sm_100
+    constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(OZ_M >> 4) << 24);
+    const int kp = 32 * nch;
+    const uint32_t b_slice16 = (uint32_t)(N * kp) >> 4, a_slice_cols = (uint32_t)kp >> 2;
+#pragma unroll
+    for (int lv = 0; lv < 2; ++lv) {
+        const int q = 2 * ((pr + 1) % OZ_NPAIR) + lv;
+        const uint32_t d = d0 + (uint32_t)(lv * N);
+        const int s_lo = q > 3 ? q - 3 : 0, s_hi = q < 3 ? q : 3;
+#pragma unroll
+        for (int s = s_lo; s <= s_hi; ++s) {
+            if constexpr (NCH > 0) {
+#pragma unroll
+                for (int kc = 0; kc < NCH; ++kc) {
+                    // one MMA = 32 atoms: A from 8 TMEM columns, B = two 16-byte K halves of N / 8 core matrices
+                    const uint64_t bd = ((uint64_t)DESC_HI << 32) | (b_lo + (uint32_t)(q - s) * b_slice16 + (uint32_t)(kc * 2 * N));
+                    umma_i8_ts(d, a0 + (uint32_t)s * a_slice_cols + (uint32_t)(kc * 8), bd, IDESC, (s > s_lo || kc > 0) ? 1u : 0u);
+                }
+            } else {
+#pragma unroll 2
+                for (int kc = 0; kc < nch; ++kc) {
+                    const uint64_t bd = ((uint64_t)DESC_HI << 32) | (b_lo + (uint32_t)(q - s) * b_slice16 + (uint32_t)(kc * 2 * N));
+                    umma_i8_ts(d, a0 + (uint32_t)s * a_slice_cols + (uint32_t)(kc * 8), bd, IDESC, (s > s_lo || kc > 0) ? 1u : 0u);
+                }
+            }
+        }
+    }
+}
+
+template <int PW>
+__global__ void __launch_bounds__(TsCfg<PW>::THREADS, 1) gram_i8_ts_kernel(const OzParams p) {
+    using Cfg = TsCfg<PW>;
+    constexpr int FJ = Cfg::FJ, N = Cfg::N, CW = Cfg::CW, PITCH = Cfg::PITCH, NR = Cfg::NR;
     extern __shared__ __align__(1024) unsigned char smem[];
     double* scratch = reinterpret_cast<double*>(smem + 2 * Cfg::B_STAGE);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * Cfg::B_STAGE + Cfg::SCRATCH);
     uint64_t* bfull = bars;           // [2] B stage loaded
     uint64_t* bempty = bars + 2;      // [2] B stage consumed
-    uint64_t* tfull = bars + 4;       // [2] level pair complete in TMEM
-    uint64_t* tempty = bars + 6;      // [2] level pair drained
-    uint64_t* a_ready = bars + 8;     // A tile of the current block row is in TMEM (4 warps)
-    uint64_t* a_free = bars + 9;      // every MMA of the previous block row has completed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    uint64_t* tfull = bars + 4;       // [3] level pair complete in TMEM
+    uint64_t* tempty = bars + 7;      // [3] level pair in registers (buffer free)
+    uint64_t* a_ready = bars + 10;    // A tile of the current block row is in TMEM (4 warps)
+    uint64_t* a_free = bars + 11;     // every MMA of the previous block row has completed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int ti_begin = p.row_begin / OZ_FI;
@@ -483,13 +550,14 @@ __global__ void __launch_bounds__(TsCfg<NWG>::THREADS, 1) gram_i8_ts_kernel(cons
     const long long blk_count = p.total_blocks * (blockIdx.x + 1) / gridDim.x - blk_start;
     const int nch = p.last_chunks;    // 32-atom chunks of the contraction (all in one stage)
     const int kp = 32 * nch;          // padded atoms = bytes per operand row per slice
+    const int nbuf = Cfg::nbuf(kp);   // level-pair buffers in TMEM
+    const uint32_t acol = (uint32_t)(nbuf * 2 * N);   // first TMEM column of the A operand
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1);
-            mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4 * NWG);
-        }
+        for (int s = 0; s < 2; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1); }
+#pragma unroll
+        for (int s = 0; s < 3; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4 * Cfg::WGS); }
         mbar_init(a_ready, 4); mbar_init(a_free, 1);
         fence_barrier_init();
     }
@@ -500,21 +568,22 @@ __global__ void __launch_bounds__(TsCfg<NWG>::THREADS, 1) gram_i8_ts_kernel(cons
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // provably warp-uniform
 
     if (warp < 4) {
-        if constexpr (NWG == 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TS_CTRL_REGS));
-        else asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+        if constexpr (PW == 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TS_CTRL_REGS));
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TS_CTRL_REGS_N48));
         if (warp == 0 && lane == 0) {
             // ---- producer: the B tile of every block, four slices ------------------------------------------------
             TsWalker<FJ> w;
             w.init(ti_begin, ntj, blk_start, blk_count);
             int stage = 0; uint32_t phase = 0;
             const uint32_t b_slice = (uint32_t)(N * kp);   // one digit slice of a B tile
+            const uint64_t keep = l2_policy_evict_last();
             for (; w.valid(); w.next()) {
                 mbar_wait_sleep(&bempty[stage], phase ^ 1, 2000u);
                 mbar_expect_tx(&bfull[stage], OZ_SLICES * b_slice);
                 unsigned char* dst = smem + stage * Cfg::B_STAGE;
                 const uint8_t* src = p.packB + (size_t)w.tj * (OZ_SLICES * b_slice);
 #pragma unroll
-                for (int s = 0; s < OZ_SLICES; ++s) bulk_g2s(dst + s * b_slice, src + s * b_slice, b_slice, &bfull[stage]);
+                for (int s = 0; s < OZ_SLICES; ++s) bulk_g2s_hint(dst + s * b_slice, src + s * b_slice, b_slice, &bfull[stage], keep);
                 stage ^= 1; if (stage == 0) phase ^= 1;
             }
         } else if (warp == 1) {
@@ -524,7 +593,6 @@ __global__ void __launch_bounds__(TsCfg<NWG>::THREADS, 1) gram_i8_ts_kernel(cons
             int stage = 0; uint32_t phase = 0;
             int tb = 0; uint32_t tphase = 0;
             int cur_ti = -1; uint32_t a_phase = 0;
-            constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);
             for (; w.valid(); w.next()) {
                 if (w.ti != cur_ti) {
                     // new block row: the accumulate warps replace the A tile once the MMAs that read the old one are done
@@ -537,36 +605,23 @@ __global__ void __launch_bounds__(TsCfg<NWG>::THREADS, 1) gram_i8_ts_kernel(cons
                 mbar_wait(&bfull[stage], phase);
                 tc_fence_after();
                 const uint32_t b_lo = ((uint32_t)(N * 16 >> 4) << 16) | (smem_u32(smem + stage * Cfg::B_STAGE) >> 4);
-                const uint32_t b_slice16 = (uint32_t)(N * kp) >> 4, a_slice_cols = (uint32_t)kp >> 2;
 #pragma unroll
                 for (int pr = 0; pr < OZ_NPAIR; ++pr) {
                     mbar_wait(&tempty[tb], tphase ^ 1);
                     tc_fence_after();
                     if (elect_one()) {
-#pragma unroll
-                        for (int lv = 0; lv < 2; ++lv) {
-                            // Level pairs in the order (2,3), (4,5), (0,1) = 28, 20 and 12 MMAs per 128 atoms: the pair that can only
-                            // be issued once the epilogue has drained the first one (two TMEM buffers) is the cheapest, so the
-                            // epilogue, which needs it 1-2 conversions later, does not wait for the tensor pipe
-                            const int q = 2 * ((pr + 1) % OZ_NPAIR) + lv;
-                            const uint32_t d = tmem_base + (uint32_t)(tb * 2 * N + lv * N);
-                            const int s_lo = q > 3 ? q - 3 : 0, s_hi = q < 3 ? q : 3;
-#pragma unroll
-                            for (int s = s_lo; s <= s_hi; ++s) {
-#pragma unroll 2
-                                for (int kc = 0; kc < nch; ++kc) {
-                                    // one MMA = 32 atoms: A from 8 TMEM columns, B = two 16-byte K halves of N / 8 core matrices
-                                    const uint64_t bd = ((uint64_t)DESC_HI << 32) |
-                                                        (b_lo + (uint32_t)(q - s) * b_slice16 + (uint32_t)(kc * 2 * N));
-                                    umma_i8_ts(d, tmem_base + (uint32_t)ACOL + (uint32_t)s * a_slice_cols + (uint32_t)(kc * 8), bd,
-                                               Cfg::IDESC, (s > s_lo || kc > 0) ? 1u : 0u);
-                                }
-                            }
-                        }
+                        // Level pairs in the order (2,3), (4,5), (0,1) = 28, 20 and 12 MMAs per 128 atoms: with two TMEM
+                        // buffers the third pair of a block can only be issued once the epilogue has taken the first one
+                        // out of its buffer; it is the cheapest, so the epilogue waits least for the tensor pipe.
+                        // (A variant with the chunk loop unrolled per contraction length and compile-time operand offsets
+                        // issued an MMA in ~26 instead of ~57 cycles and made the kernels SLOWER -- cfg2 40.0 -> 35.5, K = 300
+                        // 21.0 -> 20.6 Gpairs/s: issue is not the limiter, and the larger code of five instantiations costs
+                        // instruction-cache misses in the epilogue warps.)
+                        ts_issue_pair<N, 0>(pr, tmem_base + (uint32_t)(tb * 2 * N), tmem_base + acol, b_lo, nch);
                         umma_commit(&tfull[tb]);
                     }
                     __syncwarp();
-                    tb ^= 1; if (tb == 0) tphase ^= 1;
+                    if (++tb == nbuf) { tb = 0; tphase ^= 1; }
                 }
                 if (elect_one()) umma_commit(&bempty[stage]);
                 __syncwarp();
@@ -574,12 +629,12 @@ __global__ void __launch_bounds__(TsCfg<NWG>::THREADS, 1) gram_i8_ts_kernel(cons
             }
         }
     } else {
-        // ---- epilogue warps (4 warpgroups): warpgroup wg owns accumulator columns 24 wg .. 24 wg + 23 = 8 column frames ----
+        // ---- epilogue warps (4 warpgroups): warpgroup wg owns accumulator columns CW wg .. CW wg + CW - 1 = PW column frames ----
         // 96 registers x 640 threads are the CTA's allocation: the control warps keep 32, which leaves 112 for each epilogue thread
-        if constexpr (NWG == 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TS_EPI_REGS));
-        else asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        if constexpr (PW == 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TS_EPI_REGS));
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TS_EPI_REGS_N48));
         const int quarter = warp & 3;                 // TMEM lanes 32 * quarter .. + 31
-        const int wg = (warp - 4) >> 2;               // 0..NWG-1
+        const int wg = (warp - 4) >> 2;               // 0..3
         const int wt = tid - 128 - wg * 128;          // thread index inside the warpgroup
         const int g = lane / 3, a = lane - 3 * g;
         const bool row_ok = lane < 30;
@@ -594,37 +649,58 @@ __global__ void __launch_bounds__(TsCfg<NWG>::THREADS, 1) gram_i8_ts_kernel(cons
         //   acc = acc + fma(xm_hi, s_hi, -MAGIC s_hi)         = the whole element, rounded ONCE     (the fma is exact: v_hi s_hi)
         // (scales are powers of two 2^16 apart, |v| < 2^34.)  4 FP64 operations per value instead of 6, on the pipe the
         // epilogue is throttled by, and a correctly rounded sum.
-        constexpr double MAGIC = NWG == 4 ? 4503601774854144.0 : 6755399441055744.0;   // 2^52 + 2^31 | 2^52 + 2^51
+        constexpr double MAGIC = PW == 8 ? 4503601774854144.0 : 6755399441055744.0;   // 2^52 + 2^31 | 2^52 + 2^51
         const double kfold_mid = -MAGIC * (s_mid + s_lo), kfold_hi = -MAGIC * s_hi;
-        double* wg_scratch = scratch + wg * (OZ_FI * TS_WG_PITCH);
+        double* wg_scratch = scratch + wg * (OZ_FI * PITCH);
         // per-warpgroup tables of the current block row, refreshed when the row changes: element offset of every row's
         // start in the output slab (shifted so that column j indexes it directly) and G of the row's frame
         long long* row_off_s = reinterpret_cast<long long*>(smem + 2 * Cfg::B_STAGE + Cfg::SCRATCH + 256) + wg * (2 * OZ_FI);
         double* row_g_s = reinterpret_cast<double*>(row_off_s + OZ_FI);
+        // Pairs of this warpgroup: 40 rows x PW columns, solved in warp passes of 32 lanes.  Warp ww of the warpgroup takes
+        // the passes q, q + 4, ... with q = (ww - wg) mod 4: the warps with one pass more sit on different schedulers in
+        // different warpgroups (warp ww of every warpgroup shares scheduler ww).
+        //   PW = 8: a pass = four rows 8 apart x 8 columns (lane = 8 sub + jl): 40 (row, sub) slots, ten passes -> 3,3,2,2.
+        //   PW = 4: a pass = two half-warps of four rows 4 apart x 4 columns (lane = 16 h + 4 sub + jl): twelve half-warps
+        //           (rows 32-39 fill theirs half), six passes -> 2,2,1,1.
+        // With the row pitch = 9 (mod 16) doubles the 16 lanes of a shared-memory wavefront then read 16 different 8-byte
+        // bank units (PW = 8: except where a pass wraps from row 32+ to row 1+), and the writers -- lane 3 g + a holds
+        // the row of frame g, coordinate a -- write conflict-free; every row's PW results are one run of the output.
+        const int q_pass = ((wt >> 5) - wg) & 3;
         // Thread-invariant shared-memory addresses, made opaque so that the compiler keeps them in registers instead of
         // re-deriving them from the thread index in every block (~75 instructions per block otherwise)
-        uint32_t my_row_s = smem_u32(wg_scratch + (quarter * 10 + g) * TS_WG_PITCH + 3 * a);
-        uint32_t rd_s[3], tab_s[3];
-        int il_r[3];
+        uint32_t my_row_s = smem_u32(wg_scratch + (quarter * 10 + g) * PITCH + 3 * a);
+        uint32_t rd_s[NR], tab_s[NR];
+        int il_r[NR];
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            // warp ww of the warpgroup takes the passes with (pass + wg) % 4 == ww: the two warps with three passes sit on
-            // different schedulers in different warpgroups (warp ww of every warpgroup shares scheduler ww)
-            const int pass = (((wt >> 5) - wg) & 3) + 4 * r;
-            const int slot = 4 * pass + (lane >> 3);          // 0..39 (valid) .. 47
-            const int il = slot < OZ_FI ? (slot / 5) + 8 * (slot % 5) : 0;
-            il_r[r] = slot < OZ_FI ? il : -1;
-            rd_s[r] = smem_u32(wg_scratch + il * TS_WG_PITCH + (lane & 7) * 9);
+        for (int r = 0; r < NR; ++r) {
+            const int pass = q_pass + 4 * r;
+            int il, jl;
+            bool valid;
+            if constexpr (PW == 8) {
+                const int slot = 4 * pass + (lane >> 3);          // 0..39 (valid) .. 47
+                valid = slot < OZ_FI;
+                il = (slot / 5) + 8 * (slot % 5);
+                jl = lane & 7;
+            } else {
+                const int hw = 2 * pass + (lane >> 4);            // half-warp 0..11 (valid) .. 15
+                il = 16 * (hw >> 2) + (hw & 3) + 4 * ((lane >> 2) & 3);
+                valid = hw < 12 && il < OZ_FI;
+                jl = lane & 3;
+            }
+            if (!valid) il = 0;
+            il_r[r] = valid ? il : -1;
+            rd_s[r] = smem_u32(wg_scratch + il * PITCH + jl * 9);
             tab_s[r] = smem_u32(row_off_s + il);
             asm volatile("" : "+r"(rd_s[r]), "+r"(tab_s[r]), "+r"(il_r[r]));
         }
         asm volatile("" : "+r"(my_row_s));
+        const int jl_mine = PW == 8 ? (lane & 7) : (lane & 3);
         const int last_row = min(p.row_end, p.M - 1);
         TsWalker<FJ> w;
         w.init(ti_begin, ntj, blk_start, blk_count);
         int tb = 0; uint32_t tphase = 0;
         int cur_ti = -1; uint32_t afree_phase = 0;
-        // register pairs that hold the high word of the magic constant for good: a conversion only replaces the low word
+        // register pairs that hold the high word of the magic constant (PW = 8: the 32-bit form of the conversion)
         double magic_pair[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) magic_pair[k] = p.qinfo[4 + k];   // 2^52 + 2^31, opaque to the compiler (see quant_info_kernel)
@@ -633,13 +709,13 @@ __global__ void __launch_bounds__(TsCfg<NWG>::THREADS, 1) gram_i8_ts_kernel(cons
             if (wg == 0 && new_row) {
                 // this warp's 32 A rows of the new block row: global -> registers -> TMEM
                 if (cur_ti >= 0) { mbar_wait(a_free, afree_phase); afree_phase ^= 1; tc_fence_after(); }
-                const uint4* src = reinterpret_cast<const uint4*>(p.packT + ((size_t)w.ti * OZ_M + quarter * 32 + lane) * (size_t)(OZ_SLICES * kp));
+                const uint8_t* src = p.packT + ((size_t)w.ti * OZ_M + quarter * 32 + lane) * (size_t)(OZ_SLICES * kp);
 #pragma unroll
                 for (int s = 0; s < OZ_SLICES; ++s) {
                     for (int kc = 0; kc < nch; ++kc) {   // 32 atoms = 32 bytes = 8 TMEM columns
-                        const uint4 x0 = __ldg(src + (s * kp >> 4) + 2 * kc), x1 = __ldg(src + (s * kp >> 4) + 2 * kc + 1);
-                        const uint32_t v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-                        tmem_st8(tlane + (uint32_t)(ACOL + s * (kp >> 2) + kc * 8), v);
+                        uint32_t v[8];
+                        ldg256_evict_first(src + s * kp + 32 * kc, v);
+                        tmem_st8(tlane + acol + (uint32_t)(s * (kp >> 2) + kc * 8), v);
                     }
                 }
                 tmem_wait_st();
@@ -649,17 +725,18 @@ __global__ void __launch_bounds__(TsCfg<NWG>::THREADS, 1) gram_i8_ts_kernel(cons
             }
             cur_ti = w.ti;
             // G of this thread's column frame: fetched now, used after the accumulate phase
-            const double gj = p.Gq[w.tj * FJ + wg * 8 + (lane & 7)];
-            // Level pairs -> FP64 covariance rows.  A pair's TMEM buffer goes back to the MMA warp the moment its 24 columns are
-            // in registers, BEFORE they are converted: the third pair of a block can only be issued into the buffer of the
-            // first (two buffers), and every cycle between that release and the point where the epilogue needs the third pair
+            const int j = w.tj * FJ + wg * PW + jl_mine;
+            const double gj = p.Gq[j];
+            // Level pairs -> FP64 covariance rows.  A pair's TMEM buffer goes back to the MMA warp the moment its columns are
+            // in registers, BEFORE they are converted: with two buffers the third pair of a block can only be issued into the
+            // buffer of the first, and every cycle between that release and the point where the epilogue needs the third pair
             // is one it does not wait for the tensor pipe.
-            double acc[24];
+            double acc[CW];
             auto convert = [&](int pr, int n, uint32_t e_raw, uint32_t o_raw) {
                 const int e = (int)e_raw, o = (int)o_raw;
                 double xm;
-                if constexpr (NWG == 4) {
-                    // 2^52 + 2^31 + v: only the low word of a resident register pair changes
+                if constexpr (PW == 8) {
+                    // kp <= 128: |256 e + o| < 2^31.  2^52 + 2^31 + v: only the low word of a resident register pair changes
                     const int lo = (e * 256 + o) ^ (int)0x80000000;
                     asm("{\n.reg .b32 l, h;\nmov.b64 {l, h}, %0;\nmov.b64 %0, {%1, h};\n}" : "+d"(magic_pair[n & 7]) : "r"(lo));
                     xm = magic_pair[n & 7];
@@ -674,27 +751,28 @@ __global__ void __launch_bounds__(TsCfg<NWG>::THREADS, 1) gram_i8_ts_kernel(cons
             for (int pr = 0; pr < OZ_NPAIR; ++pr) {
                 mbar_wait(&tfull[tb], tphase);
                 tc_fence_after();
-                const uint32_t t0 = tlane + (uint32_t)(tb * 2 * N + wg * 24);
-                uint32_t ev[16], od[16], ev2[8], od2[8];
-                tmem_ld16(t0, ev);
-                tmem_ld16(t0 + N, od);
-                tmem_ld8(t0 + 16, ev2);
-                tmem_ld8(t0 + N + 16, od2);
+                const uint32_t t0 = tlane + (uint32_t)(tb * 2 * N + wg * CW);
+                uint32_t ev[2 * PW], od[2 * PW], ev2[PW], od2[PW];   // CW columns = 2 PW + PW
+                if constexpr (PW == 8) {
+                    tmem_ld16(t0, ev); tmem_ld16(t0 + N, od); tmem_ld8(t0 + 16, ev2); tmem_ld8(t0 + N + 16, od2);
+                } else {
+                    tmem_ld8(t0, ev); tmem_ld8(t0 + N, od); tmem_ld4(t0 + 8, ev2); tmem_ld4(t0 + N + 8, od2);
+                }
                 tmem_wait_ld();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[tb]);
-                tb ^= 1; if (tb == 0) tphase ^= 1;
+                if (++tb == nbuf) { tb = 0; tphase ^= 1; }
 #pragma unroll
-                for (int n = 0; n < 16; ++n) convert(pr, n, ev[n], od[n]);
+                for (int n = 0; n < 2 * PW; ++n) convert(pr, n, ev[n], od[n]);
 #pragma unroll
-                for (int n = 0; n < 8; ++n) convert(pr, 16 + n, ev2[n], od2[n]);
+                for (int n = 0; n < PW; ++n) convert(pr, 2 * PW + n, ev2[n], od2[n]);
             }
             // ---- transposition through shared memory: rows (frame i, coordinate a) in, whole 3x3 of one pair out ----
             asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");   // everyone has read the previous block (and its tables)
             if (row_ok) {
 #pragma unroll
-                for (int jj = 0; jj < 8; ++jj) {
+                for (int jj = 0; jj < PW; ++jj) {
                     asm volatile("st.shared.f64 [%0], %1;" ::"r"(my_row_s + (uint32_t)(jj * 72)), "d"(acc[3 * jj + 0]) : "memory");
                     asm volatile("st.shared.f64 [%0], %1;" ::"r"(my_row_s + (uint32_t)(jj * 72 + 8)), "d"(acc[3 * jj + 1]) : "memory");
                     asm volatile("st.shared.f64 [%0], %1;" ::"r"(my_row_s + (uint32_t)(jj * 72 + 16)), "d"(acc[3 * jj + 2]) : "memory");
@@ -706,16 +784,11 @@ __global__ void __launch_bounds__(TsCfg<NWG>::THREADS, 1) gram_i8_ts_kernel(cons
                 row_g_s[wt] = p.Gq[i];
             }
             asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
-            // Pairs of this warpgroup: 40 rows x 8 columns.  A warp pass takes four 8-row-apart rows (lane = 8 * sub + jl),
-            // so that the 16 lanes of a shared-memory wavefront read 16 different 8-byte bank units (il + jl all different
-            // mod 16) and every row's 8 results are one 64-byte run of the condensed vector.  40 (row class, sub) slots,
-            // four per warp pass: passes 0-9, a warp does passes q, q + 4, q + 8 with q = (ww - wg) mod 4.
-            double qa[3], qb[3], qd[3], hg[3], lam[3];
-            long long out_off[3];   // offset of the pair's entry in the output slab
-            bool pmine[3];
-            const int j = w.tj * FJ + wg * 8 + (lane & 7);
+            double qa[NR], qb[NR], qd[NR], hg[NR], lam[NR];
+            long long out_off[NR];   // offset of the pair's entry in the output slab
+            bool pmine[NR];
 #pragma unroll
-            for (int r = 0; r < 3; ++r) {
+            for (int r = 0; r < NR; ++r) {
                 const int i = w.ti * OZ_FI + il_r[r];
                 const bool live = il_r[r] >= 0 && i < j && j < p.M;
                 pmine[r] = live && i >= p.row_begin && i < last_row;
@@ -738,15 +811,19 @@ __global__ void __launch_bounds__(TsCfg<NWG>::THREADS, 1) gram_i8_ts_kernel(cons
                 quartic_invariants(s9, qa[r], qb[r], qd[r]);
             }
             unsigned okmask;
-            if ((((wt >> 5) - wg) & 3) < 2) {
-                okmask = largest_root_fast<3>(qa, qb, qd, hg, lam);
-            } else {  // passes 10 and 11 do not exist: warps 2 and 3 of the warpgroup have two passes
-                double a2[2] = {qa[0], qa[1]}, b2[2] = {qb[0], qb[1]}, d2[2] = {qd[0], qd[1]}, h2[2] = {hg[0], hg[1]}, l2[2];
-                okmask = largest_root_fast<2>(a2, b2, d2, h2, l2);
-                lam[0] = l2[0]; lam[1] = l2[1]; lam[2] = 0.0;
+            if (q_pass < 2) {
+                okmask = largest_root_fast<NR>(qa, qb, qd, hg, lam);
+            } else {  // the last pass does not exist for these warps
+                double a2[NR - 1], b2[NR - 1], d2[NR - 1], h2[NR - 1], l2[NR - 1];
+#pragma unroll
+                for (int r = 0; r < NR - 1; ++r) { a2[r] = qa[r]; b2[r] = qb[r]; d2[r] = qd[r]; h2[r] = hg[r]; }
+                okmask = largest_root_fast<NR - 1>(a2, b2, d2, h2, l2);
+#pragma unroll
+                for (int r = 0; r < NR - 1; ++r) lam[r] = l2[r];
+                lam[NR - 1] = 0.0;
             }
 #pragma unroll
-            for (int r = 0; r < 3; ++r) {
+            for (int r = 0; r < NR; ++r) {
                 const double eh = hg[r] - lam[r];
                 const double v = (eh > 0.0 ? eh : 0.0) * p.inv_k2;
                 const double y = rsqrt_approx_f64(v + 1e-300);        // sqrt(v) = v / sqrt(v), one Newton step
@@ -798,13 +875,13 @@ __global__ void quant_info_kernel(const unsigned long long* maxbits, double* qin
     qinfo[0] = ldexp(1.0, -2 * f);
     qinfo[1] = (double)f;
     qinfo[2] = __longlong_as_double((long long)*maxbits);
-    // 2^52 + 2^31: the epilogue of gram_i8_ts_kernel<4> reads these eight copies at run time so that the compiler sees eight
+    // 2^52 + 2^31: the epilogue of gram_i8_ts_kernel<8> reads these eight copies at run time so that the compiler sees eight
     // unrelated values and keeps each in its own register pair, of which a conversion only replaces the low word
     for (int k = 0; k < 8; ++k) qinfo[4 + k] = 4503601774854144.0;
 }
 
 // Which tcgen05 kernel serves K kept atoms, and the operand layouts it reads.
-//   mode 4 / 2: gram_i8_ts_kernel<4> / <2> (A in TMEM; column tiles of 32 / 16 frames), whole contraction in one stage:
+//   mode 4 / 2: gram_i8_ts_kernel<8> / <4> (A in TMEM; column tiles of 32 / 16 frames), whole contraction in one stage:
 //               packT [ti][128 rows][slice][kp B], packB [tj][slice][kp / 16][N / 8][8 rows][16 B]
 //   mode 0    : gram_i8_kernel (A and B through shared memory, K-blocks of 128 atoms): packA / packB as in OzParams
 struct OzPlan {
@@ -816,8 +893,8 @@ static OzPlan oz_plan(int K) {
     const int kp = (K + 31) / 32 * 32;
     const char* force = getenv("CLUSTTRAJ_B200_OZ_MODE");   // development: 2 = prefer the N = 48 shape, 0 = shared-memory kernel
     const int fm = force ? atoi(force) : 4;
-    if (kp <= TsCfg<4>::KP_MAX && fm == 4) pl = {4, kp, TsCfg<4>::FJ, TsCfg<4>::N, kp / 16};
-    else if (kp <= TsCfg<2>::KP_MAX && fm != 0) pl = {2, kp, TsCfg<2>::FJ, TsCfg<2>::N, kp / 16};
+    if (kp <= TsCfg<8>::KP_MAX && fm == 4) pl = {4, kp, TsCfg<8>::FJ, TsCfg<8>::N, kp / 16};
+    else if (kp <= TsCfg<4>::KP_MAX && fm != 0) pl = {2, kp, TsCfg<4>::FJ, TsCfg<4>::N, kp / 16};
     else pl = {0, OZ_KB, OZ_FJ, OZ_N, (K + OZ_KB - 1) / OZ_KB * 8};
     return pl;
 }
@@ -937,9 +1014,9 @@ cudaError_t launch_quant_pack(const double* centred, int M, int K, uint8_t* pack
     return cudaGetLastError();
 }
 
-template <int NWG>
+template <int PW>
 static cudaError_t launch_ts(OzParams p, int sm_count, cudaStream_t stream) {
-    using Cfg = TsCfg<NWG>;
+    using Cfg = TsCfg<PW>;
     const int ti_begin = p.row_begin / OZ_FI;
     const int last_row = p.row_end < p.M - 1 ? p.row_end : p.M - 1;
     const int ti_end = (last_row + OZ_FI - 1) / OZ_FI;
@@ -949,9 +1026,9 @@ static cudaError_t launch_ts(OzParams p, int sm_count, cudaStream_t stream) {
     if (blocks <= 0) return cudaSuccess;
     p.total_blocks = blocks;
     const long long grid = blocks < sm_count ? blocks : sm_count;
-    cudaError_t e = cudaFuncSetAttribute(gram_i8_ts_kernel<NWG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gram_i8_ts_kernel<PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) return e;
-    gram_i8_ts_kernel<NWG><<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM, stream>>>(p);
+    gram_i8_ts_kernel<PW><<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -960,7 +1037,7 @@ cudaError_t launch_gram_i8(OzParams p, int K, int sm_count, cudaStream_t stream)
     if (pl.mode) {
         p.nkb = 1;
         p.last_chunks = pl.kp / 32;
-        return pl.mode == 4 ? launch_ts<4>(p, sm_count, stream) : launch_ts<2>(p, sm_count, stream);
+        return pl.mode == 4 ? launch_ts<8>(p, sm_count, stream) : launch_ts<4>(p, sm_count, stream);
     }
     p.nkb = (K + OZ_KB - 1) / OZ_KB;
     const int tail = K - (p.nkb - 1) * OZ_KB;

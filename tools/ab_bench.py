@@ -12,8 +12,8 @@ from clusttraj_b200.synth import make_trajectory
 shapes = sys.argv[1].split(",")
 tag = sys.argv[2]
 for sh in shapes:
-    M, N = (int(x) for x in sh.split("x")[:2])
     noh = sh.endswith("n")
+    M, N = (int(x) for x in sh.rstrip("n").split("x")[:2])
     atoms, coords = make_trajectory(M, N, seed=20250602)
     eng = _engine.Engine(0)
     eng.load_frames(coords, atoms, _engine.make_opts(no_hydrogen=noh))
