@@ -38,7 +38,11 @@ for k, a in enumerate(sys.argv):
     if a == "--shapes":
         shapes = sys.argv[k + 1]
         libs = [x for x in libs if x != shapes]
-for k, lib in enumerate(libs):
-    print(os.path.basename(lib), flush=True)
+for k, spec in enumerate(libs):
+    lib, *sets = spec.split("@")      # lib.so@CLUSTTRAJ_B200_PACE=4,0  runs the library with that environment variable set
+    print(os.path.basename(lib), *sets, flush=True)
     env = dict(os.environ, CLUSTTRAJ_B200_LIB=os.path.abspath(lib))
+    for kv in sets:
+        key, val = kv.split("=", 1)
+        env[key] = val
     subprocess.run([sys.executable, "-c", CHILD, shapes, str(k)], env=env)
