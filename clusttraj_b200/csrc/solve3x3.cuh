@@ -406,4 +406,81 @@ __device__ __forceinline__ double kabsch_rotation(const double* s, double* U) {
     return lam;
 }
 
+// The same rotation without the Jacobi sweeps (the per-pair kernel computes three of them per pair, redundantly in all 32
+// lanes: 13 % of its time).  lambda is the largest root of the quartic, by Newton from the upper bound sqrt(3a) in full
+// FP64; the quaternion is the null vector of M = K - lambda I, taken as the column of adj(M) with the largest diagonal
+// cofactor (adj(M) = q q^T prod(other eigenvalue gaps) for a simple eigenvalue).  Accepted only when the residual |M q| is
+// at round-off level relative to |K| |q|; anything else -- a (near-)double largest eigenvalue: collinear structures, mirror
+// images of near-symmetric ones, a stalled Newton iteration -- returns false and the caller runs the Jacobi solver.
+__device__ __forceinline__ bool kabsch_rotation_adjugate(const double* s, double* U, double& lam_out) {
+    double a, b, d;
+    quartic_invariants(s, a, b, d);
+    if (!(a > 0.0) || !(a <= 1.7976931348623157e308)) return false;
+    double x = sqrt(3.0 * a) * 1.0000001;
+    bool settled = false;
+#pragma unroll 1
+    for (int it = 0; it < 48; ++it) {
+        const double t = fma(x, x, -a);
+        const double f = fma(t, t, -fma(8.0 * d, x, 4.0 * b));
+        const double fq = fma(x, t, -2.0 * d);
+        if (!(fq > 0.0)) break;
+        const double step = f * (0.25 * rcp_approx_f64(fq));   // 23-bit reciprocal: a Newton step is self-correcting
+        x -= step;
+        // a step below 1e-9 x leaves a quadratically smaller error (the root is simple, or the residual test below refuses)
+        if (fabs(step) <= 1e-9 * x) {
+            const double t2 = fma(x, x, -a);
+            x -= fma(t2, t2, -fma(8.0 * d, x, 4.0 * b)) * (0.25 * rcp_approx_f64(fma(x, t2, -2.0 * d)));   // one more, for the last bits
+            settled = true;
+            break;
+        }
+    }
+    if (!settled) return false;
+    const double Sxx = s[0], Sxy = s[1], Sxz = s[2], Syx = s[3], Syy = s[4], Syz = s[5], Szx = s[6], Szy = s[7], Szz = s[8];
+    // M = K - lambda I, symmetric: m00 m01 m02 m03 / m11 m12 m13 / m22 m23 / m33
+    const double m00 = Sxx + Syy + Szz - x, m11 = Sxx - Syy - Szz - x, m22 = -Sxx + Syy - Szz - x, m33 = -Sxx - Syy + Szz - x;
+    const double m01 = Syz - Szy, m02 = Szx - Sxz, m03 = Sxy - Syx, m12 = Sxy + Syx, m13 = Szx + Sxz, m23 = Syz + Szy;
+    // 2x2 minors of rows (2,3) and of rows (0,1), shared by the cofactors
+    const double r01 = m02 * m13 - m03 * m12, r02 = m02 * m23 - m03 * m22, r03 = m02 * m33 - m03 * m23;
+    const double r12 = m12 * m23 - m13 * m22, r13 = m12 * m33 - m13 * m23, r23 = m22 * m33 - m23 * m23;
+    const double t01 = m00 * m11 - m01 * m01, t02 = m00 * m12 - m01 * m02, t03 = m00 * m13 - m01 * m03;
+    const double t12 = m01 * m12 - m11 * m02, t13 = m01 * m13 - m11 * m03, t23 = m02 * m13 - m12 * m03;
+    // adjugate of the symmetric 4x4 (Laplace expansion over row pairs (0,1) | (2,3))
+    const double c00 = m11 * r23 - m12 * r13 + m13 * r12;
+    const double c01 = -(m01 * r23 - m12 * r03 + m13 * r02);
+    const double c02 = m01 * r13 - m11 * r03 + m13 * r01;
+    const double c03 = -(m01 * r12 - m11 * r02 + m12 * r01);
+    const double c11 = m00 * r23 - m02 * r03 + m03 * r02;
+    const double c12 = -(m00 * r13 - m01 * r03 + m03 * r01);
+    const double c13 = m00 * r12 - m01 * r02 + m02 * r01;
+    const double c22 = m33 * t01 - m13 * t03 + m03 * t13;
+    const double c23 = -(m23 * t01 - m13 * t02 + m03 * t12);
+    const double c33 = m22 * t01 - m12 * t02 + m02 * t12;
+    (void)t23;
+    // column with the largest diagonal cofactor
+    double q0 = c00, q1 = c01, q2 = c02, q3 = c03, best = fabs(c00);
+    if (fabs(c11) > best) { best = fabs(c11); q0 = c01; q1 = c11; q2 = c12; q3 = c13; }
+    if (fabs(c22) > best) { best = fabs(c22); q0 = c02; q1 = c12; q2 = c22; q3 = c23; }
+    if (fabs(c33) > best) { best = fabs(c33); q0 = c03; q1 = c13; q2 = c23; q3 = c33; }
+    const double n2 = q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3;
+    if (!(n2 > 0.0) || !(n2 <= 1.7976931348623157e308)) return false;
+    const double nrm = rsqrt(n2);
+    q0 *= nrm; q1 *= nrm; q2 *= nrm; q3 *= nrm;
+    // residual of the eigen-equation: round-off level or the Jacobi solver takes over
+    const double e0 = m00 * q0 + m01 * q1 + m02 * q2 + m03 * q3, e1 = m01 * q0 + m11 * q1 + m12 * q2 + m13 * q3;
+    const double e2 = m02 * q0 + m12 * q1 + m22 * q2 + m23 * q3, e3 = m03 * q0 + m13 * q1 + m23 * q2 + m33 * q3;
+    const double res2 = e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
+    if (!(res2 <= 1e-29 * a)) return false;     // |M q| <= 3e-15 |S|_F  (an exact eigenvector leaves ~1e-15 through lambda's last bit)
+    // ... and the eigenvalue must be well separated (forward error ~ residual / gap): adj(M) = q q^T x (product of the
+    // three gaps), so the largest diagonal cofactor measures the gaps against |S|^3
+    if (!(best >= 1e-5 * a * sqrt(a))) return false;
+    const double r00 = q0 * q0 + q1 * q1 - q2 * q2 - q3 * q3, r01_ = 2.0 * (q1 * q2 - q0 * q3), r02_ = 2.0 * (q1 * q3 + q0 * q2);
+    const double r10 = 2.0 * (q2 * q1 + q0 * q3), r11 = q0 * q0 - q1 * q1 + q2 * q2 - q3 * q3, r12_ = 2.0 * (q2 * q3 - q0 * q1);
+    const double r20 = 2.0 * (q3 * q1 - q0 * q2), r21 = 2.0 * (q3 * q2 + q0 * q1), r22 = q0 * q0 - q1 * q1 - q2 * q2 + q3 * q3;
+    U[0] = r00; U[1] = r10; U[2] = r20;
+    U[3] = r01_; U[4] = r11; U[5] = r21;
+    U[6] = r02_; U[7] = r12_; U[8] = r22;
+    lam_out = x;
+    return true;
+}
+
 }  // namespace ct

@@ -14,6 +14,7 @@
 #include "solve3x3.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <vector>
@@ -33,6 +34,7 @@ struct PairPlan {
     const int* block_off[2];  // [nblocks+1] offsets into idx
     const int* idx[2];        // kept-atom positions, ascending inside a block
     int nmax;                 // largest block
+    int credit0;              // initial credit of the two-row collision shortcut (0 switches it off)
 };
 
 struct PairPlanHost {
@@ -45,6 +47,9 @@ struct PairPlanHost {
 };
 
 static constexpr int PAIR_WARPS = 4;
+#ifndef CT_NN_UNROLL
+#define CT_NN_UNROLL 1    // columns per iteration of the nearest-column pass (2 and 4 measured slower: 8.6 -> 8.0 -> 7.1e6 pairs/s)
+#endif
 
 __host__ __device__ inline int pair_smem_per_warp(int nmax) {
     // Qe, Pe (3 doubles per row/column), u, v, shortest (doubles), pred, row4col, col4row, old perm (ints),
@@ -56,7 +61,8 @@ __host__ __device__ inline int pair_smem_per_warp(int nmax) {
 // sqrt for the Euclidean cost: rsqrt.approx.f64 seed (one XU operation, ~22 bits; the FP32 rsqrt it replaces needed
 // two F2F conversions around it, and the quarter-rate XU pipe was as loaded as the FP64 pipe in the frontier scans)
 // + two FP64 Newton steps on the residual: within 1 ulp of the correctly rounded value, ~3x cheaper than the IEEE
-// sequence and free of long dependent chains
+// sequence and free of long dependent chains.  (One step, 6e-14 relative, would do for the assignment -- but measured
+// SLOWER: with the shorter chain ptxas interleaves the eight columns of a scan less: cfg4 shape 8.3 -> 7.6e6 pairs/s.)
 __device__ __forceinline__ double cost_sqrt(double d2) {
     // + 1e-300: keeps d2 = 0 away from rsqrt's infinity and changes no other input by a bit (one DADD where fmax's NaN
     // handling costs eight instructions per entry)
@@ -84,9 +90,12 @@ __device__ __forceinline__ double dist2(double dx, double dy, double dz) { retur
 // square root per row), and the sequential insertion loop runs the Dijkstra scans only for the rows whose nearest
 // column is taken or has a moved dual (~10 % of the rows on solvent-shell data).  The result is the one the plain
 // insertion order produces, step for step.
-template <int C>
+// SHORTCUT: with the two-row collision shortcut below.  A separate instantiation because the mere presence of that code
+// changes how ptxas schedules the frontier scans (-e without -ns, where the shortcut almost never applies and ~3800
+// scans per pair remain: 5.8e5 pairs/s without the code, 4.4e5 with it); the host picks per run (PairPlan::credit0).
+template <int C, bool SHORTCUT>
 __device__ int lsap_warp_reg(int n, const double* Qe, const double* Pe, double* u, int* pred, int* r4c, int* c4r,
-                             double* m_row, int* a_row, unsigned char* moved, int lane) {
+                             double* m_row, int* a_row, unsigned char* moved, int lane, int credit) {
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     {
         double qx[C], qy[C], qz[C], bd[C];
@@ -98,7 +107,8 @@ __device__ int lsap_warp_reg(int n, const double* Qe, const double* Pe, double* 
             qx[c] = in ? Qe[3 * i] : 0.0; qy[c] = in ? Qe[3 * i + 1] : 0.0; qz[c] = in ? Qe[3 * i + 2] : 0.0;
             bd[c] = INF; bj[c] = -1;
         }
-#pragma unroll 1
+        constexpr int NN_UNROLL = CT_NN_UNROLL;
+#pragma unroll NN_UNROLL
         for (int j = 0; j < n; ++j) {
             const double x = Pe[3 * j], y = Pe[3 * j + 1], z = Pe[3 * j + 2];
 #pragma unroll
@@ -130,6 +140,7 @@ __device__ int lsap_warp_reg(int n, const double* Qe, const double* Pe, double* 
     for (int c = 0; c < C; ++c) if (lane + 32 * c < n) valid |= 1u << c;
     int steps = 0;   // frontier scans + direct assignments (each stands for the first scan of its row)
     int cur = 0;
+    // credit: two-row collision shortcut: +1 per success (up to 8), -2 per miss, not attempted at <= 0
 #pragma unroll 1
     while (cur < n) {
         // direct assignments, 32 consecutive rows at a time: a row takes its nearest column when that column is
@@ -152,6 +163,81 @@ __device__ int lsap_warp_reg(int n, const double* Qe, const double* Pe, double* 
             steps += run;
             cur += run;
             if (run == 32 || cur >= n) continue;
+        }
+        // Two-row collision, resolved without frontier scans.  Row `cur` lost its nearest column a to an earlier row i1 and a's
+        // dual has not moved.  The scans would then go: scan 1 (from cur) pops a at m_cur; scan 2 (from i1, offset
+        // m_cur - u[i1]) leaves every other column j at min(c(cur,j), c(i1,j) + m_cur - u[i1]) - v_j, whose minimum lies at the
+        // nearest other column of cur (b2) or of i1 (b1), provided their duals are still 0 (v <= 0 always, so a moved column
+        // can only look worse than its distance).  If that column is unmatched the augmentation ends there: one fused pass over
+        // SQUARED distances for both rows (12 FP64 operations per column instead of two scans' 2 x 17 + bookkeeping, two square
+        // roots in all) gives the same assignment, duals and tie decisions, bit for bit.  Anything else takes the scans.
+        {
+            const int a = a_row[cur];
+            const int i1 = a >= 0 ? r4c[a] : -1;
+            bool fast = SHORTCUT && i1 >= 0 && !moved[a] && credit > 0;   // (credit: see below)
+            if (fast) {
+                // nearest column other than a, first for row cur (t = 0), then for row i1 (t = 1): one copy of the pass, rolled, so
+                // that it adds little code and few live registers next to the 80 that hold the columns
+                unsigned long long kmin0 = 0, kmin1 = 0;
+                int b2 = 0x7fffffff, b1 = 0x7fffffff;
+#pragma unroll 1
+                for (int t = 0; t < 2; ++t) {
+                    const int row = t ? i1 : cur;
+                    const double qx = Qe[3 * row], qy = Qe[3 * row + 1], qz = Qe[3 * row + 2];
+                    double dm = INF;
+                    int jm = 0x7fffffff;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        const int j = lane + 32 * c;
+                        const double e = dist2(qx - px[c], qy - py[c], qz - pz[c]);
+                        const bool take = ((valid >> c) & 1u) && j != a && e < dm;
+                        dm = take ? e : dm; jm = take ? j : jm;
+                    }
+                    // warp argmin (d >= 0: the bit pattern orders like the value; lowest column on a tie)
+                    const unsigned long long k = (unsigned long long)__double_as_longlong(dm);
+                    const unsigned hi = __reduce_min_sync(0xffffffffu, (unsigned)(k >> 32));
+                    const unsigned lo = __reduce_min_sync(0xffffffffu, (unsigned)(k >> 32) == hi ? (unsigned)k : 0xffffffffu);
+                    const unsigned long long km = ((unsigned long long)hi << 32) | lo;
+                    const int bc = (int)__reduce_min_sync(0xffffffffu, k == km ? (unsigned)jm : 0x7fffffffu);
+                    if (t == 0) { kmin0 = km; b2 = bc; } else { kmin1 = km; b1 = bc; }
+                }
+                fast = b2 != 0x7fffffff && b1 != 0x7fffffff && !moved[b2] && !moved[b1];
+                if (fast) {
+                    const double m_cur = m_row[cur];
+                    // what the scans would compute: r = cost + (minVal - u[i]) - v[j], with v = 0 here
+                    const double A = cost_sqrt(__longlong_as_double((long long)kmin0)) + (0.0 - u[cur]);
+                    const double B = cost_sqrt(__longlong_as_double((long long)kmin1)) + (m_cur - u[i1]);
+                    // column b (both rows' candidate when b1 == b2: the later scan only replaces on a strictly lower value)
+                    const bool via_i1 = (b1 == b2) ? (B < A) : (B < A || (B == A && b1 < b2));
+                    const int jw = via_i1 ? b1 : b2;
+                    const double mu = via_i1 ? B : A;
+                    fast = r4c[jw] < 0 && A == A && B == B;
+                    if (fast) {
+                        const double delta = mu - m_cur;                     // minVal - sh[a]
+                        if (delta != 0.0) {
+                            if ((a & 31) == lane) {
+#pragma unroll
+                                for (int c = 0; c < C; ++c) if ((a >> 5) == c) v[c] -= delta;
+                            }
+                            if (lane == 0) { moved[a] = 1; u[i1] += delta; }
+                        }
+                        if (lane == 0) {
+                            u[cur] += mu;
+                            if (via_i1) { r4c[jw] = i1; c4r[i1] = jw; r4c[a] = cur; c4r[cur] = a; }
+                            else { r4c[jw] = cur; c4r[cur] = jw; }
+                        }
+                        __syncwarp();
+                        steps += 2;
+                        ++cur;
+                        credit = credit < 8 ? credit + 1 : 8;
+                        continue;
+                    }
+                }
+                // The fused pass was for nothing.  Where the frames are poorly superposed (no -ns: the whole system is
+                // rotated at once) most collisions need long augmenting paths: after a few misses in a row the attempt is
+                // skipped for the rest of the block.
+                credit -= 2;
+            }
         }
 #pragma unroll
         for (int c = 0; c < C; ++c) sh[c] = INF;
@@ -223,6 +309,13 @@ __device__ int lsap_warp_reg(int n, const double* Qe, const double* Pe, double* 
         ++cur;
     }
     return steps;
+}
+
+template <int C>
+__device__ __forceinline__ int lsap_reg_dispatch(int credit0, int n, const double* Qe, const double* Pe, double* u, int* pred, int* r4c,
+                                                 int* c4r, double* m_row, int* a_row, unsigned char* moved, int lane) {
+    if (credit0 > 0) return lsap_warp_reg<C, true>(n, Qe, Pe, u, pred, r4c, c4r, m_row, a_row, moved, lane, credit0);
+    return lsap_warp_reg<C, false>(n, Qe, Pe, u, pred, r4c, c4r, m_row, a_row, moved, lane, 0);
 }
 
 // ---- warp-parallel shortest augmenting path ------------------------------------------------------------
@@ -299,7 +392,12 @@ __device__ int lsap_warp(int n, const double* Qe, const double* Pe, double* u, d
 
 // One copy of the 4x4 Jacobi instead of one per call site: the per-pair kernel is bound by instruction fetch before
 // anything else (ncu: "no instruction" is its largest stall), so code size is a first-order quantity here.
-__device__ __noinline__ double kabsch_rotation_shared(const double* s, double* U) { return kabsch_rotation(s, U); }
+__device__ __noinline__ double kabsch_rotation_jacobi(const double* s, double* U) { return kabsch_rotation(s, U); }
+__device__ __noinline__ double kabsch_rotation_shared(const double* s, double* U) {
+    double lam;
+    if (kabsch_rotation_adjugate(s, U, lam)) return lam;   // Newton root + adjugate null vector: ~20x less work
+    return kabsch_rotation_jacobi(s, U);                   // (near-)degenerate largest eigenvalue
+}
 
 // rotate the working frame in place: W[k] = W[k] * U (row vector times matrix)
 __device__ __noinline__ void warp_rotate(double* W, int K, const double* U, int lane) {
@@ -398,10 +496,10 @@ __device__ __noinline__ int reorder_phase(const PairPlan& pl, int phase, double*
         } else
         switch ((n + 31) >> 5) {
             // three register-resident instances (2, 4, 8 columns per lane) rather than one per block size: code size
-            case 1: case 2: st = lsap_warp_reg<2>(n, Qe, Pe, u, pred, r4c, c4r, v, reinterpret_cast<int*>(sh), scanned, lane); break;
-            case 3: case 4: st = lsap_warp_reg<4>(n, Qe, Pe, u, pred, r4c, c4r, v, reinterpret_cast<int*>(sh), scanned, lane); break;
+            case 1: case 2: st = lsap_reg_dispatch<2>(pl.credit0, n, Qe, Pe, u, pred, r4c, c4r, v, reinterpret_cast<int*>(sh), scanned, lane); break;
+            case 3: case 4: st = lsap_reg_dispatch<4>(pl.credit0, n, Qe, Pe, u, pred, r4c, c4r, v, reinterpret_cast<int*>(sh), scanned, lane); break;
             case 5: case 6: case 7: case 8:
-                st = lsap_warp_reg<8>(n, Qe, Pe, u, pred, r4c, c4r, v, reinterpret_cast<int*>(sh), scanned, lane); break;
+                st = lsap_reg_dispatch<8>(pl.credit0, n, Qe, Pe, u, pred, r4c, c4r, v, reinterpret_cast<int*>(sh), scanned, lane); break;
             default: st = lsap_warp(n, Qe, Pe, u, v, sh, pred, r4c, c4r, scanned, lane); break;
         }
         steps += st < 0 ? -st : st;
@@ -623,6 +721,12 @@ int pair_plan_build(PairPlanHost** out, const int32_t* kept_z, int K, int natoms
     p.final_direct = p.has_ns && p.do_reorder && !o->final_kabsch;
     p.weighted = o->weight_solute != 0.0;
     p.final_kabsch = o->final_kabsch != 0;
+    {
+        // the two-row collision shortcut pays where the frames are superposed on a solute first (-ns): the solvent atoms
+        // then sit near their partners and nearly every collision is a two-row affair
+        const char* ce = getenv("CLUSTTRAJ_B200_LSAP_CREDIT");   // development: 0 = plain scans only
+        p.credit0 = ce ? atoi(ce) : (p.has_ns ? 6 : 0);
+    }
     if (p.weighted) {
         if (!p.has_ns || K == natoms) { delete h; err = "weight_solute needs solute_natoms and at least one solvent atom"; return CT_ERR_UNSUPPORTED; }
         p.w_solute = o->weight_solute / natoms;

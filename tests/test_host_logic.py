@@ -320,10 +320,11 @@ def test_silhouette_and_metrics_match_the_unmodified_reference(tmp_path, monkeyp
 
 
 def test_folded_level_recombination_is_exact():
-    """The int8 Gram epilogue (csrc/ozaki.cu) takes the bias of the integer->double trick out inside its FMAs:
-    acc = fma(M+v_hi, s_hi, -M(s_hi+s_mid)); acc = fma(M+v_mid, s_mid, acc); acc = fma(M+v_lo, s_lo, acc - M s_lo).
-    Exact rational arithmetic: the two intermediate values are exact and the result is the correctly rounded element,
-    for both bias constants (32-bit and 34-bit level sums) and every fixed-point exponent the engine accepts."""
+    """The int8 Gram epilogue (csrc/ozaki.cu) takes the bias of the integer->double trick out inside its FMAs, level pairs
+    in the order the MMA warp issues them (middle, low, high):
+      acc = fma(M+v_mid, s_mid, -M(s_mid+s_lo)); acc = fma(M+v_lo, s_lo, acc); acc = acc + fma(M+v_hi, s_hi, -M s_hi).
+    Exact rational arithmetic: the two intermediate values and the high product are exact and the result is the correctly
+    rounded element, for both bias constants (32-bit and 34-bit level sums) and every fixed-point exponent the engine accepts."""
     import random
     from fractions import Fraction as F
 
@@ -334,21 +335,21 @@ def test_folded_level_recombination_is_exact():
     for magic, bits in ((4503601774854144.0, 31), (6755399441055744.0, 34)):
         for f in (22, 26, 30):
             s2 = 2.0 ** (-2 * f)
-            sc = [s2 * 2.0 ** 40, s2 * 2.0 ** 24, s2 * 2.0 ** 8]
-            k0, k2 = -magic * (sc[0] + sc[1]), -magic * sc[2]
-            assert F(k0) == -F(magic) * (F(sc[0]) + F(sc[1])) and F(k2) == -F(magic) * F(sc[2])
+            s_hi, s_mid, s_lo = s2 * 2.0 ** 40, s2 * 2.0 ** 24, s2 * 2.0 ** 8
+            k_mid, k_hi = -magic * (s_mid + s_lo), -magic * s_hi
+            assert F(k_mid) == -F(magic) * (F(s_mid) + F(s_lo)) and F(k_hi) == -F(magic) * F(s_hi)
             lim = 2 ** bits - 1
             for t in range(1500):
-                v = [rnd.choice([-lim, lim, 0, 1, -1]) if t < 30 else rnd.randint(-lim, lim) for _ in range(3)]
-                xm = [magic + vi for vi in v]
-                assert all(F(x) == F(magic) + vi for x, vi in zip(xm, v))
-                a = fma(xm[0], sc[0], k0)
-                assert F(a) == v[0] * F(sc[0]) - F(magic) * F(sc[1])
-                a = fma(xm[1], sc[1], a)
-                assert F(a) == v[0] * F(sc[0]) + v[1] * F(sc[1])
-                u = a + k2
-                assert F(u) == F(a) + F(k2)
-                assert fma(xm[2], sc[2], u) == float(v[0] * F(sc[0]) + v[1] * F(sc[1]) + v[2] * F(sc[2]))
+                v_hi, v_mid, v_lo = (rnd.choice([-lim, lim, 0, 1, -1]) if t < 30 else rnd.randint(-lim, lim) for _ in range(3))
+                xm = [magic + vi for vi in (v_hi, v_mid, v_lo)]
+                assert all(F(x) == F(magic) + vi for x, vi in zip(xm, (v_hi, v_mid, v_lo)))
+                a = fma(xm[1], s_mid, k_mid)
+                assert F(a) == v_mid * F(s_mid) - F(magic) * F(s_lo)
+                a = fma(xm[2], s_lo, a)
+                assert F(a) == v_mid * F(s_mid) + v_lo * F(s_lo)
+                h = fma(xm[0], s_hi, k_hi)
+                assert F(h) == v_hi * F(s_hi)
+                assert a + h == float(v_hi * F(s_hi) + v_mid * F(s_mid) + v_lo * F(s_lo))
 
 
 def test_native_xyz_parser_matches_the_line_parser_bit_for_bit(tmp_path, golden_dir):
