@@ -48,18 +48,54 @@ def visible_devices():
 
 
 def _load_trajectory(trajfile):
-    """(atomic numbers int32[N], coords float64[M,N,3]); the engine needs frame-invariant atoms."""
+    """(atomic numbers, coords float64[M,N,3]); the atomic numbers are int32[N] when every frame lists the same atoms
+    in the same order (the usual trajectory) and int32[M,N] otherwise (see frame_invariant_view)."""
     key = (os.path.abspath(trajfile), os.path.getmtime(trajfile), os.path.getsize(trajfile))
     hit = _traj_cache.get("last")
     if hit and hit[0] == key:
         return hit[1], hit[2]
     atoms, coords = read_trajectory(trajfile)
-    if (atoms != atoms[0]).any():
-        raise NotImplementedError(
-            "clusttraj_b200 needs the same atom order in every frame (the reference tolerates per-frame "
-            "element lists; the B200 engine packs a frame-invariant mask)")
-    _traj_cache["last"] = (key, atoms[0].copy(), coords)
-    return atoms[0], coords
+    atoms = atoms[0].copy() if not (atoms != atoms[0]).any() else atoms
+    _traj_cache["last"] = (key, atoms, coords)
+    return atoms, coords
+
+
+def frame_invariant_view(atoms, coords, noh, reorder, nsatoms):
+    """Per-frame element lists (the reference reads every frame's own atoms, distmat.py:131-141) brought to the
+    frame-invariant form the engine packs: returns (atoms int32[K], coords, noh, nsatoms) to compute with.
+
+    The reference uses a frame's elements for two things only: the ``-n`` mask (P[p_atoms != 1], Q[q_atoms != 1]; what is
+    left is paired by POSITION) and the element blocks of a reorder.  So frames whose lists differ are handled here by
+    applying each frame's own hydrogen mask on the host and handing the engine the compacted frames with the mask off,
+    provided the kept atoms can be described once for all frames:
+      * every frame keeps the same number of atoms (the reference's Kabsch needs equal shapes too: ValueError);
+      * with ``-ns -n`` the number of kept solute atoms is the same in every frame (the reference takes it from the row
+        frame, :116-118);
+      * with a reorder the kept elements are the same sequence in every frame (element blocks are per frame in the
+        reference; differing sequences are refused loudly rather than approximated).
+    """
+    atoms = np.asarray(atoms)
+    if atoms.ndim == 1 or not (atoms != atoms[0]).any():
+        return np.ascontiguousarray(atoms if atoms.ndim == 1 else atoms[0], dtype=np.int32), coords, noh, nsatoms
+    keep = (atoms != 1) if noh else np.ones(atoms.shape, dtype=bool)
+    counts = keep.sum(axis=1)
+    if (counts != counts[0]).any():
+        k = int(np.argmax(counts != counts[0]))
+        raise ValueError(f"frames keep different numbers of atoms ({int(counts[0])} in frame 0, {int(counts[k])} in frame {k}): "
+                         "the RMSD of structures of different sizes is not defined")
+    if nsatoms and noh:
+        nat = (atoms[:, :nsatoms] != 1).sum(axis=1)
+        if (nat != nat[0]).any():
+            raise NotImplementedError("clusttraj_b200: -ns with -n needs the same number of non-hydrogen solute atoms in every "
+                                      "frame (the reference takes it from the row frame of each pair)")
+        nsatoms = int(nat[0])
+    K = int(counts[0])
+    kept = atoms[keep].reshape(len(atoms), K)
+    if reorder_mode_of(reorder) != 0 and (kept != kept[0]).any():
+        raise NotImplementedError("clusttraj_b200: a reorder needs the same sequence of (kept) elements in every frame; the "
+                                  "reference builds the element blocks per frame, the B200 engine once per trajectory")
+    coords = np.ascontiguousarray(np.asarray(coords, dtype=np.float64)[keep].reshape(len(atoms), K, 3))
+    return np.ascontiguousarray(kept[0], dtype=np.int32), coords, False, nsatoms
 
 
 def _opts_from(noh, reorder, reorder_solvent_only, nsatoms, weight_solute, reorderexcl, final_kabsch):
@@ -200,9 +236,10 @@ def get_distmat_saving_in_background(clust_opt):
 def build_distance_matrix(clust_opt):
     """Whole condensed matrix for the options in ``clust_opt`` (distmat.py:44-78)."""
     atoms, coords = _load_trajectory(clust_opt.trajfile)
-    opts = _opts_from(clust_opt.no_hydrogen, clust_opt.reorder_alg, clust_opt.reorder_solvent_only,
-                      clust_opt.solute_natoms, clust_opt.weight_solute, clust_opt.reorder_excl,
-                      clust_opt.final_kabsch)
+    atoms, coords, noh, nsatoms = frame_invariant_view(atoms, coords, clust_opt.no_hydrogen, clust_opt.reorder_alg,
+                                                       clust_opt.solute_natoms)
+    opts = _opts_from(noh, clust_opt.reorder_alg, clust_opt.reorder_solvent_only, nsatoms, clust_opt.weight_solute,
+                      clust_opt.reorder_excl, clust_opt.final_kabsch)
     return condensed_matrix(atoms, coords, opts)
 
 
@@ -213,8 +250,10 @@ def compute_distmat_line(idx1, q_info, trajfile, noh, reorder, reorder_solvent_o
     atoms, coords = _load_trajectory(trajfile)
     if q_info is not None:
         q_atoms = np.asarray(q_info[0])
-        if q_atoms.shape != atoms.shape or (q_atoms != atoms).any():
+        row_atoms = atoms if atoms.ndim == 1 else atoms[int(idx1)]
+        if q_atoms.shape != row_atoms.shape or (q_atoms != row_atoms).any():
             raise ValueError("q_info atoms do not match the trajectory file")
+    atoms, coords, noh, nsatoms = frame_invariant_view(atoms, coords, noh, reorder, nsatoms)
     opts = _opts_from(noh, reorder, reorder_solvent_only, nsatoms, weight_solute, reorderexcl, final_kabsch)
     eng = _engine_for(visible_devices()[0])
     eng.load_frames(coords, atoms, opts)

@@ -285,6 +285,9 @@ def superposed_frames(trajfile, reference, members, noh, reorder, reorder_solven
     from .distmat import _engine_for, _load_trajectory, _opts_from, visible_devices
 
     atoms, coords = _load_trajectory(trajfile)
+    if atoms.ndim == 2:
+        raise NotImplementedError("clusttraj_b200: superposed-structure output needs the same atoms in every frame "
+                                  "(the matrix itself accepts per-frame element lists, see distmat.frame_invariant_view)")
     opts = _opts_from(noh, reorder, reorder_solvent_only, nsatoms, weight_solute, reorderexcl, final_kabsch)
     centres = _frame_centres(atoms, coords, bool(noh), nsatoms)
     ref = coords[reference] - centres[reference]

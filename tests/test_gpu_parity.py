@@ -1039,6 +1039,65 @@ def test_gather_into_a_reserved_matrix_on_one_gpu():
     root.close(); other.close()
 
 
+def test_per_frame_element_lists(tmp_path):
+    """Frames that list their atoms differently (reference distmat.py:131-141 reads each frame's own atoms): the drop-in entry
+    points against the oracle run on the per-frame lists; what the engine cannot describe once per trajectory is refused."""
+    from clusttraj_b200 import distmat as D
+    from clusttraj_b200.io import ClustOptions
+    from clusttraj_b200.reorder import reorder_hungarian
+    from clusttraj_b200.synth import make_trajectory
+
+    rng = np.random.default_rng(11)
+    atoms0, coords = make_trajectory(12, 20, seed=5)
+    M, N = coords.shape[:2]
+    sym = {1: "H", 6: "C", 7: "N", 8: "O"}
+    heavy = np.array([6, 7, 8], dtype=np.int32)
+    none = np.asarray([], np.int32)
+
+    def write(path, atoms2d):
+        with open(path, "w") as fh:
+            for m in range(M):
+                fh.write(f"{N}\nframe {m}\n")
+                for z, (x, y, z3) in zip(atoms2d[m], coords[m]):
+                    fh.write(f"{sym[int(z)]} {x:.5f} {y:.5f} {z3:.5f}\n")
+
+    # (1) the heavy atoms change element from frame to frame, the hydrogens stay where they are
+    a1 = np.tile(atoms0, (M, 1))
+    for m in range(1, M):
+        hv = np.where(a1[m] != 1)[0]
+        a1[m, hv] = rng.choice(heavy, size=len(hv))
+    # (2) the hydrogens move around too (same count): -n keeps different positions in different frames
+    a2 = a1.copy()
+    for m in range(1, M):
+        a2[m] = a2[m][rng.permutation(N)]
+    for tag, atoms2d in (("a1", a1), ("a2", a2)):
+        path = str(tmp_path / f"{tag}.xyz")
+        write(path, atoms2d)
+        for noh in (True, False):
+            opt = ClustOptions(trajfile=path, no_hydrogen=noh, reorder=False, reorder_alg=None)
+            got = D.build_distance_matrix(opt)
+            want = oracle_rows(atoms2d, coords, range(M), noh=noh)
+            assert got.shape == want.shape and np.abs(got - want).max() < 1e-8, (tag, noh)
+        line = D.compute_distmat_line(2, (atoms2d[2], coords[2]), path, True, None, False, None, None, none, False)
+        want = oracle_rows(atoms2d, coords, [2], noh=True)
+        assert np.abs(np.asarray(line) - want).max() < 1e-8
+        # -ns -n: the kept solute atoms are counted per frame; (1) keeps the count, so it runs
+        if tag == "a1":
+            line = D.compute_distmat_line(3, None, path, True, None, False, 6, None, none, False)
+            want = oracle_rows(atoms2d, coords, [3], noh=True, ns=6)
+            assert np.abs(np.asarray(line) - want).max() < 1e-8
+    # a reorder over element blocks that differ per frame is refused, not approximated
+    with pytest.raises(NotImplementedError):
+        D.compute_distmat_line(0, None, str(tmp_path / "a2.xyz"), False, reorder_hungarian, False, None, None, none, False)
+    # ... frames with different numbers of kept atoms have no RMSD (the reference's Kabsch fails on the shapes)
+    a4 = a1.copy()
+    a4[5, np.where(a4[5] != 1)[0][0]] = 1
+    path = str(tmp_path / "a4.xyz")
+    write(path, a4)
+    with pytest.raises(ValueError):
+        D.compute_distmat_line(0, None, path, True, None, False, None, None, none, False)
+
+
 def test_in_process_multi_gpu_slabs():
     """condensed_matrix(devices=[0, 1, ...]) — the in-process multi-GPU path the CLI uses (one engine + one host thread
     per GPU, equal-area row slabs): bit-identical to one GPU, and the whole matrix is left resident on the first GPU
