@@ -1015,7 +1015,7 @@ cudaError_t launch_quant_pack(const double* centred, int M, int K, uint8_t* pack
 }
 
 template <int PW>
-static cudaError_t launch_ts(OzParams p, int sm_count, cudaStream_t stream) {
+static cudaError_t launch_ts(OzParams p, int sm_count, size_t b_bytes, cudaStream_t stream) {
     using Cfg = TsCfg<PW>;
     const int ti_begin = p.row_begin / OZ_FI;
     const int last_row = p.row_end < p.M - 1 ? p.row_end : p.M - 1;
@@ -1028,8 +1028,40 @@ static cudaError_t launch_ts(OzParams p, int sm_count, cudaStream_t stream) {
     const long long grid = blocks < sm_count ? blocks : sm_count;
     cudaError_t e = cudaFuncSetAttribute(gram_i8_ts_kernel<PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) return e;
+    // The B operand is what every CTA re-reads (one 16- or 32-frame tile per block, the whole array once per row of blocks)
+    // while 8 bytes per pair stream out through the same L2: mark it persisting for this launch (an access policy window over
+    // the array; a hit ratio below 1 when it exceeds the set-aside part of the L2), everything else streaming.
+    static const bool l2_window = !(getenv("CLUSTTRAJ_B200_L2_WINDOW") && atoi(getenv("CLUSTTRAJ_B200_L2_WINDOW")) == 0);
+    bool window_set = false;
+    if (l2_window && b_bytes > 0) {
+        int dev = 0, max_persist = 0, max_window = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        if (max_persist > 0 && max_window > 0) {
+            size_t lim = 0;
+            if (cudaDeviceGetLimit(&lim, cudaLimitPersistingL2CacheSize) != cudaSuccess || lim < (size_t)max_persist)
+                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+            cudaStreamAttrValue av{};
+            const size_t bytes = b_bytes < (size_t)max_window ? b_bytes : (size_t)max_window;
+            av.accessPolicyWindow.base_ptr = const_cast<uint8_t*>(p.packB);
+            av.accessPolicyWindow.num_bytes = bytes;
+            av.accessPolicyWindow.hitRatio = bytes <= (size_t)max_persist ? 1.0f : (float)((double)max_persist / (double)bytes);
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            window_set = cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess;
+        }
+        cudaGetLastError();   // the hint is optional: never fail the launch over it
+    }
     gram_i8_ts_kernel<PW><<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM, stream>>>(p);
-    return cudaGetLastError();
+    e = cudaGetLastError();
+    if (window_set) {
+        cudaStreamAttrValue av{};
+        av.accessPolicyWindow.num_bytes = 0;
+        cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av);
+        cudaGetLastError();
+    }
+    return e;
 }
 
 cudaError_t launch_gram_i8(OzParams p, int K, int sm_count, cudaStream_t stream) {
@@ -1037,7 +1069,8 @@ cudaError_t launch_gram_i8(OzParams p, int K, int sm_count, cudaStream_t stream)
     if (pl.mode) {
         p.nkb = 1;
         p.last_chunks = pl.kp / 32;
-        return pl.mode == 4 ? launch_ts<8>(p, sm_count, stream) : launch_ts<4>(p, sm_count, stream);
+        const size_t b_bytes = oz_packB_bytes(p.M, K);
+        return pl.mode == 4 ? launch_ts<8>(p, sm_count, b_bytes, stream) : launch_ts<4>(p, sm_count, b_bytes, stream);
     }
     p.nkb = (K + OZ_KB - 1) / OZ_KB;
     const int tail = K - (p.nkb - 1) * OZ_KB;
