@@ -1,4 +1,4 @@
-"""Timing of the per-pair (stepwise / Hungarian) kernel on a cfg4-shaped sample: python tools/pair_bench.py [M]"""
+"""Timing of the per-pair (stepwise / Hungarian) kernel on a cfg4-shaped sample: python tools/pair_bench.py [M] [solvent molecules]"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -6,7 +6,8 @@ from clusttraj_b200 import _engine
 from clusttraj_b200.synth import make_solute_solvent
 
 M = int(sys.argv[1]) if len(sys.argv) > 1 else 600
-atoms, coords = make_solute_solvent(M, n_solute=60, n_solvent_mol=100, seed=20250604)
+NMOL = int(sys.argv[2]) if len(sys.argv) > 2 else 100
+atoms, coords = make_solute_solvent(M, n_solute=60, n_solvent_mol=NMOL, seed=20250604)
 eng = _engine.Engine(0)
 for name, kw in [("ns60_e", dict(solute_natoms=60, reorder=True)), ("ns60_e_rs", dict(solute_natoms=60, reorder=True, reorder_solvent_only=True)),
                  ("e_only", dict(reorder=True)), ("ns60_noreorder_pairpath", None)]:
