@@ -154,8 +154,13 @@ __device__ int lsap_warp_reg(int n, const double* Qe, const double* Pe, double* 
                 a = a_row[row];
                 ok = a >= 0 && r4c[a] < 0 && !moved[a];
             }
-            const unsigned same = __match_any_sync(0xffffffffu, a);
-            ok = ok && (__ffs(same) - 1 == lane);
+            // "no earlier row of the batch wants the same column": the lowest row claims the column in shared memory
+            // (pred[] is scratch between two searches).  MATCH.ANY did the same in ~300 cycles, 3.4 % of the kernel.
+            if (a >= 0) pred[a] = 0x7fffffff;
+            __syncwarp();
+            if (a >= 0) atomicMin(&pred[a], row);
+            __syncwarp();
+            ok = ok && pred[a] == row;
             const unsigned fail = ~__ballot_sync(0xffffffffu, ok);
             const int run = fail ? __ffs(fail) - 1 : 32;
             if (lane < run) { r4c[a] = row; c4r[row] = a; u[row] = m_row[row]; }
@@ -215,10 +220,10 @@ __device__ int lsap_warp_reg(int n, const double* Qe, const double* Pe, double* 
                     if (fast) {
                         const double delta = mu - m_cur;                     // minVal - sh[a]
                         if (delta != 0.0) {
-                            if ((a & 31) == lane) {
+                            // branch-free: an `if ((a >> 5) == c)` inside the owner lane turns v[] into a local-memory array
+                            // behind a jump table (LDL / STL: 8 % of the kernel's stall samples)
 #pragma unroll
-                                for (int c = 0; c < C; ++c) if ((a >> 5) == c) v[c] -= delta;
-                            }
+                            for (int c = 0; c < C; ++c) v[c] -= (a == lane + 32 * c) ? delta : 0.0;
                             if (lane == 0) { moved[a] = 1; u[i1] += delta; }
                         }
                         if (lane == 0) {
@@ -482,7 +487,8 @@ __device__ __noinline__ int reorder_phase(const PairPlan& pl, int phase, double*
         const int o0 = pl.block_off[phase][b], n = pl.block_off[phase][b + 1] - o0;
         if (n < 2) continue;
         const int* idx = pl.idx[phase] + o0;
-        for (int t = lane; t < n; t += 32) {
+#pragma unroll 4
+        for (int t = lane; t < n; t += 32) {   // (unrolled: index -> coordinate is a chain of two dependent global loads)
             const int k = idx[t];
             Qe[3 * t] = Q[3 * k]; Qe[3 * t + 1] = Q[3 * k + 1]; Qe[3 * t + 2] = Q[3 * k + 2];
             Pe[3 * t] = W[3 * k]; Pe[3 * t + 1] = W[3 * k + 1]; Pe[3 * t + 2] = W[3 * k + 2];
