@@ -1,7 +1,8 @@
 """Turn the scratch ncu output under gpurun_out/ into the tracked summaries under profiles/.
 
     python tools/make_profiles.py <round-tag> <gram .ncu-rep> [<pair .ncu-rep>|-] [<launch list csv>|-] [<label>]
-    python tools/make_profiles.py <round-tag> --only <.ncu-rep> <name>      (just the summary of one capture)
+    python tools/make_profiles.py <round-tag> --only <.ncu-rep> <name> [pairs per launch]   (just the summary of one capture;
+                                                                                              with the pair count also <name>_traffic.json)
 
 <label> (default "gram") names the Gram kernel the capture is of: "gram" = FP64 DMMA kernel, "gram_i8" = int8 tcgen05 kernel.
 """
@@ -59,7 +60,17 @@ def summarise(rep, name):
 
 
 if sys.argv[2] == "--only":
-    summarise(sys.argv[3], sys.argv[4])
+    ms1 = summarise(sys.argv[3], sys.argv[4])
+    if len(sys.argv) > 5:   # pairs per launch of the capture: also write <name>_traffic.json with DRAM bytes per pair
+        pairs = int(sys.argv[5])
+        m1 = ms1[-1]
+        rd, wr = to_bytes(*m1["dram__bytes_read.sum"]), to_bytes(*m1["dram__bytes_write.sum"])
+        json.dump({"kernel": m1["Kernel Name"][0], "workload": f"one launch = {pairs} pairs", "dram_bytes_read": rd, "dram_bytes_write": wr,
+                   "dram_bytes_per_launch": rd + wr, "pairs_per_launch": pairs, "per_pair": (rd + wr) / pairs,
+                   "note": "per_pair scales the capture to other frame counts of the same kernel shape: the 8 B per pair written dominate, "
+                           "the operand reads (proportional to the frame count, not the pair count) are the small remainder",
+                   "duration_ms_under_ncu": float(m1["gpu__time_duration.sum"][0]), "source": os.path.basename(sys.argv[3])},
+                  open(os.path.join(out_dir, f"{tag}_{sys.argv[4]}_traffic.json"), "w"), indent=1)
     sys.exit(0)
 ms = summarise(sys.argv[2], label)
 m = ms[-1]
