@@ -289,6 +289,23 @@ class Job:
             self.dist.destroy_process_group()
 
 
+def ncu_pipe_busy(summary_path):
+    """tensor / FP64 / shared pipe busy fractions from a committed tools/make_profiles.py summary (None if absent)."""
+    want = {"sm__pipe_shared_cycles_active.avg.pct_of_peak_sustained_elapsed": "busy",
+            "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed": "tensor",
+            "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed": "fp64"}
+    got = {}
+    try:
+        with open(summary_path) as fh:
+            for line in fh:
+                parts = line.split()
+                if len(parts) >= 2 and parts[0] in want and want[parts[0]] not in got:
+                    got[want[parts[0]]] = float(parts[1]) / 100.0
+    except (OSError, ValueError):
+        return None
+    return got if len(got) == 3 else None
+
+
 def roofline_of(name, kw, M, K, r0, r1, my_pairs, mean_gram_ms, st):
     """Roofline of the dominant kernel of one launch (this rank's slab).  Pure-Kabsch workloads: the algorithmic work is
     18 K FP64 flop per pair; on the int8 tensor pipe the same contraction is 15 exact digit GEMMs, i.e.
@@ -346,6 +363,16 @@ def roofline_of(name, kw, M, K, r0, r1, my_pairs, mean_gram_ms, st):
                        "forces (atoms to 32, 40-frame row tiles in 128 lanes, diagonal blocks); `fp64_equiv` is the same launch "
                        "counted as 18 K FP64 flop per pair against the FP64 DMMA peak (not bounded by 1: another pipe does "
                        "the work).  The kernel is bound by its FP64 recombination + 3x3 solve epilogue, see profiles/"}
+        # what the kernel is bound by: on B200 the int8 tcgen05 MMAs and the FP64 unit are one pipe (profiles/r02_shared_pipe_probe.json),
+        # so its busy fraction = tensor + FP64 (recombination and 3x3 solve) -- from the committed ncu capture of the same kernel
+        if chunks <= 10:
+            cap = os.path.join(ROOT, "profiles", "r02_gram_i8_ncu_summary.txt" if chunks <= 4 else "r02_gram_i8_k300_ncu_summary.txt")
+            busy = ncu_pipe_busy(cap)
+            if busy:
+                out["shared_pipe"] = dict(busy, source=os.path.relpath(cap, ROOT),
+                                          note="static: ncu --set full capture of this kernel "
+                                               + ("on cfg2" if chunks <= 4 else "on 16000 frames x 300 atoms (the same kernel at this run's atom count differs in the MMA share)")
+                                               + "; busy = sm__pipe_shared_cycles_active = tensor + fp64: the FP64 unit and the int8 MMAs exclude each other")
         traffic_file = os.path.join(ROOT, "profiles", "r02_gram_i8_traffic.json" if chunks <= 4 else "r02_gram_i8_k300_traffic.json")
         if not os.path.exists(traffic_file):
             traffic_file = traffic_file.replace("r02_", "r01_")
