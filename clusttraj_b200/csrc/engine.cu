@@ -463,6 +463,12 @@ static int finish_stats(ct_engine* e, int64_t pairs, int64_t launches) {
     e->stats.launches = launches;
     e->stats.flagged = (int64_t)c[0];
     e->stats.lsap_steps = (int64_t)c[1];
+    if (e->use_i8) {
+        // the int8 Gram launches mark their B operand L2-persisting (csrc/ozaki.cu launch_ts); the stream is idle here, so
+        // hand the set-aside lines back before the consumers (clustering, matrix reductions) run
+        cudaCtxResetPersistingL2Cache();
+        cudaGetLastError();
+    }
     return CT_OK;
 }
 
