@@ -406,6 +406,7 @@ __device__ __noinline__ double kabsch_rotation_shared(const double* s, double* U
 
 // rotate the working frame in place: W[k] = W[k] * U (row vector times matrix)
 __device__ __noinline__ void warp_rotate(double* W, int K, const double* U, int lane) {
+#pragma unroll 1
     for (int k = lane; k < K; k += 32) {
         const double x = W[3 * k], y = W[3 * k + 1], z = W[3 * k + 2];
         W[3 * k] = fma(x, U[0], fma(y, U[3], z * U[6]));
@@ -418,6 +419,7 @@ __device__ __noinline__ void warp_rotate(double* W, int K, const double* U, int 
 __device__ __noinline__ void warp_cov(const double* P, const double* Q, int k1, int lane, double* s) {
 #pragma unroll
     for (int t = 0; t < 9; ++t) s[t] = 0.0;
+#pragma unroll 1
     for (int k = lane; k < k1; k += 32) {
         const double px = P[3 * k], py = P[3 * k + 1], pz = P[3 * k + 2];
         const double qx = Q[3 * k], qy = Q[3 * k + 1], qz = Q[3 * k + 2];
@@ -487,8 +489,8 @@ __device__ __noinline__ int reorder_phase(const PairPlan& pl, int phase, double*
         const int o0 = pl.block_off[phase][b], n = pl.block_off[phase][b + 1] - o0;
         if (n < 2) continue;
         const int* idx = pl.idx[phase] + o0;
-#pragma unroll 4
-        for (int t = lane; t < n; t += 32) {   // (unrolled: index -> coordinate is a chain of two dependent global loads)
+#pragma unroll 1
+        for (int t = lane; t < n; t += 32) {   // ( index -> coordinate is a chain of two dependent global loads)
             const int k = idx[t];
             Qe[3 * t] = Q[3 * k]; Qe[3 * t + 1] = Q[3 * k + 1]; Qe[3 * t + 2] = Q[3 * k + 2];
             Pe[3 * t] = W[3 * k]; Pe[3 * t + 1] = W[3 * k + 1]; Pe[3 * t + 2] = W[3 * k + 2];
@@ -502,8 +504,7 @@ __device__ __noinline__ int reorder_phase(const PairPlan& pl, int phase, double*
         } else
         switch ((n + 31) >> 5) {
             // three register-resident instances (2, 4, 8 columns per lane) rather than one per block size: code size
-            case 1: case 2: st = lsap_reg_dispatch<2>(pl.credit0, n, Qe, Pe, u, pred, r4c, c4r, v, reinterpret_cast<int*>(sh), scanned, lane); break;
-            case 3: case 4: st = lsap_reg_dispatch<4>(pl.credit0, n, Qe, Pe, u, pred, r4c, c4r, v, reinterpret_cast<int*>(sh), scanned, lane); break;
+            case 1: case 2: case 3: case 4: st = lsap_reg_dispatch<4>(pl.credit0, n, Qe, Pe, u, pred, r4c, c4r, v, reinterpret_cast<int*>(sh), scanned, lane); break;
             case 5: case 6: case 7: case 8:
                 st = lsap_reg_dispatch<8>(pl.credit0, n, Qe, Pe, u, pred, r4c, c4r, v, reinterpret_cast<int*>(sh), scanned, lane); break;
             default: st = lsap_warp(n, Qe, Pe, u, v, sh, pred, r4c, c4r, scanned, lane); break;
@@ -511,6 +512,7 @@ __device__ __noinline__ int reorder_phase(const PairPlan& pl, int phase, double*
         steps += st < 0 ? -st : st;
         if (st >= 0) {
             // rmsd.reorder_hungarian: the atom matched to reference row t moves to position idx[t]
+#pragma unroll 1
             for (int t = lane; t < n; t += 32) {
                 const int c = c4r[t], k = idx[t];
                 W[3 * k] = Pe[3 * c]; W[3 * k + 1] = Pe[3 * c + 1]; W[3 * k + 2] = Pe[3 * c + 2];
@@ -540,6 +542,7 @@ __device__ double pair_value_warp(const PairPlan& pl, const double* __restrict__
         for (int k = lane; k < ns; k += 32) { qc0 += Qg[3 * k]; qc1 += Qg[3 * k + 1]; qc2 += Qg[3 * k + 2]; }
         qc0 = warp_sum(qc0) / ns; qc1 = warp_sum(qc1) / ns; qc2 = warp_sum(qc2) / ns;
     }
+#pragma unroll 1
     for (int k = lane; k < K; k += 32) {
         W[3 * k] = Pg[3 * k] - qc0; W[3 * k + 1] = Pg[3 * k + 1] - qc1; W[3 * k + 2] = Pg[3 * k + 2] - qc2;
         perm[k] = k;
@@ -565,6 +568,7 @@ __device__ double pair_value_warp(const PairPlan& pl, const double* __restrict__
     // final value (distmat.py:259-275)
     if (pl.final_direct) {
         double res = 0.0;
+#pragma unroll 1
         for (int k = lane; k < K; k += 32) {
             const double dx = W[3 * k] - Qg[3 * k], dy = W[3 * k + 1] - Qg[3 * k + 1], dz = W[3 * k + 2] - Qg[3 * k + 2];
             const double d2 = dx * dx + dy * dy + dz * dz;
