@@ -489,12 +489,20 @@ __device__ __noinline__ int reorder_phase(const PairPlan& pl, int phase, double*
         const int o0 = pl.block_off[phase][b], n = pl.block_off[phase][b + 1] - o0;
         if (n < 2) continue;
         const int* idx = pl.idx[phase] + o0;
+        // index -> coordinate is a chain of two dependent global loads: two atoms per lane in flight, stores afterwards
 #pragma unroll 1
-        for (int t = lane; t < n; t += 32) {   // ( index -> coordinate is a chain of two dependent global loads)
-            const int k = idx[t];
-            Qe[3 * t] = Q[3 * k]; Qe[3 * t + 1] = Q[3 * k + 1]; Qe[3 * t + 2] = Q[3 * k + 2];
-            Pe[3 * t] = W[3 * k]; Pe[3 * t + 1] = W[3 * k + 1]; Pe[3 * t + 2] = W[3 * k + 2];
-            oldp[t] = perm[k];
+        for (int t0 = lane; t0 < n; t0 += 64) {
+            const int t1 = t0 + 32 < n ? t0 + 32 : t0;
+            const int k0 = idx[t0], k1 = idx[t1];
+            const double qa = Q[3 * k0], qb = Q[3 * k0 + 1], qc = Q[3 * k0 + 2], qd = Q[3 * k1], qe = Q[3 * k1 + 1], qf = Q[3 * k1 + 2];
+            const double pa = W[3 * k0], pb = W[3 * k0 + 1], pc = W[3 * k0 + 2], pd = W[3 * k1], pe = W[3 * k1 + 1], pf = W[3 * k1 + 2];
+            const int o0p = perm[k0], o1p = perm[k1];
+            Qe[3 * t0] = qa; Qe[3 * t0 + 1] = qb; Qe[3 * t0 + 2] = qc;
+            Pe[3 * t0] = pa; Pe[3 * t0 + 1] = pb; Pe[3 * t0 + 2] = pc;
+            oldp[t0] = o0p;
+            Qe[3 * t1] = qd; Qe[3 * t1 + 1] = qe; Qe[3 * t1 + 2] = qf;
+            Pe[3 * t1] = pd; Pe[3 * t1 + 1] = pe; Pe[3 * t1 + 2] = pf;
+            oldp[t1] = o1p;
         }
         __syncwarp();
         int st;
