@@ -140,34 +140,44 @@ __device__ int lsap_warp_reg(int n, const double* Qe, const double* Pe, double* 
     for (int c = 0; c < C; ++c) if (lane + 32 * c < n) valid |= 1u << c;
     int steps = 0;   // frontier scans + direct assignments (each stands for the first scan of its row)
     int cur = 0;
+    int b_base = 0, b_a = -1;       // the current batch of direct assignments: first row, this lane's nearest column,
+    bool b_ok = false, b_valid = false;   // whether this lane's row may take it, whether the evaluation still holds
     // credit: two-row collision shortcut: +1 per success (up to 8), -2 per miss, not attempted at <= 0
 #pragma unroll 1
     while (cur < n) {
         // direct assignments, 32 consecutive rows at a time: a row takes its nearest column when that column is
         // unmatched, its dual has not moved and no earlier row of the batch wants it too; the rows before the first
-        // failing one are committed together, the failing one goes through the scans below
+        // failing one are committed together, the failing one goes through the shortcut or the scans below.
+        // The evaluation of a batch (b_base, b_a, b_ok) stays valid across collision shortcuts: a shortcut matches exactly
+        // one new column jw and moves no dual of an unmatched column, so the rows after the failing one only have to drop
+        // out if they wanted jw; after a frontier search the batch is evaluated afresh.
         {
-            const int row = cur + lane;
-            int a = -1;
-            bool ok = false;
-            if (row < n) {
-                a = a_row[row];
-                ok = a >= 0 && r4c[a] < 0 && !moved[a];
+            if (!b_valid) {
+                b_base = cur;
+                const int row = b_base + lane;
+                b_a = -1;
+                b_ok = false;
+                if (row < n) {
+                    b_a = a_row[row];
+                    b_ok = b_a >= 0 && r4c[b_a] < 0 && !moved[b_a];
+                }
+                // "no earlier row of the batch wants the same column": the lowest row claims the column in shared memory
+                // (pred[] is scratch between two searches).  MATCH.ANY did the same in ~300 cycles, 3.4 % of the kernel.
+                if (b_a >= 0) pred[b_a] = 0x7fffffff;
+                __syncwarp();
+                if (b_a >= 0) atomicMin(&pred[b_a], row);
+                __syncwarp();
+                b_ok = b_ok && pred[b_a] == row;
+                b_valid = SHORTCUT;
             }
-            // "no earlier row of the batch wants the same column": the lowest row claims the column in shared memory
-            // (pred[] is scratch between two searches).  MATCH.ANY did the same in ~300 cycles, 3.4 % of the kernel.
-            if (a >= 0) pred[a] = 0x7fffffff;
+            const int off = cur - b_base;   // rows of the batch already dealt with (< 32)
+            const unsigned fail = ~__ballot_sync(0xffffffffu, b_ok) & (0xffffffffu << off);
+            const int first = fail ? __ffs(fail) - 1 : 32;
+            if (lane >= off && lane < first) { r4c[b_a] = b_base + lane; c4r[b_base + lane] = b_a; u[b_base + lane] = m_row[b_base + lane]; }
             __syncwarp();
-            if (a >= 0) atomicMin(&pred[a], row);
-            __syncwarp();
-            ok = ok && pred[a] == row;
-            const unsigned fail = ~__ballot_sync(0xffffffffu, ok);
-            const int run = fail ? __ffs(fail) - 1 : 32;
-            if (lane < run) { r4c[a] = row; c4r[row] = a; u[row] = m_row[row]; }
-            __syncwarp();
-            steps += run;
-            cur += run;
-            if (run == 32 || cur >= n) continue;
+            steps += first - off;
+            cur = b_base + first;
+            if (first == 32 || cur >= n) { b_valid = false; continue; }
         }
         // Two-row collision, resolved without frontier scans.  Row `cur` lost its nearest column a to an earlier row i1 and a's
         // dual has not moved.  The scans would then go: scan 1 (from cur) pops a at m_cur; scan 2 (from i1, offset
@@ -235,6 +245,8 @@ __device__ int lsap_warp_reg(int n, const double* Qe, const double* Pe, double* 
                         steps += 2;
                         ++cur;
                         credit = credit < 8 ? credit + 1 : 8;
+                        if (b_a == jw) b_ok = false;                  // the one column that is no longer free
+                        if (cur - b_base >= 32) b_valid = false;
                         continue;
                     }
                 }
@@ -312,6 +324,7 @@ __device__ int lsap_warp_reg(int n, const double* Qe, const double* Pe, double* 
         }
         __syncwarp();
         ++cur;
+        b_valid = false;   // duals and matches of many columns may have changed
     }
     return steps;
 }
