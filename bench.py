@@ -291,9 +291,13 @@ class Job:
 
 def ncu_pipe_busy(summary_path):
     """tensor / FP64 / shared pipe busy fractions from a committed tools/make_profiles.py summary (None if absent)."""
-    want = {"sm__pipe_shared_cycles_active.avg.pct_of_peak_sustained_elapsed": "busy",
-            "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed": "tensor",
-            "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed": "fp64"}
+    return ncu_metrics(summary_path, {"sm__pipe_shared_cycles_active.avg.pct_of_peak_sustained_elapsed": "busy",
+                                      "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed": "tensor",
+                                      "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed": "fp64"})
+
+
+def ncu_metrics(summary_path, want):
+    """{short name: fraction} for the percentage metrics `want` names, from a tools/make_profiles.py summary."""
     got = {}
     try:
         with open(summary_path) as fh:
@@ -303,7 +307,7 @@ def ncu_pipe_busy(summary_path):
                     got[want[parts[0]]] = float(parts[1]) / 100.0
     except (OSError, ValueError):
         return None
-    return got if len(got) == 3 else None
+    return got if len(got) == len(want) else None
 
 
 def roofline_of(name, kw, M, K, r0, r1, my_pairs, mean_gram_ms, st):
@@ -316,12 +320,20 @@ def roofline_of(name, kw, M, K, r0, r1, my_pairs, mean_gram_ms, st):
         # per-pair kernel: HBM traffic 2 frames in + 8 B out per pair, latency bound
         bytes_per_launch = my_pairs * (2 * K * 24 + 8)
         achieved = bytes_per_launch / (mean_gram_ms * 1e-3) / 1e9
-        return {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "kernel": "pair_kernel",
-                "bytes_per_pair": 2 * K * 24 + 8, "pairs_per_launch": my_pairs, "launch_ms": mean_gram_ms,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if os.path.exists(PEAKS_FILE) else "fallback 6650 GB/s",
-                "note": "latency / issue bound assignment solver (one warp per pair, costs recomputed per scan); the HBM "
-                        "figure is reported because SURVEY 8d asks for it, see profiles/ for the pipe utilisation"}
+        out = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+               "frac": achieved / peaks["hbm_gbs"], "traffic": None, "kernel": "pair_kernel",
+               "bytes_per_pair": 2 * K * 24 + 8, "pairs_per_launch": my_pairs, "launch_ms": mean_gram_ms,
+               "peak_source": "MEASURED_PEAKS.json hbm_gbs" if os.path.exists(PEAKS_FILE) else "fallback 6650 GB/s",
+               "note": "latency / issue bound assignment solver (one warp per pair, costs recomputed per scan); the HBM "
+                       "figure is reported because SURVEY 8d asks for it; what the kernel is bound by is in `pipes`"}
+        cap = os.path.join(ROOT, "profiles", "r02_pair_ncu_summary.txt")
+        pipes = ncu_metrics(cap, {"sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed": "fp64_busy",
+                                  "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_active",
+                                  "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_active"})
+        if pipes:
+            out["pipes"] = dict(pipes, source=os.path.relpath(cap, ROOT),
+                                note="static: ncu --set full capture of pair_kernel on a 300-frame sample of the cfg4 shape")
+        return out
     fp64 = load_json(FP64_PEAK_FILE, None)
     fp64_peak = float(fp64["dmma884_sustained_tflops"]) if fp64 else 37.1
     fp64_src = ("measured DMMA m8n8k4 microbenchmark on this pool (profiles/r01_fp64_peak_microbench.json); "
