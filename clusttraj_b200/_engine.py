@@ -43,7 +43,7 @@ EXPORTS = [
     "ct_version", "ct_device_count", "ct_last_error", "ct_engine_create", "ct_engine_destroy", "ct_host_alloc",
     "ct_host_free", "ct_load_frames", "ct_rows_pairs", "ct_rmsd_rows", "ct_rmsd_rows_device", "ct_copy_slab",
     "ct_rmsd_condensed", "ct_pair_values", "ct_get_stats", "ct_pack_resident", "ct_matrix_consumers",
-    "ct_pair_transforms", "ct_linkage", "ct_matrix_reserve", "ct_rmsd_rows_gather", "ct_matrix_commit", "ct_read_xyz", "ct_read_pdb", "ct_read_gro", "ct_format_xyz", "ct_buffer_free", "ct_device_memory",
+    "ct_pair_transforms", "ct_linkage", "ct_matrix_reserve", "ct_rmsd_rows_gather", "ct_matrix_commit", "ct_read_xyz", "ct_read_pdb", "ct_read_gro", "ct_format_xyz", "ct_buffer_free", "ct_device_memory", "ct_set_frame_elements",
 ]
 
 _lib = None
@@ -91,6 +91,7 @@ def load_library(build_if_missing=True):
         lib.ct_rmsd_rows.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, P(ct_stats)]
         lib.ct_rmsd_rows_device.argtypes = [C.c_void_p, C.c_int64, C.c_int64, P(C.c_void_p), P(ct_stats)]
         lib.ct_copy_slab.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
+        lib.ct_set_frame_elements.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32]
         lib.ct_matrix_reserve.argtypes = [C.c_void_p, C.c_int64]
         lib.ct_rmsd_rows_gather.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, P(ct_stats)]
         lib.ct_matrix_commit.argtypes = [C.c_void_p, C.c_int64]
@@ -211,7 +212,9 @@ class Engine:
         if rc != 0:
             raise EngineError(f"{what} failed ({rc}): " + (self._lib.ct_last_error(self._h) or b"").decode())
 
-    def load_frames(self, coords, atomic_nums, opts):
+    def load_frames(self, coords, atomic_nums, opts, frame_elements=None):
+        """coords [M, N, 3], atomic_nums [N] (frame 0's when `frame_elements` [M, N] gives every frame its own list:
+        ct_set_frame_elements; those frames must come already masked, with no_hydrogen off)."""
         coords = np.ascontiguousarray(coords, dtype=np.float64)
         if coords.ndim != 3 or coords.shape[2] != 3:
             raise ValueError("coords must be [M, N, 3]")
@@ -222,6 +225,11 @@ class Engine:
                                              coords.shape[1], C.byref(opts)), "ct_load_frames")
         self.M, self.N = coords.shape[0], coords.shape[1]
         self.K = int(self.stats()["kept_atoms"])
+        if frame_elements is not None:
+            fz = np.ascontiguousarray(frame_elements, dtype=np.int32)
+            if fz.shape != (self.M, self.K):
+                raise ValueError("frame_elements must be [M, K] (kept atoms of every frame)")
+            self._check(self._lib.ct_set_frame_elements(self._h, fz.ctypes.data, self.M, self.K), "ct_set_frame_elements")
 
     def pack_resident(self):
         """Re-run K1 (centre + pack) on the coordinates already on the GPU; returns its device time in ms."""

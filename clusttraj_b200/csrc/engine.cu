@@ -41,6 +41,7 @@ struct PairPlan;
 struct PairPlanHost;
 int pair_plan_build(PairPlanHost** out, const int32_t* kept_z, int K, int natoms, const ct_opts* o, std::string& err);
 void pair_plan_free(PairPlanHost* p);
+int pair_plan_frame_elements(PairPlanHost* h, const int32_t* z, int M, int K, std::string& err);
 cudaError_t launch_pairs_rows(const PairPlanHost* plan, const double* centred, int M, int K, int row_begin, int row_end,
                               double* out, long long idx_base, unsigned long long* counters, int sm_count,
                               cudaStream_t stream);
@@ -58,6 +59,7 @@ struct ct_engine {
     int64_t M = 0;
     int N = 0, K = 0, natoms = 0, m_pad = 0, kq_total = 0;
     bool loaded = false;
+    bool per_frame_elements = false;   // ct_set_frame_elements replaced the plan's index lists (reset by ct_load_frames)
     bool use_gram = false;  // pure Kabsch modes go through the DMMA Gram kernel
     ct_opts opts{};
     std::vector<int32_t> excl;
@@ -299,6 +301,7 @@ int ct_load_frames(ct_engine* e, const double* coords, const int32_t* atomic_num
         return fail(e, CT_ERR_ARG, "ct_load_frames: solute_natoms out of range");
     CT_CUDA(e, cudaSetDevice(e->device));
     e->loaded = false;
+    e->per_frame_elements = false;
     e->opts = *opts;
     e->excl.assign(opts->reorder_excl, opts->reorder_excl + opts->n_excl);
     e->opts.reorder_excl = e->excl.data();
@@ -739,6 +742,23 @@ static int pair_values_impl(ct_engine* e, const int64_t* pairs, int64_t n_pairs,
     return CT_OK;
 }
 
+int ct_set_frame_elements(ct_engine* e, const int32_t* elements, int64_t M, int32_t K) {
+    if (!e) return fail(nullptr, CT_ERR_ARG, "engine is NULL");
+    if (!e->loaded) return fail(e, CT_ERR_STATE, "ct_set_frame_elements: load frames first");
+    if (!elements || M != e->M || K != e->K)
+        return fail(e, CT_ERR_ARG, "ct_set_frame_elements: elements must be [M][K] for the loaded frames (K = kept atoms)");
+    if (!e->plan || e->opts.reorder_mode == 0) return CT_OK;   // the elements only matter to a reorder
+    if (e->opts.no_hydrogen)
+        return fail(e, CT_ERR_UNSUPPORTED, "ct_set_frame_elements: apply the per-frame hydrogen masks on the host and load the "
+                                           "compacted frames with no_hydrogen = 0 (clusttraj_b200.distmat.frame_invariant_view)");
+    CT_CUDA(e, cudaSetDevice(e->device));
+    std::string perr;
+    const int rc = ct::pair_plan_frame_elements(e->plan, elements, (int)M, (int)K, perr);
+    if (rc) return fail(e, rc, perr.c_str());
+    e->per_frame_elements = true;
+    return CT_OK;
+}
+
 int ct_pair_values(ct_engine* e, const int64_t* pairs, int64_t n_pairs, double* values, int32_t* perms, ct_stats* stats) {
     return pair_values_impl(e, pairs, n_pairs, values, perms, nullptr, true, stats, "ct_pair_values");
 }
@@ -746,6 +766,8 @@ int ct_pair_values(ct_engine* e, const int64_t* pairs, int64_t n_pairs, double* 
 int ct_pair_transforms(ct_engine* e, const int64_t* pairs, int64_t n_pairs, double* values, double* transforms,
                        ct_stats* stats) {
     if (n_pairs > 0 && !transforms) return fail(e, CT_ERR_ARG, "ct_pair_transforms: transforms is NULL");
+    if (e && e->per_frame_elements)
+        return fail(e, CT_ERR_UNSUPPORTED, "ct_pair_transforms: not available for trajectories with per-frame element lists");
     return pair_values_impl(e, pairs, n_pairs, values, nullptr, transforms, false, stats, "ct_pair_transforms");
 }
 

@@ -33,12 +33,17 @@ struct PairPlan {
     int nblocks[2];
     const int* block_off[2];  // [nblocks+1] offsets into idx
     const int* idx[2];        // kept-atom positions, ascending inside a block
+    long long idx_stride[2];  // 0: the same index lists for every frame; > 0: one list per frame (per-frame element lists,
+                              // distmat.py:131-141: the reference builds the element blocks from each frame's own atoms)
     int nmax;                 // largest block
     int credit0;              // initial credit of the two-row collision shortcut (0 switches it off)
 };
 
 struct PairPlanHost {
     PairPlan plan{};
+    std::vector<int> view[2], off[2];   // host copies: the atoms each phase reorders (ascending) and the block boundaries
+    std::vector<int> block_z[2];        // element of every block
+    int* d_frame_idx = nullptr;   // per-frame index lists (pair_plan_frame_elements)
     int* d_ints = nullptr;        // all index arrays in one allocation
     double* d_work = nullptr;     // per-resident-warp working copy of the moving frame [K][3]
     int* d_perm = nullptr;        // per-resident-warp composite permutation [K]
@@ -484,8 +489,37 @@ __device__ void match_by_norm(int n, const double* Qe, const double* Pe, double*
     __syncwarp();
 }
 
+// Per-frame element lists: the moving frame keeps its atoms of element X at other positions than the reference frame.
+// Relabel it first -- its t-th atom of the phase's element-sorted list moves to the position of the reference frame's t-th --
+// through the second half of the warp's working buffers (block by block in place would overwrite atoms that a later block
+// still has to read).  The columns of every block keep their order, so the assignment problems, and with them the reordered
+// frame and the composite permutation, are the reference's; from here on both frames use the reference frame's lists.
+// (Out of line: cold code inside reorder_phase costs the frame-invariant runs instruction-cache space.)
+__device__ __noinline__ void relabel_moving_frame(const PairPlan& pl, int phase, double* W, int* perm, int lane, int frame_q,
+                                                  int frame_p) {
+    const int nv = (int)pl.idx_stride[phase];
+    const int* iq = pl.idx[phase] + (size_t)frame_q * nv;
+    const int* ip = pl.idx[phase] + (size_t)frame_p * nv;
+    double* T = W + 3 * (size_t)pl.K;
+    int* tp = perm + pl.K;
+#pragma unroll 1
+    for (int t = lane; t < nv; t += 32) {
+        const int k = ip[t];
+        T[3 * t] = W[3 * k]; T[3 * t + 1] = W[3 * k + 1]; T[3 * t + 2] = W[3 * k + 2];
+        tp[t] = perm[k];
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int t = lane; t < nv; t += 32) {
+        const int k = iq[t];
+        W[3 * k] = T[3 * t]; W[3 * k + 1] = T[3 * t + 1]; W[3 * k + 2] = T[3 * t + 2];
+        perm[k] = tp[t];
+    }
+    __syncwarp();
+}
+
 __device__ __noinline__ int reorder_phase(const PairPlan& pl, int phase, double* W, int* perm, const double* Q, unsigned char* sm,
-                             int lane) {
+                             int lane, int frame_q, int frame_p) {
     const int nmax = pl.nmax;
     double* Qe = reinterpret_cast<double*>(sm);
     double* Pe = Qe + 3 * nmax;
@@ -498,10 +532,11 @@ __device__ __noinline__ int reorder_phase(const PairPlan& pl, int phase, double*
     int* oldp = c4r + nmax;
     unsigned char* scanned = reinterpret_cast<unsigned char*>(oldp + nmax);
     int steps = 0;
+    if (pl.idx_stride[phase]) relabel_moving_frame(pl, phase, W, perm, lane, frame_q, frame_p);   // per-frame element lists
     for (int b = 0; b < pl.nblocks[phase]; ++b) {
         const int o0 = pl.block_off[phase][b], n = pl.block_off[phase][b + 1] - o0;
         if (n < 2) continue;
-        const int* idx = pl.idx[phase] + o0;
+        const int* idx = pl.idx[phase] + (size_t)frame_q * pl.idx_stride[phase] + o0;   // the reference frame's list
         // index -> coordinate is a chain of two dependent global loads: two atoms per lane in flight, stores afterwards
 #pragma unroll 1
         for (int t0 = lane; t0 < n; t0 += 64) {
@@ -524,7 +559,7 @@ __device__ __noinline__ int reorder_phase(const PairPlan& pl, int phase, double*
             st = 0;
         } else
         switch ((n + 31) >> 5) {
-            // three register-resident instances (2, 4, 8 columns per lane) rather than one per block size: code size
+            // two register-resident instances (4 and 8 columns per lane) rather than one per block size: code size
             case 1: case 2: case 3: case 4: st = lsap_reg_dispatch<4>(pl.credit0, n, Qe, Pe, u, pred, r4c, c4r, v, reinterpret_cast<int*>(sh), scanned, lane); break;
             case 5: case 6: case 7: case 8:
                 st = lsap_reg_dispatch<8>(pl.credit0, n, Qe, Pe, u, pred, r4c, c4r, v, reinterpret_cast<int*>(sh), scanned, lane); break;
@@ -551,7 +586,8 @@ __device__ __noinline__ int reorder_phase(const PairPlan& pl, int phase, double*
 // for the last one, which align_mol only applies for -ns -e --final-kabsch and for -ws --final-kabsch (io.py:733-746).
 template <bool XF>
 __device__ double pair_value_warp(const PairPlan& pl, const double* __restrict__ Pg, const double* __restrict__ Qg,
-                                  double* W, int* perm, unsigned char* sm, int lane, int& steps, double* xf) {
+                                  double* W, int* perm, unsigned char* sm, int lane, int& steps, double* xf, int frame_q,
+                                  int frame_p) {
     const int K = pl.K, ns = pl.natoms;
     double s[9], U[9];
     double Rt[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, Tt[3] = {0, 0, 0};
@@ -577,7 +613,7 @@ __device__ double pair_value_warp(const PairPlan& pl, const double* __restrict__
     // phase 0: solute reorder + second solute rotation (distmat.py:184-223); phase 1: main reorder (:231-256).  One call
     // site in a loop, so that the compiler keeps ONE copy of the solver instead of one clone per constant phase
     for (int phase = pl.solute_phase ? 0 : 1; phase < 2 && pl.do_reorder; ++phase) {
-        steps += reorder_phase(pl, phase, W, perm, Qg, sm, lane);
+        steps += reorder_phase(pl, phase, W, perm, Qg, sm, lane, frame_q, frame_p);
         if (phase == 0) {
             warp_cov(W, Qg, ns, lane, s);
             kabsch_rotation_shared(s, U);
@@ -691,8 +727,9 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) pair_kernel(const PairPlan pl
     const long long gw = (long long)blockIdx.x * PAIR_WARPS + warp;
     const long long nw = (long long)gridDim.x * PAIR_WARPS;
     unsigned char* sm = pair_smem + (size_t)warp * smem_per_warp;
-    double* W = work + (size_t)gw * pl.K * 3;
-    int* perm = perm_work + (size_t)gw * pl.K;
+    const int wmul = (pl.idx_stride[0] | pl.idx_stride[1]) ? 2 : 1;   // per-frame element lists: room to relabel the moving frame
+    double* W = work + (size_t)gw * pl.K * 3 * wmul;
+    int* perm = perm_work + (size_t)gw * pl.K * wmul;
     unsigned long long my_steps = 0;
     for (long long e = gw; e < n_entries; e += nw) {
         int i, j;
@@ -709,7 +746,7 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) pair_kernel(const PairPlan pl
         }
         int steps;
         const double val = pair_value_warp<XF>(pl, centred + (size_t)j * pl.K * 3, centred + (size_t)i * pl.K * 3, W, perm, sm,
-                                               lane, steps, XF ? xf_out + (size_t)e * 12 : nullptr);
+                                               lane, steps, XF ? xf_out + (size_t)e * 12 : nullptr, i, j);
         my_steps += (unsigned long long)steps;
         if (lane == 0) out[e] = val;
         if (perms_out) {
@@ -722,15 +759,18 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) pair_kernel(const PairPlan pl
 }
 
 // ---- host side: build the frame-invariant plan ---------------------------------------------------------
-static void element_blocks(const std::vector<int>& view, const int32_t* kept_z, std::vector<int>& off, std::vector<int>& idx) {
+static void element_blocks(const std::vector<int>& view, const int32_t* kept_z, std::vector<int>& off, std::vector<int>& idx,
+                           std::vector<int>* block_z = nullptr) {
     // np.unique(ref atoms) order = ascending atomic number; positions ascending inside an element
     std::map<int, std::vector<int>> by_z;
     for (int k : view) by_z[kept_z[k]].push_back(k);
     off.assign(1, 0);
     idx.clear();
+    if (block_z) block_z->clear();
     for (auto& kv : by_z) {
         idx.insert(idx.end(), kv.second.begin(), kv.second.end());
         off.push_back((int)idx.size());
+        if (block_z) block_z->push_back(kv.first);
     }
 }
 
@@ -770,13 +810,16 @@ int pair_plan_build(PairPlanHost** out, const int32_t* kept_z, int K, int natoms
     if (p.solute_phase) {
         std::vector<int> view;
         for (int k = 0; k < natoms; ++k) if (!excl[k]) view.push_back(k);
-        element_blocks(view, kept_z, off[0], idx[0]);
+        element_blocks(view, kept_z, off[0], idx[0], &h->block_z[0]);
+        h->view[0] = view;
     }
     if (p.do_reorder) {
         std::vector<int> view;
         for (int k = p.has_ns ? natoms : 0; k < K; ++k) if (!excl[k]) view.push_back(k);
-        element_blocks(view, kept_z, off[1], idx[1]);
+        element_blocks(view, kept_z, off[1], idx[1], &h->block_z[1]);
+        h->view[1] = view;
     }
+    h->off[0] = off[0]; h->off[1] = off[1];
     p.nmax = 1;
     for (int ph = 0; ph < 2; ++ph) {
         p.nblocks[ph] = (int)off[ph].size() - 1;
@@ -807,8 +850,43 @@ int pair_plan_build(PairPlanHost** out, const int32_t* kept_z, int K, int natoms
     return CT_OK;
 }
 
+// Per-frame element lists (distmat.py:131-141: every frame's own atoms decide its element blocks).  z = [M][K] atomic numbers
+// of the kept atoms of every frame.  The blocks of a pair are (reference frame's atoms of element X) x (moving frame's atoms
+// of element X): the same counts in every frame are required (the reference fails on a pair whose counts differ), the
+// positions may differ from frame to frame.  Replaces the plan's index lists by one list per frame.
+int pair_plan_frame_elements(PairPlanHost* h, const int32_t* z, int M, int K, std::string& err) {
+    PairPlan& p = h->plan;
+    if (K != p.K) { err = "frame elements: K does not match the loaded frames"; return CT_ERR_ARG; }
+    const size_t n0 = h->view[0].size(), n1 = h->view[1].size();
+    std::vector<int> all((size_t)M * (n0 + n1));
+    std::vector<int> off, idx, bz;
+    for (int ph = 0; ph < 2; ++ph) {
+        const size_t nv = ph ? n1 : n0, base = ph ? (size_t)M * n0 : 0;
+        if (!nv) continue;
+        for (int f = 0; f < M; ++f) {
+            element_blocks(h->view[ph], z + (size_t)f * K, off, idx, &bz);
+            if (off != h->off[ph] || bz != h->block_z[ph]) {
+                err = "frame " + std::to_string(f) + " does not have the element counts of frame 0 among the atoms to reorder "
+                      "(the reference's per-element assignment needs equal counts in both frames of a pair)";
+                return CT_ERR_ARG;
+            }
+            std::copy(idx.begin(), idx.end(), all.begin() + base + (size_t)f * nv);
+        }
+    }
+    if (h->d_frame_idx) { cudaFree(h->d_frame_idx); h->d_frame_idx = nullptr; }
+    if (cudaMalloc(&h->d_frame_idx, sizeof(int) * std::max<size_t>(all.size(), 1)) != cudaSuccess ||
+        cudaMemcpy(h->d_frame_idx, all.data(), sizeof(int) * all.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+        err = std::string("frame elements upload failed: ") + cudaGetErrorString(cudaGetLastError());
+        return CT_ERR_CUDA;
+    }
+    p.idx[0] = h->d_frame_idx; p.idx_stride[0] = (long long)n0;
+    p.idx[1] = h->d_frame_idx + (size_t)M * n0; p.idx_stride[1] = (long long)n1;
+    return CT_OK;
+}
+
 void pair_plan_free(PairPlanHost* p) {
     if (!p) return;
+    cudaFree(p->d_frame_idx);
     cudaFree(p->d_ints); cudaFree(p->d_work); cudaFree(p->d_perm);
     delete p;
 }
@@ -828,7 +906,7 @@ static cudaError_t launch_pairs(PairPlanHost* h, const double* centred, int M, l
     long long grid = (long long)sm_count * per_sm;
     const long long need = (n_entries + PAIR_WARPS - 1) / PAIR_WARPS;
     if (grid > need) grid = need;
-    const size_t warps = (size_t)grid * PAIR_WARPS;
+    const size_t warps = (size_t)grid * PAIR_WARPS * ((h->plan.idx_stride[0] | h->plan.idx_stride[1]) ? 2 : 1);
     if (warps > h->work_warps) {
         cudaFree(h->d_work); cudaFree(h->d_perm);
         h->d_work = nullptr; h->d_perm = nullptr; h->work_warps = 0;

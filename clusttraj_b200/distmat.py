@@ -61,22 +61,24 @@ def _load_trajectory(trajfile):
 
 
 def frame_invariant_view(atoms, coords, noh, reorder, nsatoms):
-    """Per-frame element lists (the reference reads every frame's own atoms, distmat.py:131-141) brought to the
-    frame-invariant form the engine packs: returns (atoms int32[K], coords, noh, nsatoms) to compute with.
+    """Per-frame element lists (the reference reads every frame's own atoms, distmat.py:131-141) brought to the form the
+    engine takes: returns (atoms int32[K], coords, noh, nsatoms, frame_elements) to compute with; ``frame_elements`` is
+    None or int32[M, K] for ``Engine.load_frames(..., frame_elements=...)``.
 
     The reference uses a frame's elements for two things only: the ``-n`` mask (P[p_atoms != 1], Q[q_atoms != 1]; what is
-    left is paired by POSITION) and the element blocks of a reorder.  So frames whose lists differ are handled here by
-    applying each frame's own hydrogen mask on the host and handing the engine the compacted frames with the mask off,
-    provided the kept atoms can be described once for all frames:
-      * every frame keeps the same number of atoms (the reference's Kabsch needs equal shapes too: ValueError);
-      * with ``-ns -n`` the number of kept solute atoms is the same in every frame (the reference takes it from the row
-        frame, :116-118);
-      * with a reorder the kept elements are the same sequence in every frame (element blocks are per frame in the
-        reference; differing sequences are refused loudly rather than approximated).
+    left is paired by POSITION) and the element blocks of a reorder.  Frames whose lists differ are handled by applying each
+    frame's own hydrogen mask here, on the host, and handing the engine the compacted frames with the mask off; a reorder
+    then gets every frame's own (kept) element list (``ct_set_frame_elements``: one set of block index lists per frame).
+    Refused loudly, because the reference has no defined result or the engine no description for it:
+      * frames that keep different numbers of atoms (the reference's Kabsch needs equal shapes too: ValueError);
+      * with ``-ns -n`` a number of kept solute atoms that changes from frame to frame (the reference takes it from the
+        row frame of each pair, :116-118);
+      * a reorder over frames whose element COUNTS differ among the atoms it reorders (refused by the engine: the
+        reference's per-element assignment fails on such a pair).
     """
     atoms = np.asarray(atoms)
     if atoms.ndim == 1 or not (atoms != atoms[0]).any():
-        return np.ascontiguousarray(atoms if atoms.ndim == 1 else atoms[0], dtype=np.int32), coords, noh, nsatoms
+        return np.ascontiguousarray(atoms if atoms.ndim == 1 else atoms[0], dtype=np.int32), coords, noh, nsatoms, None
     keep = (atoms != 1) if noh else np.ones(atoms.shape, dtype=bool)
     counts = keep.sum(axis=1)
     if (counts != counts[0]).any():
@@ -90,12 +92,10 @@ def frame_invariant_view(atoms, coords, noh, reorder, nsatoms):
                                       "frame (the reference takes it from the row frame of each pair)")
         nsatoms = int(nat[0])
     K = int(counts[0])
-    kept = atoms[keep].reshape(len(atoms), K)
-    if reorder_mode_of(reorder) != 0 and (kept != kept[0]).any():
-        raise NotImplementedError("clusttraj_b200: a reorder needs the same sequence of (kept) elements in every frame; the "
-                                  "reference builds the element blocks per frame, the B200 engine once per trajectory")
+    kept = np.ascontiguousarray(atoms[keep].reshape(len(atoms), K), dtype=np.int32)
+    frame_elements = kept if (reorder_mode_of(reorder) != 0 and (kept != kept[0]).any()) else None
     coords = np.ascontiguousarray(np.asarray(coords, dtype=np.float64)[keep].reshape(len(atoms), K, 3))
-    return np.ascontiguousarray(kept[0], dtype=np.int32), coords, False, nsatoms
+    return np.ascontiguousarray(kept[0], dtype=np.int32), coords, False, nsatoms, frame_elements
 
 
 def _opts_from(noh, reorder, reorder_solvent_only, nsatoms, weight_solute, reorderexcl, final_kabsch):
@@ -126,7 +126,7 @@ def slab_bounds(M, parts):
     return cuts
 
 
-def condensed_matrix(atomic_nums, coords, opts, devices=None, out=None, return_stats=False):
+def condensed_matrix(atomic_nums, coords, opts, devices=None, out=None, return_stats=False, frame_elements=None):
     """All-pairs matrix of in-memory frames on one or several GPUs (one engine + one host thread per
     GPU, no collective: every GPU owns a contiguous slab of the condensed vector)."""
     coords = np.ascontiguousarray(coords, dtype=np.float64)
@@ -144,7 +144,7 @@ def condensed_matrix(atomic_nums, coords, opts, devices=None, out=None, return_s
         # that would not leave room for the clustering's working copy are streamed in chunks instead (below).
         eng = _engine_for(devices[0])
         if 8 * total * 4 < eng.free_memory():
-            eng.load_frames(coords, atomic_nums, opts)
+            eng.load_frames(coords, atomic_nums, opts, frame_elements)
             _, n, st = eng.rmsd_rows_device(0, M)
             out = eng.copy_slab(0, n)
             eng._note_resident(out)
@@ -171,7 +171,7 @@ def condensed_matrix(atomic_nums, coords, opts, devices=None, out=None, return_s
     def work(k):
         try:
             eng = _engine_for(devices[k])
-            eng.load_frames(coords, atomic_nums, opts)
+            eng.load_frames(coords, atomic_nums, opts, frame_elements)
             lo = cuts[k] * M - cuts[k] * (cuts[k] + 1) // 2
             n = eng.rows_pairs(cuts[k], cuts[k + 1])
             if root is not None:
@@ -236,11 +236,11 @@ def get_distmat_saving_in_background(clust_opt):
 def build_distance_matrix(clust_opt):
     """Whole condensed matrix for the options in ``clust_opt`` (distmat.py:44-78)."""
     atoms, coords = _load_trajectory(clust_opt.trajfile)
-    atoms, coords, noh, nsatoms = frame_invariant_view(atoms, coords, clust_opt.no_hydrogen, clust_opt.reorder_alg,
-                                                       clust_opt.solute_natoms)
+    atoms, coords, noh, nsatoms, frame_z = frame_invariant_view(atoms, coords, clust_opt.no_hydrogen, clust_opt.reorder_alg,
+                                                                clust_opt.solute_natoms)
     opts = _opts_from(noh, clust_opt.reorder_alg, clust_opt.reorder_solvent_only, nsatoms, clust_opt.weight_solute,
                       clust_opt.reorder_excl, clust_opt.final_kabsch)
-    return condensed_matrix(atoms, coords, opts)
+    return condensed_matrix(atoms, coords, opts, frame_elements=frame_z)
 
 
 def compute_distmat_line(idx1, q_info, trajfile, noh, reorder, reorder_solvent_only, nsatoms, weight_solute,
@@ -253,9 +253,9 @@ def compute_distmat_line(idx1, q_info, trajfile, noh, reorder, reorder_solvent_o
         row_atoms = atoms if atoms.ndim == 1 else atoms[int(idx1)]
         if q_atoms.shape != row_atoms.shape or (q_atoms != row_atoms).any():
             raise ValueError("q_info atoms do not match the trajectory file")
-    atoms, coords, noh, nsatoms = frame_invariant_view(atoms, coords, noh, reorder, nsatoms)
+    atoms, coords, noh, nsatoms, frame_z = frame_invariant_view(atoms, coords, noh, reorder, nsatoms)
     opts = _opts_from(noh, reorder, reorder_solvent_only, nsatoms, weight_solute, reorderexcl, final_kabsch)
     eng = _engine_for(visible_devices()[0])
-    eng.load_frames(coords, atoms, opts)
+    eng.load_frames(coords, atoms, opts, frame_z)
     line, _ = eng.rmsd_rows(int(idx1), int(idx1) + 1)
     return [np.float64(x) for x in line]

@@ -80,6 +80,15 @@ int ct_host_free(void* ptr);
 int ct_load_frames(ct_engine* e, const double* coords, const int32_t* atomic_nums, int64_t M, int32_t N,
                    const ct_opts* opts);
 
+/* Per-frame element lists.  The reference reads every frame's own atoms (distmat.py:123-141) and builds the element blocks of
+ * a reorder from them per pair (rmsd.reorder_hungarian / reorder_distance over Qa[view], Pa[view]: distmat.py:192,243), so
+ * frames may list their atoms in different orders.  elements = [M][K] atomic numbers of the KEPT atoms of every frame of the
+ * last ct_load_frames (whose own atomic_nums then only describe frame 0); load the frames with no_hydrogen = 0 after applying
+ * each frame's own -n mask on the host (clusttraj_b200.distmat.frame_invariant_view).  Every frame must have the element
+ * counts of frame 0 among the atoms a phase reorders (the reference fails on a pair whose counts differ): CT_ERR_ARG
+ * otherwise.  Without a reorder the elements are not used and the call is a no-op. */
+int ct_set_frame_elements(ct_engine* e, const int32_t* elements, int64_t M, int32_t K);
+
 /* Re-run the centre/pack kernels (K1) on the coordinates already resident on the GPU (kernel-only
  * timing of the whole hot path without the host->device copy). */
 int ct_pack_resident(ct_engine* e, ct_stats* stats);

@@ -1086,9 +1086,11 @@ def test_per_frame_element_lists(tmp_path):
             line = D.compute_distmat_line(3, None, path, True, None, False, 6, None, none, False)
             want = oracle_rows(atoms2d, coords, [3], noh=True, ns=6)
             assert np.abs(np.asarray(line) - want).max() < 1e-8
-    # a reorder over element blocks that differ per frame is refused, not approximated
-    with pytest.raises(NotImplementedError):
-        D.compute_distmat_line(0, None, str(tmp_path / "a2.xyz"), False, reorder_hungarian, False, None, None, none, False)
+    # a reorder over frames whose element COUNTS differ has no defined result (the reference's per-element assignment
+    # fails on such a pair): refused by the engine
+    from clusttraj_b200._engine import EngineError
+    with pytest.raises(EngineError, match="element counts"):
+        D.compute_distmat_line(0, None, str(tmp_path / "a1.xyz"), False, reorder_hungarian, False, None, None, none, False)
     # ... frames with different numbers of kept atoms have no RMSD (the reference's Kabsch fails on the shapes)
     a4 = a1.copy()
     a4[5, np.where(a4[5] != 1)[0][0]] = 1
@@ -1096,6 +1098,53 @@ def test_per_frame_element_lists(tmp_path):
     write(path, a4)
     with pytest.raises(ValueError):
         D.compute_distmat_line(0, None, path, True, None, False, None, None, none, False)
+
+
+@pytest.mark.parametrize("mode", ["e", "ns_e", "ns_e_noh", "e_distance", "ns_rs_excl"])
+def test_reorder_with_per_frame_element_lists(tmp_path, mode):
+    """Frames that list the SAME atoms in different orders (reference distmat.py:131-141, 192, 243: the element blocks of a
+    reorder come from each frame's own atoms): ct_set_frame_elements gives every frame its own block index lists.  Values
+    and composite permutations against the oracle run on the per-frame lists."""
+    from clusttraj_b200 import _engine
+    from clusttraj_b200 import distmat as D
+    from clusttraj_b200.reorder import reorder_distance, reorder_hungarian
+    from clusttraj_b200.synth import make_solute_solvent
+
+    rng = np.random.default_rng(23)
+    ns = 9
+    atoms0, coords = make_solute_solvent(7, n_solute=ns, n_solvent_mol=8, seed=31, box=6.0)
+    M, N = coords.shape[:2]
+    atoms2d = np.tile(atoms0, (M, 1))
+    coords = coords.copy()
+    kw = {"e": dict(reorder=True), "ns_e": dict(reorder=True, ns=ns), "ns_e_noh": dict(reorder=True, ns=ns, noh=True),
+          "e_distance": dict(reorder="distance"), "ns_rs_excl": dict(reorder=True, ns=ns, rs=True, excl=(ns + 1, ns + 4))}[mode]
+    fixed = set(kw.get("excl", ()))   # excluded positions keep their atoms (exclusions are positional)
+    for m in range(1, M):   # shuffle the atom order inside the solute and inside the solvent, frame by frame
+        solv = np.array([k for k in range(ns, N) if k not in fixed])
+        p = np.arange(N)
+        p[:ns] = rng.permutation(ns)
+        p[solv] = rng.permutation(solv)
+        atoms2d[m] = atoms2d[m][p]
+        coords[m] = coords[m][p]
+    want = oracle_rows(atoms2d, coords, range(M), **kw)
+    handle = reorder_distance if kw["reorder"] == "distance" else reorder_hungarian
+    a, c, noh, nsat, fz = D.frame_invariant_view(atoms2d, coords, kw.get("noh", False), handle, kw.get("ns"))
+    assert fz is not None and fz.shape == (M, c.shape[1])
+    opts = D._opts_from(noh, handle, kw.get("rs", False), nsat, None, np.asarray(kw.get("excl", ()), np.int32), False)
+    got = D.condensed_matrix(a, c, opts, devices=[0], frame_elements=fz)
+    assert got.shape == want.shape and np.abs(got - want).max() < 1e-9, mode
+    # the permutations too (pair_values on the same engine state)
+    eng = _engine.Engine(0)
+    eng.load_frames(c, a, opts, fz)
+    pairs = [(0, 3), (2, 5), (1, 6), (4, 6)]
+    vals, perms, _ = eng.pair_values(np.asarray(pairs, dtype=np.int64), want_perms=True)
+    wv, wp = oracle_pairs(atoms2d, coords, pairs, **kw)
+    assert np.abs(vals - wv).max() < 1e-9
+    if mode != "ns_e_noh":   # (the oracle's permutation indexes the masked frame of each pair the same way)
+        assert (perms == wp).all()
+    else:
+        assert (perms == wp).all()
+    eng.close()
 
 
 def test_in_process_multi_gpu_slabs():

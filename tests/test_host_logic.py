@@ -577,20 +577,22 @@ def test_frame_invariant_view_of_per_frame_element_lists():
     rng = np.random.default_rng(3)
     coords = rng.normal(size=(3, 5, 3))
     same = np.array([[6, 1, 8, 1, 7]] * 3, dtype=np.int32)
-    a, c, noh, ns = frame_invariant_view(same, coords, True, None, 3)
-    assert a.tolist() == [6, 1, 8, 1, 7] and c is coords and noh is True and ns == 3      # nothing to do
+    a, c, noh, ns, fz = frame_invariant_view(same, coords, True, None, 3)
+    assert a.tolist() == [6, 1, 8, 1, 7] and c is coords and noh is True and ns == 3 and fz is None      # nothing to do
     # the hydrogens sit at different places, two kept solute atoms among the first three everywhere
     atoms = np.array([[6, 1, 8, 1, 7], [1, 6, 8, 7, 1], [6, 8, 1, 1, 7]], dtype=np.int32)
-    a, c, noh, ns = frame_invariant_view(atoms, coords, True, None, 3)
-    assert noh is False and ns == 2 and a.tolist() == [6, 8, 7] and c.shape == (3, 3, 3)
+    a, c, noh, ns, fz = frame_invariant_view(atoms, coords, True, None, 3)
+    assert noh is False and ns == 2 and a.tolist() == [6, 8, 7] and c.shape == (3, 3, 3) and fz is None
     assert np.array_equal(c[1], coords[1][[1, 2, 3]]) and np.array_equal(c[2], coords[2][[0, 1, 4]])
     # without -n nothing is masked: the elements only matter to a reorder
-    a, c, noh, ns = frame_invariant_view(atoms, coords, False, None, None)
-    assert noh is False and ns is None and c.shape == (3, 5, 3) and np.array_equal(c, coords)
-    with pytest.raises(NotImplementedError):
-        frame_invariant_view(atoms, coords, False, reorder_hungarian, None)     # element blocks differ per frame
-    a, c, noh, ns = frame_invariant_view(atoms, coords, True, reorder_hungarian, None)   # ... but not after the mask
-    assert a.tolist() == [6, 8, 7]
+    a, c, noh, ns, fz = frame_invariant_view(atoms, coords, False, None, None)
+    assert noh is False and ns is None and c.shape == (3, 5, 3) and np.array_equal(c, coords) and fz is None
+    # a reorder gets every frame's own list (the engine builds one set of block index lists per frame) ...
+    a, c, noh, ns, fz = frame_invariant_view(atoms, coords, False, reorder_hungarian, None)
+    assert fz is not None and fz.dtype == np.int32 and np.array_equal(fz, atoms) and a.tolist() == atoms[0].tolist()
+    # ... unless the kept elements agree after the mask
+    a, c, noh, ns, fz = frame_invariant_view(atoms, coords, True, reorder_hungarian, None)
+    assert a.tolist() == [6, 8, 7] and fz is None
     with pytest.raises(ValueError):
         frame_invariant_view(np.array([[6, 1, 8], [6, 8, 7]], dtype=np.int32), coords[:2, :3], True, None, None)
     with pytest.raises(NotImplementedError):   # -ns -n: the number of kept solute atoms changes from frame to frame
