@@ -28,5 +28,25 @@ for kw in (dict(reorder=True, solute_natoms=12), dict(reorder="distance", solute
     vals, perms, st = eng.pair_values(pairs, want_perms=True)
     v2, R, T = eng.pair_transforms(pairs)
     print("pairs", kw, float(vals.sum()), st["lsap_steps"])
+# per-frame element lists: the relabelling pre-pass of the per-pair kernel
+rng = np.random.default_rng(1)
+atoms2d = np.tile(atoms, (10, 1))
+shuf = coords.copy()
+for m in range(1, 10):
+    p = np.concatenate([rng.permutation(12), 12 + rng.permutation(len(atoms) - 12)])
+    atoms2d[m] = atoms2d[m][p]
+    shuf[m] = shuf[m][p]
+eng.load_frames(shuf, atoms2d[0], _engine.make_opts(reorder=True, solute_natoms=12), atoms2d)
+vals, perms, st = eng.pair_values(pairs, want_perms=True)
+print("per-frame lists", float(vals.sum()), st["lsap_steps"])
+# a larger solvent shell: the 8-column solver with the collision shortcut, and the K = 300 Gram shape
+atoms, coords = make_solute_solvent(8, n_solute=20, n_solvent_mol=70, seed=78, box=12.0)
+eng.load_frames(coords, atoms, _engine.make_opts(reorder=True, solute_natoms=20))
+_, n, st = eng.rmsd_rows_device(0, 8)
+print("shell", n, st["lsap_steps"])
+atoms, coords = make_trajectory(200, 300, seed=6)
+eng.load_frames(coords, atoms, _engine.make_opts())
+_, n, st = eng.rmsd_rows_device(0, 200)
+print("gram K=300", st["gram_path"], n)
 eng.close()
 print("done")
