@@ -614,6 +614,9 @@ static int rows_stream(ct_engine* e, int64_t row_begin, int64_t row_end, double*
     CT_CUDA(e, cudaEventRecord(e->ev_a, e->s_compute));
     int64_t written = 0;
     bool used[2] = {false, false};
+    const bool trace = getenv("CLUSTTRAJ_B200_TRACE_COPY") != nullptr;   // development: per-chunk copy timeline on stderr
+    std::vector<cudaEvent_t> tr_ev;
+    std::vector<int64_t> tr_n;
     for (size_t c = 0; c + 1 < cuts.size(); ++c) {
         const int b = (int)(c & 1);
         const int64_t cn = ct_rows_pairs(e->M, cuts[c], cuts[c + 1]);
@@ -629,8 +632,10 @@ static int rows_stream(ct_engine* e, int64_t row_begin, int64_t row_end, double*
         CT_CUDA(e, cudaEventRecord(e->ev_chunk_done[b], e->s_compute));
         if (out) {
             CT_CUDA(e, cudaStreamWaitEvent(e->s_copy, e->ev_chunk_done[b], 0));
+            if (trace) { cudaEvent_t ev; cudaEventCreate(&ev); cudaEventRecord(ev, e->s_copy); tr_ev.push_back(ev); }
             CT_CUDA(e, cudaMemcpyAsync(out + written, e->d_chunk[b], sizeof(double) * (size_t)cn, cudaMemcpyDeviceToHost,
                                        e->s_copy));
+            if (trace) { cudaEvent_t ev; cudaEventCreate(&ev); cudaEventRecord(ev, e->s_copy); tr_ev.push_back(ev); tr_n.push_back(cn); }
             CT_CUDA(e, cudaEventRecord(e->ev_copy_done[b], e->s_copy));
         }
         if (root) {
@@ -656,6 +661,16 @@ static int rows_stream(ct_engine* e, int64_t row_begin, int64_t row_end, double*
     CT_CUDA(e, cudaStreamSynchronize(e->s_copy));
     CT_CUDA(e, cudaStreamSynchronize(e->s_peer));
     float ms = 0.f;
+    if (trace) {
+        for (size_t c = 0; c < tr_n.size(); ++c) {
+            float t0 = 0.f, t1 = 0.f;
+            cudaEventElapsedTime(&t0, e->ev_a, tr_ev[2 * c]);
+            cudaEventElapsedTime(&t1, e->ev_a, tr_ev[2 * c + 1]);
+            fprintf(stderr, "copy %2zu: %9lld entries  start %8.3f ms  end %8.3f ms  %6.1f GB/s\n", c, (long long)tr_n[c], t0, t1,
+                    8e-6 * (double)tr_n[c] / (t1 - t0));
+        }
+        for (cudaEvent_t ev : tr_ev) cudaEventDestroy(ev);
+    }
     CT_CUDA(e, cudaEventElapsedTime(&ms, e->ev_a, e->ev_b));
     e->stats.kernel_ms = ms;  // compute stream busy time (includes waits for buffer reuse)
     e->stats.gram_ms = e->use_gram ? ms : 0.0; e->stats.pair_ms = e->use_gram ? 0.0 : ms;
