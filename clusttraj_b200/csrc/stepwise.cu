@@ -826,6 +826,7 @@ int pair_plan_build(PairPlanHost** out, const int32_t* kept_z, int K, int natoms
         for (int b = 0; b + 1 < (int)off[ph].size(); ++b) p.nmax = std::max(p.nmax, off[ph][b + 1] - off[ph][b]);
     }
     h->smem_per_warp = pair_smem_per_warp(p.nmax);
+    if (const char* pad = getenv("CLUSTTRAJ_B200_PAIR_SMEM_PAD")) h->smem_per_warp += atoi(pad) / 16 * 16;   // development: occupancy probe
     if ((size_t)h->smem_per_warp * PAIR_WARPS > 227 * 1024) {
         // fall back to fewer warps is not implemented; blocks beyond ~680 atoms per element do not fit
         delete h;
