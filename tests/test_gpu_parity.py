@@ -1147,6 +1147,49 @@ def test_reorder_with_per_frame_element_lists(tmp_path, mode):
     eng.close()
 
 
+@pytest.mark.parametrize("M", [1, 2, 3, 41, 81])
+def test_tiny_trajectories_and_empty_row_ranges(M):
+    """Edge sizes (a single frame has no pairs; 41 and 81 frames cross the 40-frame row tiles of the Gram kernels by one) and
+    empty / last-row ranges, on both Gram kernels and on the per-pair kernel, against the oracle."""
+    from clusttraj_b200 import _engine
+    from clusttraj_b200 import distmat as D
+    from clusttraj_b200.synth import make_solute_solvent, make_trajectory
+
+    atoms, coords = make_trajectory(max(M, 2), 17, seed=3)
+    atoms, coords = atoms, coords[:M]
+    total = M * (M - 1) // 2
+    want = oracle_rows(atoms, coords, range(M)) if M > 1 else np.empty(0)
+    for variant in (None, "-2"):
+        eng = _engine_with(variant)
+        eng.load_frames(coords, atoms, _engine.make_opts())
+        got, st = eng.rmsd_rows(0, M)
+        assert got.shape == (total,) and int(st["pairs"]) == total
+        if total:
+            assert np.abs(got - want).max() < 1e-6
+        # an empty range, and the last row (which owns no entries)
+        e0, _ = eng.rmsd_rows(0, 0)
+        e1, _ = eng.rmsd_rows(M - 1, M)
+        assert e0.size == 0 and e1.size == 0
+        if M > 2:   # a ragged range in the middle
+            mid, _ = eng.rmsd_rows(1, 2)
+            lo = condensed_index(M, 1, 2)
+            assert np.array_equal(mid, got[lo: lo + M - 2])
+        eng.close()
+    got = D.condensed_matrix(atoms, coords, _engine.make_opts(), devices=[0])
+    assert got.shape == (total,) and (total == 0 or np.abs(got - want).max() < 1e-6)
+    # the per-pair kernel (stepwise + Hungarian)
+    if M <= 41:
+        a2, c2 = make_solute_solvent(max(M, 2), n_solute=6, n_solvent_mol=5, seed=4, box=5.0)
+        c2 = c2[:M]
+        eng = _engine.Engine(0)
+        eng.load_frames(c2, a2, _engine.make_opts(solute_natoms=6, reorder=True))
+        got2, st2 = eng.rmsd_rows(0, M)
+        assert got2.shape == (total,)
+        if total:
+            assert np.abs(got2 - oracle_rows(a2, c2, range(M), reorder=True, ns=6)).max() < 1e-9
+        eng.close()
+
+
 def test_in_process_multi_gpu_slabs():
     """condensed_matrix(devices=[0, 1, ...]) — the in-process multi-GPU path the CLI uses (one engine + one host thread
     per GPU, equal-area row slabs): bit-identical to one GPU, and the whole matrix is left resident on the first GPU
