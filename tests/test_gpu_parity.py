@@ -1190,6 +1190,39 @@ def test_tiny_trajectories_and_empty_row_ranges(M):
         eng.close()
 
 
+def test_frame_elements_abi_argument_errors():
+    """ct_set_frame_elements through the binding: call order, shapes, the mask that must already be applied."""
+    from clusttraj_b200 import _engine
+    from clusttraj_b200.synth import make_solute_solvent
+
+    atoms, coords = make_solute_solvent(4, n_solute=6, n_solvent_mol=4, seed=9, box=5.0)
+    z2d = np.tile(atoms, (4, 1)).astype(np.int32)
+    eng = _engine.Engine(0)
+    rc = eng._lib.ct_set_frame_elements(eng._h, z2d.ctypes.data, 4, z2d.shape[1])
+    assert rc == -3                                   # CT_ERR_STATE: nothing loaded yet
+    eng.load_frames(coords, atoms, _engine.make_opts(reorder=True))
+    assert eng._lib.ct_set_frame_elements(eng._h, z2d.ctypes.data, 5, z2d.shape[1]) == -2     # CT_ERR_ARG: M
+    assert eng._lib.ct_set_frame_elements(eng._h, z2d.ctypes.data, 4, z2d.shape[1] - 1) == -2 # CT_ERR_ARG: K
+    assert eng._lib.ct_set_frame_elements(eng._h, None, 4, z2d.shape[1]) == -2
+    assert eng._lib.ct_set_frame_elements(eng._h, z2d.ctypes.data, 4, z2d.shape[1]) == 0
+    with pytest.raises(_engine.EngineError, match="per-frame element lists"):
+        eng.pair_transforms([(0, 1)])
+    # without a reorder the elements are not used: accepted, nothing changes
+    eng.load_frames(coords, atoms, _engine.make_opts())
+    a, _ = eng.rmsd_rows(0, 4)
+    assert eng._lib.ct_set_frame_elements(eng._h, z2d.ctypes.data, 4, z2d.shape[1]) == 0
+    b, _ = eng.rmsd_rows(0, 4)
+    assert np.array_equal(a, b)
+    # the engine's own mask and per-frame lists do not combine: the host applies the masks (frame_invariant_view)
+    eng.load_frames(coords, atoms, _engine.make_opts(reorder=True, no_hydrogen=True))
+    K = eng.K
+    zk = np.ascontiguousarray(np.tile(atoms[atoms != 1], (4, 1)), dtype=np.int32)
+    assert zk.shape[1] == K
+    with pytest.raises(_engine.EngineError, match="no_hydrogen"):
+        eng._check(eng._lib.ct_set_frame_elements(eng._h, zk.ctypes.data, 4, K), "ct_set_frame_elements")
+    eng.close()
+
+
 def test_in_process_multi_gpu_slabs():
     """condensed_matrix(devices=[0, 1, ...]) — the in-process multi-GPU path the CLI uses (one engine + one host thread
     per GPU, equal-area row slabs): bit-identical to one GPU, and the whole matrix is left resident on the first GPU
