@@ -14,6 +14,11 @@ path; the frame count grows with sqrt(N) so that every GPU keeps config 2's pair
   value : whole-job pairs/s with the coordinates already resident in HBM, output left in HBM.
   e2e   : the same through the C ABI with HOST buffers: pinned host coordinates -> GPU -> condensed slab
           streamed to pinned host memory, all inside the timed region.
+  roofline : against the pipe the dominant kernel runs on -- the algorithmic int8 work of the 15 exact digit GEMMs over the
+          measured tcgen05 int8 peak (`frac`; `issued_frac` with the padding of the MMA shape; `fp64_equiv` = 18 K flop per
+          pair over the measured DMMA peak); `shared_pipe` = how busy the pipe that the int8 MMAs and the FP64 unit share
+          is (tensor + FP64, from the committed ncu capture); `traffic` = DRAM bytes of that capture.  The per-pair
+          (Hungarian) kernel reports the HBM figure SURVEY 8d asks for plus `pipes` (FP64 pipe, issue slots, occupancy).
   parity: at EVERY N each rank checks sampled rows of its own slab (as they arrived in pinned host memory in the
           end-to-end leg) against the CPU oracle; the MAX over ranks is printed (tolerance of the north star: 1e-6 A).
   extra.workloads : the other BASELINE configs measured by the same run at the same N, each with value / e2e / roofline /
